@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- the AM-receiver chain of BASELINE.json (config 5) on N B200s, one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference            # the CPU path on the box's host cores
+
+A step is one pass of the hot path over one block: `channels` channels x 65536 complex64 samples at
+2 MS/s through ComplexIIRFilter(cheby2-8) -> ComplexResampler(0.024) -> AGC -> AmpModem(dsb, carrier)
+-> DeemphasisFilter, state carried from block to block.  Channels are independent, so each rank owns
+its own `channels` (weak scaling, no collective on the data path; torch.distributed only carries the
+barrier and the max-over-ranks of the device time).
+
+value   : whole-job input Msamples/s with the block already resident in HBM (CUDA events on the
+          launching stream, max over ranks).  Each block is >= 4 GB, far larger than the 126 MB L2.
+e2e     : the same metric through the C ABI's host-pointer entry (lqb_chain_execute): pinned host
+          input, H2D, kernels, D2H of the audio, all inside the timed region.
+roofline: the full-rate kernel seq[iir4+resamp] timed by its own events; algorithmic bytes per input
+          sample 8 (c64 in) + 0.024*8 (c64 out) = 8.192 (DESIGN.md "Roofline").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "python-liquiddsp_b200"))
+
+BLOCK = 65536
+FS, PCM = 2.0e6, 48.0e3
+METRIC = "AM-chain aggregate input Msamples/s"
+UNIT = "Msamples/s"
+
+
+# ------------------------------------------------------------------------------------- CPU arm
+def cpu_worker(seconds, seed):
+    """One channel of config 1 (README AMRadio, 64K blocks, state carried) on one core; prints samples/s."""
+    import numpy as np
+    from oracle import oracle as O
+    try:
+        os.sched_setaffinity(0, {seed % (os.cpu_count() or 1)})
+    except (AttributeError, OSError):
+        pass
+    rng = np.random.default_rng(0xB200 + seed)
+    t = np.arange(BLOCK * 8) / FS
+    a = 0.6 * np.sin(2 * np.pi * 1000 * t) + 0.4 * np.sin(2 * np.pi * 2500 * t)
+    x = 0.1 * (1 + 0.5 * a) * np.exp(1j * (2 * np.pi * (200 + 10 * (seed % 32)) * t)) + 0.05 * np.exp(2j * np.pi * 60e3 * t)
+    x = (x + 0.02 / np.sqrt(2) * (rng.standard_normal(t.size) + 1j * rng.standard_normal(t.size))).astype(np.complex64)
+    radio = O.AMRadio(15000, FS, PCM)
+    for b in range(2):
+        radio(x[b * BLOCK:(b + 1) * BLOCK])
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for b in range(8):
+            radio(x[b * BLOCK:(b + 1) * BLOCK]); n += BLOCK
+    dt = time.perf_counter() - t0
+    print(json.dumps({"samples": n, "seconds": dt}))
+
+
+def run_cpu_pool(seconds, procs):
+    """`procs` worker processes, one channel each; returns aggregate Msamples/s."""
+    ps = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", str(seconds), str(i)],
+                           stdout=subprocess.PIPE, text=True) for i in range(procs)]
+    tot = 0.0
+    for p in ps:
+        out, _ = p.communicate()
+        r = json.loads(out.strip().splitlines()[-1])
+        tot += r["samples"] / r["seconds"]
+    return tot / 1e6
+
+
+def cpu_kind():
+    return "port"      # oracle/_ref cannot exist: the reference's arithmetic is in liquid-dsp, absent here
+
+
+# ------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15); self.p.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+def build_radio(L, channels):
+    iir = L.ComplexIIRFilter(filter_type="cheby2", order=8, Fc=15000 / FS, channels=channels)
+    rs = L.ComplexResampler(rate=PCM / FS, Fc=PCM / FS, channels=channels)
+    agc = L.AGC(channels=channels); agc.lock = False; agc.scale = 0.01
+    am = L.AmpModem(modulation=0.5, type="dsb", carrier=True, channels=channels)
+    de = L.DeemphasisFilter(PCM, channels=channels)
+    return iir, rs, agc, am, de
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--channels", type=int, default=65536, help="channels per GPU (config 5: 65536)")
+    ap.add_argument("--e2e-channels", type=int, default=8192, help="channels per GPU of the host-buffer (e2e) leg")
+    ap.add_argument("--fuse", type=int, default=1, help="chain fusion level (0, 1, 2)")
+    ap.add_argument("--cpu-seconds", type=float, default=6.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-worker", nargs=2, metavar=("SECONDS", "SEED"))
+    args = ap.parse_args()
+
+    if args.cpu_worker:
+        cpu_worker(float(args.cpu_worker[0]), int(args.cpu_worker[1])); return
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = "config5: README AMRadio chain, %d channels/GPU x %d-sample blocks @ 2 MS/s, state carried" % (args.channels, BLOCK)
+
+    if args.impl == "reference":
+        # the reference's CPU implementation of the path, restated (liquid-dsp is absent): all host cores,
+        # one channel per process; a step is a bounded sample of the same workload
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        from oracle import oracle as O  # noqa: F401  (builds liboracle.so if missing)
+        for _ in range(min(args.warmup, 1)):
+            run_cpu_pool(1.0, cores)
+        secs = max(1.0, min(6.0, 60.0 / max(1, args.steps)))
+        vals = [run_cpu_pool(secs, cores) for _ in range(args.steps)]
+        v = sum(vals) / len(vals)
+        sample = "%d processes x 1 channel of config 1 (README AMRadio, 64K blocks), %.1f s per step" % (cores, secs)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_kind(), "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import liquiddsp as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local); L.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # CPU baseline first (rank 0, N = 1): separate processes, before the GPU is busy
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v = run_cpu_pool(args.cpu_seconds, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
+               "sample": "%d processes x 1 channel of config 1 (README AMRadio, 64K blocks) for %.0f s each; CPU restatement of liquid-dsp, not liquid-dsp" % (cores, args.cpu_seconds)}
+
+    C, n = args.channels, BLOCK
+    stream = torch.cuda.current_stream().cuda_stream
+    x = torch.empty((C, n), dtype=torch.complex64, device=dev)
+    stages = build_radio(L, C)
+    front, tail = L.Chain(stages[0], stages[1]), L.Chain(stages[2], stages[3], stages[4])
+    whole = L.Chain(*stages, fuse=args.fuse)
+    n_mid = front.out_len(n)
+    cap = n_mid + 2
+    mid = torch.empty((C, cap), dtype=torch.complex64, device=dev)
+    y = torch.empty((C, cap), dtype=torch.float32, device=dev)
+    L.synth_fill(0, x.data_ptr(), C, n, channel0=rank * C, n0=0, seed=0xB200, stream=stream)
+    torch.cuda.synchronize()
+
+    split = args.fuse == 1     # time the full-rate kernel on its own events when the plan has it as one launch
+
+    def step(ev=None):
+        if split:
+            if ev: ev[0].record()
+            k = front.execute_dev(x.data_ptr(), n, mid.data_ptr(), cap, stream)
+            if ev: ev[1].record()
+            tail.execute_dev(mid.data_ptr(), k, y.data_ptr(), cap, stream)
+            return 2
+        whole.execute_dev(x.data_ptr(), n, y.data_ptr(), cap, stream)
+        return whole.last_launches()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    barrier()
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for k in range(args.steps):
+        launches += step(evs[k])
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms_step = ms / args.steps
+    value = world * C * n / (ms_step * 1e-3) / 1e6
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    roof = None
+    if split:
+        kms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+        bytes_launch = C * n * 8 + C * n_mid * 8
+        ach = bytes_launch / (kms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        roof = {"bound": "hbm", "kernel": "seq_kernel<IIR|RS,4> (seq[iir4+resamp])", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "peak_source": peak_src, "traffic": traffic, "kernel_ms": kms,
+                "algorithmic_bytes_per_launch": bytes_launch, "share_of_step": kms / ms_step}
+
+    # end to end through the host-pointer C ABI: pinned host input -> H2D -> kernels -> D2H audio
+    e2e = None
+    if not args.no_e2e:
+        Ce = min(args.e2e_channels, C)
+        rs_e = build_radio(L, Ce)
+        ch_e = L.Chain(*rs_e, fuse=args.fuse)
+        xh = torch.empty((Ce, n), dtype=torch.complex64).pin_memory()
+        xh.copy_(x[:Ce].cpu())
+        xn = xh.numpy()
+        for _ in range(2):
+            yh = ch_e(xn)
+        barrier()
+        t0 = time.perf_counter()
+        reps = max(2, min(args.steps, 5))
+        for _ in range(reps):
+            yh = ch_e(xn)
+        L.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0) / reps
+        e2e = {"value": world * Ce * n / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(xn.nbytes), "d2h_bytes_per_step": int(yh.nbytes),
+               "channels_per_gpu": Ce, "ms_per_step": dt * 1e3, "api": "liquiddsp.Chain.__call__ -> lqb_chain_execute (host pointers)"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": {"workload": workload, "channels_per_gpu": C, "block": n, "fuse": args.fuse,
+                                               "plan": whole.plan() if not split else front.plan() + " -> " + tail.plan(),
+                                               "l2": "each block is %.1f GB of input, larger than L2; no flush needed" % (C * n * 8 / 1e9)},
+               "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+/*
+ * liquiddsp_b200.h -- C ABI of the B200-native streaming baseband chain.
+ *
+ * This is the drop-in boundary for the hot path of colbyAtCRI/python-liquiddsp.  The reference
+ * has no C ABI of its own: its boundary is the pybind11 class surface of src/wrapper.cpp, each
+ * class owning one liquid-dsp handle and calling liquid's create / destroy / reset /
+ * execute_block C functions.  Each family below replaces exactly that pairing and cites the
+ * reference wrapper (file:line under /root/reference/src) whose liquid calls it stands in for.
+ *
+ * Conventions
+ *   - every function returns an int status: LQB_OK (0) on success, a negative LQB_E* code
+ *     otherwise; nothing throws across the ABI.  lqb_last_error() gives the text.
+ *   - every object is batched: n_channels independent channels, each with its own carried
+ *     state, all sharing the object's parameters.  n_channels = 1 is the reference's object.
+ *   - sample buffers are dense row-major [n_channels x n] ; complex samples are interleaved
+ *     (re, im) float32 pairs == numpy complex64 == liquid_float_complex.
+ *   - *_execute()      : HOST pointers; the call does H2D, kernels, D2H and returns when done.
+ *     *_execute_dev()  : DEVICE pointers (16-byte aligned) + a cudaStream_t passed as void*;
+ *                        asynchronous, state stays resident in HBM between calls.
+ *   - there is no CPU fallback: without a CUDA device every execute returns LQB_ECUDA.
+ */
+#ifndef LIQUIDDSP_B200_H
+#define LIQUIDDSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQB_OK        0
+#define LQB_EINVAL   -1   /* bad argument / unsupported configuration                 */
+#define LQB_ECUDA    -2   /* CUDA runtime error (no device, launch failure, ...)       */
+#define LQB_ENOMEM   -3
+#define LQB_ESIZE    -4   /* output capacity too small                                 */
+#define LQB_ENOTIMPL -5   /* reference feature outside the built scope (named in text) */
+
+typedef struct { float re, im; } lqb_cf;          /* complex64 */
+typedef struct lqb_stage_s *lqb_stage;            /* any stage object below */
+typedef struct lqb_chain_s *lqb_chain;
+
+/* enum values follow liquid.h */
+enum { LQB_IIRDES_BUTTER = 0, LQB_IIRDES_CHEBY1, LQB_IIRDES_CHEBY2, LQB_IIRDES_ELLIP, LQB_IIRDES_BESSEL };
+enum { LQB_IIRDES_LOWPASS = 0, LQB_IIRDES_HIGHPASS, LQB_IIRDES_BANDPASS, LQB_IIRDES_BANDSTOP };
+enum { LQB_NCO = 0, LQB_VCO };
+enum { LQB_AMPMODEM_DSB = 0, LQB_AMPMODEM_USB, LQB_AMPMODEM_LSB };
+enum { LQB_MIX_UP = 1, LQB_MIX_DOWN = 2 };
+
+/* ---------------- library ---------------- */
+int         lqb_version(void);
+const char *lqb_last_error(void);                      /* thread-local text of the last failure */
+int         lqb_device_count(int *count);
+int         lqb_set_device(int device);                /* objects are created on the current device */
+int         lqb_device_synchronize(void);
+/* pinned host memory and raw device memory, so callers without another CUDA binding can stage data */
+int         lqb_host_alloc(void **p, size_t bytes);
+int         lqb_host_free(void *p);
+int         lqb_dev_alloc(void **p, size_t bytes);
+int         lqb_dev_free(void *p);
+int         lqb_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int         lqb_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int         lqb_stream_synchronize(void *stream);
+
+/* ---------------- generic stage operations (valid for every stage handle) ---------------- */
+int lqb_stage_destroy(lqb_stage s);
+int lqb_stage_reset(lqb_stage s);                       /* liquid *_reset(): clears carried state */
+int lqb_stage_channels(lqb_stage s, int *n_channels);
+/* output length for n input samples per channel, given the current carried state */
+int lqb_stage_out_len(lqb_stage s, size_t n, size_t *n_out);
+/* Host-pointer execute. x: [n_channels x n] of the stage's input type; y: [n_channels x *n_out].
+ * y_capacity is in samples per channel. */
+int lqb_stage_execute(lqb_stage s, const void *x, size_t n, void *y, size_t y_capacity, size_t *n_out);
+int lqb_stage_execute_dev(lqb_stage s, const void *x_dev, size_t n, void *y_dev, size_t y_capacity,
+                          size_t *n_out, void *stream);
+
+/* ---------------- iirfilt_crcf : ComplexIIRFilter, iirfilter.hpp:244-299 ----------------
+ * replaces iirfilt_crcf_create_prototype (:275), iirfilt_crcf_execute_block (:296),
+ * iirfilt_crcf_freqresponse (:288), iirfilt_crcf_destroy (:279).  complex in -> complex out. */
+int lqb_iirfilt_crcf_create_prototype(int ftype, int btype, int order, float fc, float f0,
+                                      float ap, float as, int n_channels, lqb_stage *out);
+int lqb_iirfilt_crcf_create_sos(const float *B, const float *A, int nsos, int n_channels, lqb_stage *out);
+int lqb_iirfilt_crcf_get_sos(lqb_stage s, float *B, float *A, int *nsos);   /* 3 floats per section */
+int lqb_iirfilt_crcf_freqresponse(lqb_stage s, float fc, lqb_cf *H);
+/* 0 = auto, 1 = channel-parallel sequential (bit-matches the oracle), 2 = time-parallel blocked scan */
+int lqb_iirfilt_crcf_set_mode(lqb_stage s, int mode);
+
+/* ---------------- iirfilt_rrrf one-pole : DeemphasisFilter, iirfilter.hpp:358-392 ----------
+ * replaces iirfilt_rrrf_create(b,1,a,2) (:371) and the per-sample iirfilt_rrrf_execute loop
+ * (:388-389); coefficient formula of :366-370.  real in -> real out. */
+int lqb_deemph_create(float sample_rate, int n_channels, lqb_stage *out);
+int lqb_deemph_get_coeffs(lqb_stage s, float *b0, float *a1);
+int lqb_deemph_freqresponse(lqb_stage s, float fc, lqb_cf *H);
+
+/* ---------------- firfilt_crcf : new FIRFilter class (BASELINE config 2) -------------------
+ * modelled on RealFIRFilter, firfilter.hpp:5-36 (firfilt_rrrf_create :15, _execute_block :33,
+ * _freqresponse :27); the crcf form is what demod.hpp:105,135-136 uses.  complex -> complex. */
+int lqb_firfilt_crcf_create(const float *h, int h_len, int n_channels, lqb_stage *out);
+int lqb_firfilt_crcf_create_kaiser(int h_len, float fc, float as, float mu, int n_channels, lqb_stage *out);
+int lqb_firfilt_crcf_set_scale(lqb_stage s, float scale);
+int lqb_firfilt_crcf_get_taps(lqb_stage s, float *h, int *h_len);
+int lqb_firfilt_crcf_freqresponse(lqb_stage s, float fc, lqb_cf *H);
+
+/* ---------------- resamp_cccf : ComplexResampler, resampler.hpp:127-173 ---------------------
+ * replaces resamp_cccf_create (:136), _reset (:144), _set_rate (:153) and the per-sample
+ * resamp_cccf_execute loop (:164-166).  complex in -> complex out, *n_out samples per channel
+ * (all channels share rate and phase, so the batched output is rectangular). */
+int lqb_resamp_create(float rate, int m, float fc, float as, int npfb, int n_channels, lqb_stage *out);
+int lqb_resamp_set_rate(lqb_stage s, float rate);
+int lqb_resamp_get_state(lqb_stage s, uint32_t *step, uint32_t *phase);     /* 8.24 fixed point */
+int lqb_resamp_get_bank(lqb_stage s, float *bank, int *npfb, int *sublen);  /* [npfb][sublen] as firpfb stores it */
+
+/* ---------------- nco_crcf : NCO, nco.hpp:10-81 ---------------------------------------------
+ * replaces nco_crcf_create (:18,22), set/adjust frequency and phase (:34-52), pll (:54-60) and
+ * nco_crcf_mix_block_up/down (:70,78).  Phase/frequency are uint32 and bit-exact.  Per-channel
+ * frequency/phase arrays are an extension for the batched form. */
+int lqb_nco_create(int type, int n_channels, lqb_stage *out);
+int lqb_nco_set_direction(lqb_stage s, int dir);                 /* LQB_MIX_UP (default, __call__) / LQB_MIX_DOWN */
+int lqb_nco_set_frequency(lqb_stage s, float f);                 /* radians/sample, all channels */
+int lqb_nco_adjust_frequency(lqb_stage s, float df);
+int lqb_nco_set_phase(lqb_stage s, float phi);
+int lqb_nco_adjust_phase(lqb_stage s, float dphi);
+int lqb_nco_get_frequency(lqb_stage s, float *f);                /* channel 0 */
+int lqb_nco_get_phase(lqb_stage s, float *phi);
+int lqb_nco_pll_set_bandwidth(lqb_stage s, float bw);
+int lqb_nco_pll_step(lqb_stage s, float dphi);
+int lqb_nco_set_frequency_per_channel(lqb_stage s, const float *f, int n);
+int lqb_nco_get_u32(lqb_stage s, uint32_t *theta, uint32_t *d_theta, int n);   /* per channel */
+int lqb_nco_set_u32(lqb_stage s, const uint32_t *theta, const uint32_t *d_theta, int n);
+
+/* ---------------- agc_crcf : AGC, agc.hpp:4-128 ---------------------------------------------
+ * replaces agc_crcf_create (:10) and every property call (:17-107), plus the wrapper's own loop
+ * (:109-128): per-sample agc_crcf_execute, squelch status poll, zeroing in ENABLED/SIGNALLO and
+ * the count of RISE transitions (the host then calls onRise that many times). */
+int lqb_agc_create(int n_channels, lqb_stage *out);
+int lqb_agc_set_bandwidth(lqb_stage s, float bw);
+int lqb_agc_get_bandwidth(lqb_stage s, float *bw);
+int lqb_agc_set_signal_level(lqb_stage s, float level);
+int lqb_agc_get_signal_level(lqb_stage s, float *level);         /* channel 0 */
+int lqb_agc_set_rssi(lqb_stage s, float rssi_dB);
+int lqb_agc_get_rssi(lqb_stage s, float *rssi_dB);               /* channel 0 */
+int lqb_agc_set_gain(lqb_stage s, float gain);
+int lqb_agc_get_gain(lqb_stage s, float *gain);                  /* channel 0 */
+int lqb_agc_get_gain_per_channel(lqb_stage s, float *gain, int n);
+int lqb_agc_set_scale(lqb_stage s, float scale);
+int lqb_agc_get_scale(lqb_stage s, float *scale);
+int lqb_agc_lock(lqb_stage s, int locked);
+int lqb_agc_squelch_enable(lqb_stage s, int enabled);
+int lqb_agc_squelch_set_threshold(lqb_stage s, float threshold_dB);
+int lqb_agc_squelch_get_threshold(lqb_stage s, float *threshold_dB);
+int lqb_agc_squelch_set_timeout(lqb_stage s, unsigned timeout);
+int lqb_agc_squelch_get_status(lqb_stage s, int *status);        /* channel 0, enum 0..7 of agc_docs.cpp:57-64 */
+int lqb_agc_take_rise_count(lqb_stage s, unsigned *count);       /* RISE transitions since last take, all channels */
+
+/* ---------------- ampmodem : AmpModem, demod.hpp:228-307 ------------------------------------
+ * replaces ampmodem_create(mod, type, suppressed) (:305), ampmodem_demodulate_block (:294),
+ * ampmodem_reset (:287).  complex in -> real out.  Built scope: DSB, carrier present (PLL) and
+ * suppressed (Costas); USB/LSB return LQB_ENOTIMPL. */
+int lqb_ampmodem_create(float mod_index, int type, int suppressed_carrier, int n_channels, lqb_stage *out);
+int lqb_ampmodem_get_taps(lqb_stage s, float *lowpass, int *n_lowpass, float *dcblock, int *n_dcblock);
+int lqb_ampmodem_get_nco_u32(lqb_stage s, uint32_t *theta, uint32_t *d_theta, int n);
+
+/* ---------------- freqdem : FreqDem, demod.hpp:189-219 --------------------------------------
+ * replaces freqdem_create (:197), freqdem_demodulate_block (:216), freqdem_reset (:205). */
+int lqb_freqdem_create(float kf, int n_channels, lqb_stage *out);
+
+/* ---------------- fused chain ---------------------------------------------------------------
+ * The reference composes stages in Python, one ndarray round trip per stage (README.md:53-54).
+ * A chain borrows stage handles (it does not own them; their carried state is the chain's state)
+ * and runs them as fused kernels with no HBM round trip between fused stages. */
+int lqb_chain_create(lqb_chain *out);
+int lqb_chain_append(lqb_chain c, lqb_stage s);
+int lqb_chain_destroy(lqb_chain c);
+int lqb_chain_out_len(lqb_chain c, size_t n, size_t *n_out);
+int lqb_chain_execute(lqb_chain c, const void *x, size_t n, void *y, size_t y_capacity, size_t *n_out);
+int lqb_chain_execute_dev(lqb_chain c, const void *x_dev, size_t n, void *y_dev, size_t y_capacity,
+                          size_t *n_out, void *stream);
+/* human-readable launch plan ("seq[iir4+resamp] -> seq[agc+am+deemph]") and the number of kernel
+ * launches the last execute issued */
+int lqb_chain_plan(lqb_chain c, char *buf, size_t buf_len);
+int lqb_chain_last_launches(lqb_chain c, int *n_launches);
+/* 0 = one kernel per stage, 1 = default (full-rate front and decimated tail as two kernels),
+ * 2 = longest possible runs (whole AM receiver in one kernel); results are identical */
+int lqb_chain_set_fusion(lqb_chain c, int level);
+
+/* ---------------- synthetic input generators, device side -----------------------
+ * Fill x_dev [n_channels x n] with the benchmark signal for blocks starting at absolute sample
+ * index n0.  kind: 0 = AM IQ (configs 1, 5), 1 = complex Gaussian (config 2), 2 = tone+noise
+ * (config 3), 3 = FM IQ with amplitude ramp (config 4). */
+int lqb_synth_fill(int kind, void *x_dev, int n_channels, int channel0, size_t n, uint64_t n0,
+                   uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

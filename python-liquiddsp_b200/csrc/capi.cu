@@ -1,0 +1,880 @@
+// capi.cu -- the C ABI of include/liquiddsp_b200.h: stage handles, carried state in HBM, the chain
+// planner and the host / device execute paths.
+//
+// This file is what the reference's L2 layer (one C++ class per liquid object, src/*.hpp) becomes:
+// each handle owns device state arrays instead of a liquid handle, `execute` launches kernels
+// instead of calling liquid's per-sample loops, and there is no CPU path -- without a CUDA device
+// every execute fails with LQB_ECUDA.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/liquiddsp_b200.h"
+#include "design.hpp"
+#include "params.h"
+#include "seq.h"
+#include "fir.h"
+#include "par.h"
+#include "synth.h"
+
+namespace lqb {
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define LQB_CUDA(call)                                                                              \
+    do { cudaError_t e_ = (call);                                                                   \
+         if (e_ != cudaSuccess) return ::lqb::fail(LQB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define LQB_TRY(call) do { int rc_ = (call); if (rc_ != LQB_OK) return rc_; } while (0)
+
+// ------------------------------------------------------------------------------------ device arrays
+template <class T> struct DevArr {
+    T *p = nullptr; size_t n = 0;
+    DevArr() {}
+    DevArr(const DevArr &) = delete; DevArr &operator=(const DevArr &) = delete;
+    ~DevArr() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    int alloc(size_t count)
+    {
+        release();
+        if (count == 0) return LQB_OK;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LQB_ENOMEM : LQB_ECUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+        n = count;
+        return zero();
+    }
+    int reserve(size_t count) { return count <= n ? LQB_OK : alloc(count); }
+    int zero() { if (p) LQB_CUDA(cudaMemset(p, 0, n * sizeof(T))); return LQB_OK; }
+    int fill(const T &v)
+    {
+        if (!p) return LQB_OK;
+        std::vector<T> h(n, v);
+        LQB_CUDA(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+        return LQB_OK;
+    }
+    int upload(const T *h, size_t count) { LQB_CUDA(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice)); return LQB_OK; }
+    int download(T *h, size_t count) const { LQB_CUDA(cudaMemcpy(h, p, count * sizeof(T), cudaMemcpyDeviceToHost)); return LQB_OK; }
+};
+
+// the oscillator's 1024-entry (sin, cos) table, one copy per device
+static std::mutex g_tab_mu;
+static std::map<int, float2 *> g_sincos;
+static int sincos_table(const float2 **out)
+{
+    int dev = 0; LQB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    auto it = g_sincos.find(dev);
+    if (it == g_sincos.end()) {
+        std::vector<float> s = design::nco_sintab();
+        std::vector<float2> t(1024);
+        for (int i = 0; i < 1024; i++) t[i] = make_float2(s[i], s[(i + 256) & 0x3ff]);
+        float2 *d = nullptr;
+        LQB_CUDA(cudaMalloc((void **)&d, 1024 * sizeof(float2)));
+        LQB_CUDA(cudaMemcpy(d, t.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
+        it = g_sincos.emplace(dev, d).first;
+    }
+    *out = it->second;
+    return LQB_OK;
+}
+
+// ------------------------------------------------------------------------------------ stages
+enum Kind { K_NCO = 0, K_IIR, K_RESAMP, K_AGC, K_AM, K_FM, K_DEEMPH, K_FIR };
+
+}  // namespace lqb
+
+struct lqb_chain_s;
+
+struct lqb_stage_s {
+    lqb::Kind kind; int C = 1; int device = 0;
+    lqb_chain_s *self_chain = nullptr;         // one-stage chain used by lqb_stage_execute*
+    bool ready = false;                        // device state allocated (first execute / state access)
+    lqb_stage_s(lqb::Kind k, int c) : kind(k), C(c) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    virtual ~lqb_stage_s();
+    virtual int materialize() = 0;             // allocate and initialise the carried state in HBM
+    virtual int clear() = 0;                   // liquid *_reset() on materialised state
+    int ensure() { LQB_TRY(bind()); if (!ready) { LQB_TRY(materialize()); ready = true; } return LQB_OK; }
+    virtual int reset() { host_reset(); if (!ready) return LQB_OK; LQB_TRY(bind()); LQB_CUDA(cudaDeviceSynchronize()); return clear(); }
+    virtual void host_reset() {}
+    virtual bool in_real() const { return false; }
+    virtual bool out_real() const { return false; }
+    virtual size_t out_len(size_t n) const { return n; }
+    virtual void advance(size_t n) { (void)n; }    // host bookkeeping after n samples per channel
+    int bind() const
+    {
+        cudaError_t e = cudaSetDevice(device);
+        return e == cudaSuccess ? LQB_OK : lqb::fail(LQB_ECUDA, "cudaSetDevice(%d): %s -- this library has no CPU path", device, cudaGetErrorString(e));
+    }
+};
+
+namespace lqb {
+
+struct IirStage : lqb_stage_s {
+    std::vector<float> B, A; int nsos = 0, mode = 0;
+    DevArr<float2> v;                                   // [nsos][2][C]
+    IirStage(int c) : lqb_stage_s(K_IIR, c) {}
+    int init(const std::vector<float> &b, const std::vector<float> &a)
+    {
+        nsos = (int)b.size() / 3; B.resize(3 * nsos); A.resize(3 * nsos);
+        for (int s = 0; s < nsos; s++) {               // iirfiltsos_create normalises by a0
+            const float a0 = a[3 * s];
+            for (int k = 0; k < 3; k++) { B[3 * s + k] = b[3 * s + k] / a0; A[3 * s + k] = a[3 * s + k] / a0; }
+        }
+        return LQB_OK;
+    }
+    int materialize() override { return v.alloc((size_t)nsos * 2 * C); }
+    int clear() override { return v.zero(); }
+    void fill(IirP &p, int s0, int ns) const
+    {
+        p.nsos = ns;
+        for (int s = 0; s < ns; s++) for (int k = 0; k < 3; k++) { p.b[s][k] = B[3 * (s0 + s) + k]; p.a[s][k] = A[3 * (s0 + s) + k]; }
+        p.v = v.p + (size_t)s0 * 2 * C;
+    }
+};
+
+struct DeemphStage : lqb_stage_s {
+    float b0 = 0, a1 = 0; DevArr<float> v1;
+    DeemphStage(int c) : lqb_stage_s(K_DEEMPH, c) {}
+    int materialize() override { return v1.alloc(C); }
+    int clear() override { return v1.zero(); }
+    bool in_real() const override { return true; }
+    bool out_real() const override { return true; }
+    void fill(DeP &p) const { p.b0 = b0; p.a1 = a1; p.v1 = v1.p; }
+};
+
+struct FirStage : lqb_stage_s {
+    std::vector<float> h; float scale = 1.f; DevArr<float> taps; DevArr<float2> hist[2]; int cur = 0;
+    FirStage(int c) : lqb_stage_s(K_FIR, c) {}
+    int materialize() override
+    {
+        LQB_TRY(taps.alloc(h.size())); LQB_TRY(taps.upload(h.data(), h.size()));
+        for (int k = 0; k < 2; k++) LQB_TRY(hist[k].alloc((size_t)std::max<size_t>(1, h.size() - 1) * C));
+        return LQB_OK;
+    }
+    int clear() override { LQB_TRY(hist[0].zero()); return hist[1].zero(); }
+    void advance(size_t n) override { if (n) cur ^= 1; }
+};
+
+struct ResampStage : lqb_stage_s {
+    float rate = 1.f; design::ResampDesign d; uint32_t step = 0, phase = 0, count = 0;
+    DevArr<float> bank; DevArr<float2> ring;            // ring [sublen][C]
+    ResampStage(int c) : lqb_stage_s(K_RESAMP, c) {}
+    int materialize() override
+    {
+        LQB_TRY(bank.alloc(d.bank.size())); LQB_TRY(bank.upload(d.bank.data(), d.bank.size()));
+        return ring.alloc((size_t)d.sublen * C);
+    }
+    void host_reset() override { phase = 0; count = 0; }
+    int clear() override { return ring.zero(); }
+    bool decimating() const { return (uint64_t)step >= ((uint64_t)d.sublen << 24) && d.sublen <= (unsigned)kMaxResampSub; }
+    size_t out_len(size_t n) const override
+    {
+        const uint64_t lim = ((uint64_t)n << 24);           // outputs while phase + k*step <= n*2^24 - 1
+        if (n == 0 || (uint64_t)phase > lim - 1) return 0;
+        return (size_t)((lim - 1 - phase) / step + 1);
+    }
+    void advance(size_t n) override
+    {
+        const uint64_t k = out_len(n);
+        phase = (uint32_t)((uint64_t)phase + k * step - ((uint64_t)n << 24));
+        count = (uint32_t)((count + n) % d.sublen);
+    }
+    void fill(ResampP &p) const
+    {
+        p.step = step; p.phase = phase; p.bits = (int)d.bits; p.sublen = (int)d.sublen; p.npfb = (int)d.npfb;
+        p.bank = bank.p; p.ring = ring.p; p.count = count;
+    }
+};
+
+struct NcoStage : lqb_stage_s {
+    int type = 0, dir = LQB_MIX_UP; float alpha = 0.1f, beta = 0.f;
+    DevArr<uint32_t> theta, dtheta;
+    NcoStage(int c) : lqb_stage_s(K_NCO, c) { beta = std::sqrt(alpha); }
+    int materialize() override { LQB_TRY(theta.alloc(C)); return dtheta.alloc(C); }
+    int clear() override { LQB_TRY(theta.zero()); return dtheta.zero(); }
+    int fill(NcoP &p) const
+    {
+        p.theta = theta.p; p.dtheta = dtheta.p; p.type = type; p.dir = dir;
+        return sincos_table(&p.sincos);
+    }
+    int rmw(DevArr<uint32_t> &arr, uint32_t add, bool set)
+    {
+        LQB_TRY(ensure());
+        LQB_CUDA(cudaDeviceSynchronize());
+        if (set) return arr.fill(add);
+        std::vector<uint32_t> h(C);
+        LQB_TRY(arr.download(h.data(), C));
+        for (auto &x : h) x += add;
+        return arr.upload(h.data(), C);
+    }
+};
+
+struct AgcStage : lqb_stage_s {
+    float alpha = 1e-2f, scale = 1.f, threshold = 0.f; int locked = 0; bool squelch = false; unsigned timeout = 100;
+    DevArr<float> g, y2p; DevArr<int> mode; DevArr<unsigned> timer, rise;
+    AgcStage(int c) : lqb_stage_s(K_AGC, c) {}
+    int materialize() override
+    {
+        LQB_TRY(g.alloc(C)); LQB_TRY(y2p.alloc(C)); LQB_TRY(mode.alloc(C)); LQB_TRY(timer.alloc(C)); LQB_TRY(rise.alloc(1));
+        LQB_TRY(timer.fill(timeout));
+        return clear();
+    }
+    void host_reset() override { locked = 0; }
+    int clear() override
+    {
+        LQB_TRY(g.fill(1.0f)); LQB_TRY(y2p.fill(1.0f));
+        return mode.fill(squelch ? 1 : 7);
+    }
+    void fill(AgcP &p) const
+    {
+        p.alpha = alpha; p.scale = scale; p.threshold = threshold; p.one_minus_alpha = 1.0 - (double)alpha;
+        p.locked = locked; p.timeout = timeout; p.g = g.p; p.y2p = y2p.p; p.mode = mode.p; p.timer = timer.p;
+        p.rise_count = rise.p;
+    }
+};
+
+struct AmStage : lqb_stage_s {
+    float mod = 0.75f; int type = 0, suppressed = 1; std::vector<float> lp, dc; uint32_t count = 0;
+    DevArr<float2> lp_ring; DevArr<float> dc_ring; DevArr<uint32_t> theta, dtheta;
+    AmStage(int c) : lqb_stage_s(K_AM, c) {}
+    int materialize() override
+    {
+        LQB_TRY(lp_ring.alloc((size_t)kAmRing * C)); LQB_TRY(dc_ring.alloc((size_t)kAmRing * C));
+        LQB_TRY(theta.alloc(C)); return dtheta.alloc(C);
+    }
+    void host_reset() override { count = 0; }
+    int clear() override { LQB_TRY(lp_ring.zero()); LQB_TRY(dc_ring.zero()); LQB_TRY(theta.zero()); return dtheta.zero(); }
+    bool out_real() const override { return true; }
+    void advance(size_t n) override { count = (uint32_t)((count + n) % kAmRing); }
+    int fill(AmP &p) const
+    {
+        p.mod_index = mod; p.pll_alpha = 0.001f; p.pll_beta = std::sqrt(0.001f); p.suppressed = suppressed;
+        for (int i = 0; i < kAmTaps; i++) { p.lp[i] = lp[kAmTaps - 1 - i]; p.dc[i] = dc[kAmTaps - 1 - i]; }
+        p.lp_ring = lp_ring.p; p.dc_ring = dc_ring.p; p.theta = theta.p; p.dtheta = dtheta.p; p.count = count;
+        return sincos_table(&p.sincos);
+    }
+};
+
+struct FmStage : lqb_stage_s {
+    float kf = 0.1f, ref = 0.f; DevArr<float2> rprime;
+    FmStage(int c) : lqb_stage_s(K_FM, c) {}
+    int materialize() override { return rprime.alloc(C); }
+    int clear() override { return rprime.zero(); }
+    bool out_real() const override { return true; }
+    void fill(FmP &p) const { p.ref = ref; p.rprime = rprime.p; }
+};
+
+// ------------------------------------------------------------------------------------ chain
+struct Segment {
+    enum Type { SEQ, FIR, RESAMP_PAR } type = SEQ;
+    unsigned mask = 0; int nsos = 0, sos0 = 0;
+    std::vector<lqb_stage_s *> st;
+    std::string name;
+};
+
+}  // namespace lqb
+
+struct lqb_chain_s {
+    std::vector<lqb_stage_s *> stages;
+    int fuse = 1;                              // 0 one kernel per stage, 1 front/tail split, 2 longest runs
+    int last_launches = 0;
+    std::string plan;
+    // host-execute resources: per-stream input/output staging and ping-pong scratch
+    static constexpr int kStreams = 3;
+    cudaStream_t streams[kStreams] = { nullptr, nullptr, nullptr };
+    lqb::DevArr<char> h_in[kStreams], h_out[kStreams], h_tmp[kStreams][2];
+    // device-execute scratch
+    lqb::DevArr<char> d_tmp[2];
+    ~lqb_chain_s() { for (auto &s : streams) if (s) cudaStreamDestroy(s); }
+};
+
+lqb_stage_s::~lqb_stage_s() { delete self_chain; }
+
+namespace lqb {
+
+static const char *kind_name(Kind k)
+{
+    switch (k) {
+    case K_NCO: return "nco"; case K_IIR: return "iir"; case K_RESAMP: return "resamp"; case K_AGC: return "agc";
+    case K_AM: return "ampmodem"; case K_FM: return "freqdem"; case K_DEEMPH: return "deemph"; case K_FIR: return "fir";
+    }
+    return "?";
+}
+static unsigned kind_flag(Kind k)
+{
+    switch (k) {
+    case K_NCO: return F_NCO; case K_IIR: return F_IIR; case K_RESAMP: return F_RS; case K_AGC: return F_AGC;
+    case K_AM: return F_AM; case K_FM: return F_FM; case K_DEEMPH: return F_DE; default: return 0;
+    }
+}
+// position in the order the sequential kernel applies its stages
+static int kind_rank(Kind k)
+{
+    switch (k) { case K_NCO: return 0; case K_IIR: return 1; case K_RESAMP: return 2; case K_AGC: return 3;
+                 case K_AM: case K_FM: return 4; case K_DEEMPH: return 5; default: return 99; }
+}
+
+static unsigned run_mask(const std::vector<lqb_stage_s *> &st, size_t i0, size_t len, int *nsos)
+{
+    unsigned m = 0; *nsos = 0;
+    for (size_t i = i0; i < i0 + len; i++) {
+        m |= kind_flag(st[i]->kind);
+        if (st[i]->kind == K_IIR) *nsos = static_cast<IirStage *>(st[i])->nsos;
+    }
+    if (st[i0]->in_real()) m |= F_INREAL;
+    return m;
+}
+
+static bool run_fusable(const std::vector<lqb_stage_s *> &st, size_t i0, size_t len, int level)
+{
+    int prev = -1; bool has_rs = false, has_am = false;
+    for (size_t i = i0; i < i0 + len; i++) {
+        const lqb_stage_s *s = st[i];
+        const int r = kind_rank(s->kind);
+        if (r <= prev || r == 99) return false;
+        prev = r;
+        if (s->kind == K_RESAMP && !static_cast<const ResampStage *>(s)->decimating()) return false;
+        if (s->kind == K_IIR && static_cast<const IirStage *>(s)->mode == 2) return false;
+        has_rs |= s->kind == K_RESAMP; has_am |= s->kind == K_AM;
+    }
+    // level 1 keeps the ampmodem's shared-memory windows out of the full-rate kernel: they would cut
+    // its occupancy four-fold, while the decimated hand-off they avoid is 2.4 % of the traffic
+    if (level < 2 && has_rs && has_am) return false;
+    int nsos; const unsigned m = run_mask(st, i0, len, &nsos);
+    return seq_supported(m, nsos);
+}
+
+static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
+{
+    const auto &st = c->stages;
+    segs.clear();
+    for (size_t i = 0; i < st.size();) {
+        Segment g;
+        if (st[i]->kind == K_FIR) { g.type = Segment::FIR; g.st = { st[i] }; g.name = "fir"; segs.push_back(g); i++; continue; }
+        size_t best = 1;
+        if (c->fuse) for (size_t len = std::min<size_t>(6, st.size() - i); len >= 2; len--) if (run_fusable(st, i, len, c->fuse)) { best = len; break; }
+        if (best == 1) {
+            if (st[i]->kind == K_RESAMP && !static_cast<ResampStage *>(st[i])->decimating()) {
+                g.type = Segment::RESAMP_PAR; g.st = { st[i] }; g.name = "par[resamp]"; segs.push_back(g); i++; continue;
+            }
+            if (st[i]->kind == K_IIR) {              // long cascades: kMaxSos sections per launch
+                IirStage *q = static_cast<IirStage *>(st[i]);
+                for (int s0 = 0; s0 < q->nsos; s0 += kMaxSos) {
+                    Segment h; h.type = Segment::SEQ; h.mask = F_IIR; h.sos0 = s0; h.nsos = std::min(kMaxSos, q->nsos - s0);
+                    h.st = { st[i] }; h.name = "seq[iir" + std::to_string(h.nsos) + "]"; segs.push_back(h);
+                }
+                i++; continue;
+            }
+        }
+        g.type = Segment::SEQ; g.mask = run_mask(st, i, best, &g.nsos);
+        if (!seq_supported(g.mask, g.nsos)) return fail(LQB_EINVAL, "no kernel for stage %s", kind_name(st[i]->kind));
+        g.name = "seq[";
+        for (size_t k = i; k < i + best; k++) {
+            g.st.push_back(st[k]);
+            g.name += (k > i ? "+" : "") + std::string(kind_name(st[k]->kind));
+            if (st[k]->kind == K_IIR) g.name += std::to_string(g.nsos);
+        }
+        g.name += "]";
+        segs.push_back(g); i += best;
+    }
+    c->plan.clear();
+    for (size_t k = 0; k < segs.size(); k++) c->plan += (k ? " -> " : "") + segs[k].name;
+    return LQB_OK;
+}
+
+static size_t seg_out_len(const Segment &g, size_t n) { for (auto *s : g.st) n = s->out_len(n); return n; }
+
+// run one segment on channels [ch0, ch0 + nch) of the chain; x/y point at the first of those rows
+static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_t n_out, int ch0, int nch, cudaStream_t stream)
+{
+    const lqb_stage_s *first = g.st.front();
+    if (g.type == Segment::FIR) {
+        const FirStage *f = static_cast<const FirStage *>(first);
+        FirArgs a{};
+        a.x = (const float2 *)x; a.y = (float2 *)y; a.C = nch; a.ch0 = ch0; a.Ctot = f->C; a.ntaps = (int)f->h.size();
+        a.n = (long long)n; a.scale = f->scale; a.taps = f->taps.p; a.hist_in = f->hist[f->cur].p; a.hist_out = f->hist[f->cur ^ 1].p;
+        LQB_CUDA(fir_launch(a, stream));
+        return LQB_OK;
+    }
+    if (g.type == Segment::RESAMP_PAR) {
+        const ResampStage *r = static_cast<const ResampStage *>(first);
+        ResampP p{}; r->fill(p);
+        LQB_CUDA(resamp_par_launch(p, (const float2 *)x, (float2 *)y, nch, ch0, r->C, (long long)n, (long long)n_out, stream));
+        return LQB_OK;
+    }
+    SeqArgs a{};
+    const bool in_real = (g.mask & F_INREAL) != 0, out_real = (g.mask & (F_AM | F_FM | F_INREAL)) != 0;
+    a.x = x; a.y = y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.n = (long long)n; a.out_pitch = (long long)n_out;
+    a.vec_in  = ((n * (in_real ? 4 : 8)) % 16 == 0) && (((size_t)x) % 16 == 0);
+    a.vec_out = ((n_out * (out_real ? 4 : 8)) % 16 == 0) && (((size_t)y) % 16 == 0);
+    for (lqb_stage_s *s : g.st) {
+        switch (s->kind) {
+        case K_NCO:    LQB_TRY(static_cast<NcoStage *>(s)->fill(a.nco)); break;
+        case K_IIR:    static_cast<IirStage *>(s)->fill(a.iir, g.sos0, g.nsos); break;
+        case K_RESAMP: static_cast<ResampStage *>(s)->fill(a.rs); break;
+        case K_AGC:    static_cast<AgcStage *>(s)->fill(a.agc); break;
+        case K_AM:     LQB_TRY(static_cast<AmStage *>(s)->fill(a.am)); break;
+        case K_FM:     static_cast<FmStage *>(s)->fill(a.fm); break;
+        case K_DEEMPH: static_cast<DeemphStage *>(s)->fill(a.de); break;
+        default: return fail(LQB_EINVAL, "stage kind %d cannot run in the sequential kernel", (int)s->kind);
+        }
+    }
+    LQB_CUDA(seq_launch(g.mask, g.nsos, a, stream));
+    return LQB_OK;
+}
+
+static size_t elem_bytes(bool real) { return real ? 4 : 8; }
+
+static int chain_validate(lqb_chain_s *c)
+{
+    if (!c || c->stages.empty()) return fail(LQB_EINVAL, "empty chain");
+    for (size_t i = 0; i < c->stages.size(); i++) {
+        if (c->stages[i]->C != c->stages[0]->C) return fail(LQB_EINVAL, "stages of one chain must have the same channel count");
+        if (c->stages[i]->device != c->stages[0]->device) return fail(LQB_EINVAL, "stages of one chain must live on one device");
+        if (i && c->stages[i]->in_real() != c->stages[i - 1]->out_real())
+            return fail(LQB_EINVAL, "stage %zu (%s) input type does not match the previous stage's output", i, kind_name(c->stages[i]->kind));
+    }
+    return LQB_OK;
+}
+
+// all segments over channel range [ch0, ch0+nch); tmp0/tmp1 hold intermediates
+static int run_all(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, void *y, size_t n, int ch0, int nch,
+                   char *tmp0, char *tmp1, cudaStream_t stream, int *launches)
+{
+    const void *cur = x; size_t cur_n = n; int flip = 0;
+    for (size_t k = 0; k < segs.size(); k++) {
+        const size_t on = seg_out_len(segs[k], cur_n);
+        void *dst = (k + 1 == segs.size()) ? y : (void *)(flip ? tmp1 : tmp0);
+        // a segment of the same IIR stage split by section offset keeps the sample count
+        if (on > 0 || cur_n > 0) { LQB_TRY(run_segment(segs[k], cur, dst, cur_n, on, ch0, nch, stream)); (*launches)++; }
+        cur = dst; cur_n = on; flip ^= 1;
+    }
+    (void)c;
+    return LQB_OK;
+}
+
+static size_t max_intermediate_bytes(const std::vector<Segment> &segs, size_t n, size_t rows)
+{
+    size_t worst = 0, cur = n;
+    for (size_t k = 0; k + 1 < segs.size(); k++) {
+        cur = seg_out_len(segs[k], cur);
+        worst = std::max(worst, cur * rows * elem_bytes(segs[k].st.back()->out_real()));
+    }
+    return worst;
+}
+
+static void advance_all(lqb_chain_s *c, size_t n) { for (auto *s : c->stages) { const size_t on = s->out_len(n); s->advance(n); n = on; } }
+
+static int chain_out_len(lqb_chain_s *c, size_t n, size_t *n_out) { for (auto *s : c->stages) n = s->out_len(n); *n_out = n; return LQB_OK; }
+
+static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, size_t cap, size_t *n_out, cudaStream_t stream)
+{
+    LQB_TRY(chain_validate(c));
+    for (auto *s : c->stages) LQB_TRY(s->ensure());
+    std::vector<Segment> segs; LQB_TRY(build_plan(c, segs));
+    size_t on; chain_out_len(c, n, &on);
+    if (n_out) *n_out = on;
+    if (on > cap) return fail(LQB_ESIZE, "output needs %zu samples per channel, capacity is %zu", on, cap);
+    c->last_launches = 0;
+    if (n == 0) return LQB_OK;
+    const int C = c->stages[0]->C;
+    const size_t tmpb = max_intermediate_bytes(segs, n, (size_t)C);
+    if (segs.size() > 1) LQB_TRY(c->d_tmp[0].reserve(tmpb));
+    if (segs.size() > 2) LQB_TRY(c->d_tmp[1].reserve(tmpb));
+    LQB_TRY(run_all(c, segs, x, y, n, 0, C, c->d_tmp[0].p, c->d_tmp[1].p, stream, &c->last_launches));
+    advance_all(c, n);
+    return LQB_OK;
+}
+
+static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, size_t cap, size_t *n_out)
+{
+    LQB_TRY(chain_validate(c));
+    for (auto *s : c->stages) LQB_TRY(s->ensure());
+    std::vector<Segment> segs; LQB_TRY(build_plan(c, segs));
+    size_t on; chain_out_len(c, n, &on);
+    if (n_out) *n_out = on;
+    if (on > cap) return fail(LQB_ESIZE, "output needs %zu samples per channel, capacity is %zu", on, cap);
+    c->last_launches = 0;
+    if (n == 0) return LQB_OK;
+    const int C = c->stages[0]->C;
+    const size_t ib = elem_bytes(c->stages.front()->in_real()), ob = elem_bytes(c->stages.back()->out_real());
+    // channel chunks of about 64 MB of input, three streams: H2D of chunk i+1 overlaps the kernels of chunk i
+    size_t chunk = std::max<size_t>(1, ((size_t)64 << 20) / std::max<size_t>(1, n * ib));
+    if (chunk >= 64) chunk = chunk / 64 * 64;
+    chunk = std::min<size_t>(chunk, (size_t)C);
+    for (int s = 0; s < lqb_chain_s::kStreams; s++) if (!c->streams[s]) LQB_CUDA(cudaStreamCreate(&c->streams[s]));
+    const size_t nchunks = ((size_t)C + chunk - 1) / chunk;
+    const size_t tmpb = max_intermediate_bytes(segs, n, chunk);
+    for (size_t s = 0; s < std::min<size_t>(nchunks, lqb_chain_s::kStreams); s++) {
+        LQB_TRY(c->h_in[s].reserve(chunk * n * ib)); LQB_TRY(c->h_out[s].reserve(std::max<size_t>(16, chunk * on * ob)));
+        if (segs.size() > 1) LQB_TRY(c->h_tmp[s][0].reserve(tmpb));
+        if (segs.size() > 2) LQB_TRY(c->h_tmp[s][1].reserve(tmpb));
+    }
+    for (size_t k = 0; k < nchunks; k++) {
+        const int s = (int)(k % lqb_chain_s::kStreams);
+        const size_t c0 = k * chunk, nc = std::min(chunk, (size_t)C - c0);
+        LQB_CUDA(cudaMemcpyAsync(c->h_in[s].p, (const char *)x + c0 * n * ib, nc * n * ib, cudaMemcpyHostToDevice, c->streams[s]));
+        LQB_TRY(run_all(c, segs, c->h_in[s].p, c->h_out[s].p, n, (int)c0, (int)nc, c->h_tmp[s][0].p, c->h_tmp[s][1].p, c->streams[s], &c->last_launches));
+        if (on) LQB_CUDA(cudaMemcpyAsync((char *)y + c0 * on * ob, c->h_out[s].p, nc * on * ob, cudaMemcpyDeviceToHost, c->streams[s]));
+    }
+    for (int s = 0; s < lqb_chain_s::kStreams; s++) LQB_CUDA(cudaStreamSynchronize(c->streams[s]));
+    advance_all(c, n);
+    return LQB_OK;
+}
+
+static lqb_chain_s *self_chain(lqb_stage_s *s)
+{
+    if (!s->self_chain) { s->self_chain = new lqb_chain_s(); s->self_chain->stages.push_back(s); }
+    return s->self_chain;
+}
+
+template <class T> static T *as(lqb_stage s, Kind k) { return (s && s->kind == k) ? static_cast<T *>(s) : nullptr; }
+#define LQB_GET(T, var, s, k) T *var = as<T>(s, k); if (!var) return fail(LQB_EINVAL, "%s: wrong or null stage handle", __func__)
+
+}  // namespace lqb
+
+using namespace lqb;
+
+// ================================================================================ C ABI
+extern "C" {
+
+int lqb_version(void) { return 100; }
+const char *lqb_last_error(void) { return g_err.c_str(); }
+int lqb_device_count(int *count) { LQB_CUDA(cudaGetDeviceCount(count)); return LQB_OK; }
+int lqb_set_device(int device) { LQB_CUDA(cudaSetDevice(device)); return LQB_OK; }
+int lqb_device_synchronize(void) { LQB_CUDA(cudaDeviceSynchronize()); return LQB_OK; }
+int lqb_host_alloc(void **p, size_t bytes) { LQB_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault)); return LQB_OK; }
+int lqb_host_free(void *p) { LQB_CUDA(cudaFreeHost(p)); return LQB_OK; }
+int lqb_dev_alloc(void **p, size_t bytes) { LQB_CUDA(cudaMalloc(p, bytes)); return LQB_OK; }
+int lqb_dev_free(void *p) { LQB_CUDA(cudaFree(p)); return LQB_OK; }
+int lqb_memcpy_h2d(void *d, const void *h, size_t b, void *st) { LQB_CUDA(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, (cudaStream_t)st)); return LQB_OK; }
+int lqb_memcpy_d2h(void *h, const void *d, size_t b, void *st) { LQB_CUDA(cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, (cudaStream_t)st)); return LQB_OK; }
+int lqb_stream_synchronize(void *st) { LQB_CUDA(cudaStreamSynchronize((cudaStream_t)st)); return LQB_OK; }
+
+// ---- generic
+int lqb_stage_destroy(lqb_stage s) { if (s) { if (s->ready) s->bind(); delete s; } return LQB_OK; }
+int lqb_stage_reset(lqb_stage s) { if (!s) return fail(LQB_EINVAL, "null stage"); return s->reset(); }
+int lqb_stage_channels(lqb_stage s, int *n) { if (!s) return fail(LQB_EINVAL, "null stage"); *n = s->C; return LQB_OK; }
+int lqb_stage_out_len(lqb_stage s, size_t n, size_t *n_out) { if (!s) return fail(LQB_EINVAL, "null stage"); *n_out = s->out_len(n); return LQB_OK; }
+int lqb_stage_execute(lqb_stage s, const void *x, size_t n, void *y, size_t cap, size_t *n_out)
+{ if (!s) return fail(LQB_EINVAL, "null stage"); return chain_execute_host(self_chain(s), x, n, y, cap, n_out); }
+int lqb_stage_execute_dev(lqb_stage s, const void *x, size_t n, void *y, size_t cap, size_t *n_out, void *stream)
+{ if (!s) return fail(LQB_EINVAL, "null stage"); return chain_execute_dev(self_chain(s), x, n, y, cap, n_out, (cudaStream_t)stream); }
+
+static int check_channels(int c) { return (c >= 1 && c <= (1 << 24)) ? LQB_OK : fail(LQB_EINVAL, "n_channels must be in [1, 2^24], got %d", c); }
+
+// ---- iirfilt_crcf
+int lqb_iirfilt_crcf_create_sos(const float *B, const float *A, int nsos, int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!B || !A || nsos < 1 || nsos > 64 || !out) return fail(LQB_EINVAL, "iirfilt: need 1..64 sections");
+    IirStage *q = new IirStage(C);
+    int rc = q->init(std::vector<float>(B, B + 3 * nsos), std::vector<float>(A, A + 3 * nsos));
+    if (rc != LQB_OK) { delete q; return rc; }
+    *out = q; return LQB_OK;
+}
+int lqb_iirfilt_crcf_create_prototype(int ftype, int btype, int order, float fc, float f0, float ap, float as, int C, lqb_stage *out)
+{
+    std::vector<float> B, A;
+    const int rc = design::iirdes_sos(ftype, btype, (unsigned)order, fc, f0, ap, as, B, A);
+    if (rc == -2) return fail(LQB_ENOTIMPL, "iirdes: filter family %d (ellip/bessel) is outside the built scope", ftype);
+    if (rc != 0) return fail(LQB_EINVAL, "iirdes: invalid design parameters (order %d, fc %g, f0 %g, ap %g, as %g)", order, fc, f0, ap, as);
+    return lqb_iirfilt_crcf_create_sos(B.data(), A.data(), (int)B.size() / 3, C, out);
+}
+int lqb_iirfilt_crcf_get_sos(lqb_stage s, float *B, float *A, int *nsos)
+{
+    LQB_GET(IirStage, q, s, K_IIR);
+    if (B) std::copy(q->B.begin(), q->B.end(), B);
+    if (A) std::copy(q->A.begin(), q->A.end(), A);
+    if (nsos) *nsos = q->nsos;
+    return LQB_OK;
+}
+int lqb_iirfilt_crcf_freqresponse(lqb_stage s, float fc, lqb_cf *H)
+{
+    LQB_GET(IirStage, q, s, K_IIR);
+    const design::cplx h = design::sos_freqresponse(q->B, q->A, fc);
+    H->re = h.real(); H->im = h.imag(); return LQB_OK;
+}
+int lqb_iirfilt_crcf_set_mode(lqb_stage s, int mode)
+{
+    LQB_GET(IirStage, q, s, K_IIR);
+    if (mode < 0 || mode > 2) return fail(LQB_EINVAL, "iirfilt mode must be 0, 1 or 2");
+    if (mode == 2) return fail(LQB_ENOTIMPL, "time-parallel blocked-scan IIR is not built yet");
+    q->mode = mode; return LQB_OK;
+}
+
+// ---- deemphasis
+int lqb_deemph_create(float sr, int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!(sr > 0.f) || !out) return fail(LQB_EINVAL, "deemph: sample_rate must be positive");
+    DeemphStage *q = new DeemphStage(C);
+    design::deemph_coeffs(sr, q->b0, q->a1);
+    *out = q; return LQB_OK;
+}
+int lqb_deemph_get_coeffs(lqb_stage s, float *b0, float *a1) { LQB_GET(DeemphStage, q, s, K_DEEMPH); *b0 = q->b0; *a1 = q->a1; return LQB_OK; }
+int lqb_deemph_freqresponse(lqb_stage s, float fc, lqb_cf *H)
+{
+    LQB_GET(DeemphStage, q, s, K_DEEMPH);
+    const design::cplx e1 = std::polar(1.0f, (float)(-2 * design::kPi * fc));
+    const design::cplx h = design::cplx(q->b0, 0.f) / (design::cplx(1.f, 0.f) + q->a1 * e1);
+    H->re = h.real(); H->im = h.imag(); return LQB_OK;
+}
+
+// ---- firfilt_crcf
+int lqb_firfilt_crcf_create(const float *h, int n, int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!h || n < 1 || n > kFirMaxTaps || !out) return fail(LQB_EINVAL, "firfilt: need 1..%d taps", kFirMaxTaps);
+    FirStage *q = new FirStage(C);
+    q->h.assign(h, h + n);
+    *out = q; return LQB_OK;
+}
+int lqb_firfilt_crcf_create_kaiser(int n, float fc, float as, float mu, int C, lqb_stage *out)
+{
+    std::vector<float> h;
+    if (n < 1 || !design::firdes_kaiser((unsigned)n, fc, as, mu, h)) return fail(LQB_EINVAL, "firdes_kaiser: invalid parameters");
+    return lqb_firfilt_crcf_create(h.data(), n, C, out);
+}
+int lqb_firfilt_crcf_set_scale(lqb_stage s, float scale) { LQB_GET(FirStage, q, s, K_FIR); q->scale = scale; return LQB_OK; }
+int lqb_firfilt_crcf_get_taps(lqb_stage s, float *h, int *n)
+{
+    LQB_GET(FirStage, q, s, K_FIR);
+    if (h) std::copy(q->h.begin(), q->h.end(), h);
+    if (n) *n = (int)q->h.size();
+    return LQB_OK;
+}
+int lqb_firfilt_crcf_freqresponse(lqb_stage s, float fc, lqb_cf *H)
+{
+    LQB_GET(FirStage, q, s, K_FIR);
+    const design::cplx h = design::fir_freqresponse(q->h, q->scale, fc);
+    H->re = h.real(); H->im = h.imag(); return LQB_OK;
+}
+
+// ---- resamp
+int lqb_resamp_create(float rate, int m, float fc, float as, int npfb, int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!(rate > 0.f) || m < 1 || npfb < 1 || !out) return fail(LQB_EINVAL, "resamp: rate, m and npfb must be positive");
+    if (rate < 0.004f || rate > 250.f) return fail(LQB_EINVAL, "resamp: rate %g outside [0.004, 250]", rate);
+    ResampStage *q = new ResampStage(C);
+    if (!design::resamp_design((unsigned)m, fc, as, (unsigned)npfb, q->d)) { delete q; return fail(LQB_EINVAL, "resamp: invalid prototype (fc %g, As %g)", fc, as); }
+    q->rate = rate; q->step = design::resamp_step(rate);
+    *out = q; return LQB_OK;
+}
+int lqb_resamp_set_rate(lqb_stage s, float rate)
+{
+    LQB_GET(ResampStage, q, s, K_RESAMP);
+    if (rate < 0.004f || rate > 250.f) return fail(LQB_EINVAL, "resamp: rate %g outside [0.004, 250]", rate);
+    q->rate = rate; q->step = design::resamp_step(rate); return LQB_OK;
+}
+int lqb_resamp_get_state(lqb_stage s, uint32_t *step, uint32_t *phase) { LQB_GET(ResampStage, q, s, K_RESAMP); if (step) *step = q->step; if (phase) *phase = q->phase; return LQB_OK; }
+int lqb_resamp_get_bank(lqb_stage s, float *bank, int *npfb, int *sublen)
+{
+    LQB_GET(ResampStage, q, s, K_RESAMP);
+    if (bank) std::copy(q->d.bank.begin(), q->d.bank.end(), bank);
+    if (npfb) *npfb = (int)q->d.npfb;
+    if (sublen) *sublen = (int)q->d.sublen;
+    return LQB_OK;
+}
+
+// ---- nco
+int lqb_nco_create(int type, int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!out) return fail(LQB_EINVAL, "null out");
+    NcoStage *q = new NcoStage(C);
+    q->type = type == LQB_NCO ? 0 : 1;
+    *out = q; return LQB_OK;
+}
+int lqb_nco_set_direction(lqb_stage s, int dir) { LQB_GET(NcoStage, q, s, K_NCO); if (dir != LQB_MIX_UP && dir != LQB_MIX_DOWN) return fail(LQB_EINVAL, "bad direction"); q->dir = dir; return LQB_OK; }
+int lqb_nco_set_frequency(lqb_stage s, float f)     { LQB_GET(NcoStage, q, s, K_NCO); return q->rmw(q->dtheta, design::nco_constrain(f), true); }
+int lqb_nco_adjust_frequency(lqb_stage s, float df) { LQB_GET(NcoStage, q, s, K_NCO); return q->rmw(q->dtheta, design::nco_constrain(df), false); }
+int lqb_nco_set_phase(lqb_stage s, float phi)       { LQB_GET(NcoStage, q, s, K_NCO); return q->rmw(q->theta, design::nco_constrain(phi), true); }
+int lqb_nco_adjust_phase(lqb_stage s, float dphi)   { LQB_GET(NcoStage, q, s, K_NCO); return q->rmw(q->theta, design::nco_constrain(dphi), false); }
+int lqb_nco_get_frequency(lqb_stage s, float *f)
+{ LQB_GET(NcoStage, q, s, K_NCO); LQB_TRY(q->ensure()); uint32_t d; LQB_CUDA(cudaDeviceSynchronize()); LQB_TRY(q->dtheta.download(&d, 1)); *f = design::nco_u32_to_frequency(d); return LQB_OK; }
+int lqb_nco_get_phase(lqb_stage s, float *phi)
+{ LQB_GET(NcoStage, q, s, K_NCO); LQB_TRY(q->ensure()); uint32_t t; LQB_CUDA(cudaDeviceSynchronize()); LQB_TRY(q->theta.download(&t, 1)); *phi = design::nco_u32_to_phase(t); return LQB_OK; }
+int lqb_nco_pll_set_bandwidth(lqb_stage s, float bw) { LQB_GET(NcoStage, q, s, K_NCO); if (bw < 0.f) return fail(LQB_EINVAL, "pll bandwidth must be >= 0"); q->alpha = bw; q->beta = std::sqrt(bw); return LQB_OK; }
+int lqb_nco_pll_step(lqb_stage s, float dphi)
+{
+    LQB_GET(NcoStage, q, s, K_NCO);
+    LQB_TRY(q->rmw(q->dtheta, design::nco_constrain(dphi * q->alpha), false));
+    return q->rmw(q->theta, design::nco_constrain(dphi * q->beta), false);
+}
+int lqb_nco_set_frequency_per_channel(lqb_stage s, const float *f, int n)
+{
+    LQB_GET(NcoStage, q, s, K_NCO);
+    if (!f || n != q->C) return fail(LQB_EINVAL, "need one frequency per channel");
+    LQB_TRY(q->ensure());
+    std::vector<uint32_t> d(n); for (int i = 0; i < n; i++) d[i] = design::nco_constrain(f[i]);
+    LQB_CUDA(cudaDeviceSynchronize());
+    return q->dtheta.upload(d.data(), n);
+}
+int lqb_nco_get_u32(lqb_stage s, uint32_t *theta, uint32_t *d_theta, int n)
+{
+    LQB_GET(NcoStage, q, s, K_NCO);
+    if (n < 0 || n > q->C) return fail(LQB_EINVAL, "bad channel count");
+    LQB_TRY(q->ensure());
+    LQB_CUDA(cudaDeviceSynchronize());
+    if (theta) LQB_TRY(q->theta.download(theta, n));
+    if (d_theta) LQB_TRY(q->dtheta.download(d_theta, n));
+    return LQB_OK;
+}
+int lqb_nco_set_u32(lqb_stage s, const uint32_t *theta, const uint32_t *d_theta, int n)
+{
+    LQB_GET(NcoStage, q, s, K_NCO);
+    if (n < 0 || n > q->C) return fail(LQB_EINVAL, "bad channel count");
+    LQB_TRY(q->ensure());
+    LQB_CUDA(cudaDeviceSynchronize());
+    if (theta) LQB_TRY(q->theta.upload(theta, n));
+    if (d_theta) LQB_TRY(q->dtheta.upload(d_theta, n));
+    return LQB_OK;
+}
+
+// ---- agc
+int lqb_agc_create(int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!out) return fail(LQB_EINVAL, "null out");
+    *out = new AgcStage(C); return LQB_OK;
+}
+int lqb_agc_set_bandwidth(lqb_stage s, float bw) { LQB_GET(AgcStage, q, s, K_AGC); if (bw < 0.f || bw > 1.f) return fail(LQB_EINVAL, "agc bandwidth must be in [0, 1]"); q->alpha = bw; return LQB_OK; }
+int lqb_agc_get_bandwidth(lqb_stage s, float *bw) { LQB_GET(AgcStage, q, s, K_AGC); *bw = q->alpha; return LQB_OK; }
+static int agc_set_gain_all(AgcStage *q, float g, bool reset_y2)
+{
+    LQB_TRY(q->ensure());
+    LQB_CUDA(cudaDeviceSynchronize());
+    LQB_TRY(q->g.fill(g));
+    return reset_y2 ? q->y2p.fill(1.0f) : LQB_OK;
+}
+static int agc_gain0(AgcStage *q, float *g) { LQB_TRY(q->ensure()); LQB_CUDA(cudaDeviceSynchronize()); return q->g.download(g, 1); }
+int lqb_agc_set_signal_level(lqb_stage s, float x2) { LQB_GET(AgcStage, q, s, K_AGC); if (!(x2 > 0.f)) return fail(LQB_EINVAL, "agc level must be > 0"); return agc_set_gain_all(q, 1.0f / x2, true); }
+int lqb_agc_get_signal_level(lqb_stage s, float *x2) { LQB_GET(AgcStage, q, s, K_AGC); float g; LQB_TRY(agc_gain0(q, &g)); *x2 = 1.0f / g; return LQB_OK; }
+int lqb_agc_set_rssi(lqb_stage s, float rssi)
+{
+    LQB_GET(AgcStage, q, s, K_AGC);
+    float g = std::pow(10.0f, -rssi / 20.0f); if (g < 1e-16f) g = 1e-16f;
+    return agc_set_gain_all(q, g, true);
+}
+int lqb_agc_get_rssi(lqb_stage s, float *rssi) { LQB_GET(AgcStage, q, s, K_AGC); float g; LQB_TRY(agc_gain0(q, &g)); *rssi = (float)(-20 * std::log10((double)g)); return LQB_OK; }
+int lqb_agc_set_gain(lqb_stage s, float g) { LQB_GET(AgcStage, q, s, K_AGC); if (!(g > 0.f)) return fail(LQB_EINVAL, "agc gain must be > 0"); return agc_set_gain_all(q, g, false); }
+int lqb_agc_get_gain(lqb_stage s, float *g) { LQB_GET(AgcStage, q, s, K_AGC); return agc_gain0(q, g); }
+int lqb_agc_get_gain_per_channel(lqb_stage s, float *g, int n)
+{ LQB_GET(AgcStage, q, s, K_AGC); if (n < 0 || n > q->C) return fail(LQB_EINVAL, "bad channel count"); LQB_TRY(q->ensure()); LQB_CUDA(cudaDeviceSynchronize()); return q->g.download(g, n); }
+int lqb_agc_set_scale(lqb_stage s, float sc) { LQB_GET(AgcStage, q, s, K_AGC); if (!(sc > 0.f)) return fail(LQB_EINVAL, "agc scale must be > 0"); q->scale = sc; return LQB_OK; }
+int lqb_agc_get_scale(lqb_stage s, float *sc) { LQB_GET(AgcStage, q, s, K_AGC); *sc = q->scale; return LQB_OK; }
+int lqb_agc_lock(lqb_stage s, int locked) { LQB_GET(AgcStage, q, s, K_AGC); q->locked = locked ? 1 : 0; return LQB_OK; }
+int lqb_agc_squelch_enable(lqb_stage s, int en)
+{
+    LQB_GET(AgcStage, q, s, K_AGC);
+    q->squelch = en != 0;
+    if (!q->ready) return LQB_OK;          // materialize() starts from the squelch flag
+    LQB_TRY(q->bind());
+    LQB_CUDA(cudaDeviceSynchronize());
+    return q->mode.fill(en ? 1 : 7);
+}
+int lqb_agc_squelch_set_threshold(lqb_stage s, float t) { LQB_GET(AgcStage, q, s, K_AGC); q->threshold = t; return LQB_OK; }
+int lqb_agc_squelch_get_threshold(lqb_stage s, float *t) { LQB_GET(AgcStage, q, s, K_AGC); *t = q->threshold; return LQB_OK; }
+int lqb_agc_squelch_set_timeout(lqb_stage s, unsigned t) { LQB_GET(AgcStage, q, s, K_AGC); q->timeout = t; return LQB_OK; }   /* takes effect at the next FALL, as in liquid */
+int lqb_agc_squelch_get_status(lqb_stage s, int *st)
+{
+    LQB_GET(AgcStage, q, s, K_AGC);
+    if (!q->ready) { *st = q->squelch ? 1 : 7; return LQB_OK; }
+    LQB_TRY(q->bind()); LQB_CUDA(cudaDeviceSynchronize()); return q->mode.download(st, 1);
+}
+int lqb_agc_take_rise_count(lqb_stage s, unsigned *count)
+{
+    LQB_GET(AgcStage, q, s, K_AGC);
+    if (!q->ready) { *count = 0; return LQB_OK; }
+    LQB_TRY(q->bind());
+    LQB_CUDA(cudaDeviceSynchronize());
+    LQB_TRY(q->rise.download(count, 1));
+    return q->rise.zero();
+}
+
+// ---- ampmodem
+int lqb_ampmodem_create(float mod, int type, int suppressed, int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!out || !(mod > 0.f)) return fail(LQB_EINVAL, "ampmodem: modulation index must be > 0");
+    if (type != LQB_AMPMODEM_DSB) return fail(LQB_ENOTIMPL, "ampmodem: USB/LSB (Hilbert path) is outside the built scope; DSB only");
+    AmStage *q = new AmStage(C);
+    q->mod = mod; q->type = type; q->suppressed = suppressed ? 1 : 0;
+    // constants of liquid's ampmodem_create: m = 25, lowpass kaiser(2m+1, 0.01, 40 dB), dc blocker (25, 20 dB)
+    design::firdes_kaiser(kAmTaps, 0.01f, 40.0f, 0.0f, q->lp);
+    design::firdes_notch(kAmDelay, 0.0f, 20.0f, q->dc);
+    *out = q; return LQB_OK;
+}
+int lqb_ampmodem_get_taps(lqb_stage s, float *lp, int *nlp, float *dc, int *ndc)
+{
+    LQB_GET(AmStage, q, s, K_AM);
+    if (lp) std::copy(q->lp.begin(), q->lp.end(), lp);
+    if (dc) std::copy(q->dc.begin(), q->dc.end(), dc);
+    if (nlp) *nlp = (int)q->lp.size();
+    if (ndc) *ndc = (int)q->dc.size();
+    return LQB_OK;
+}
+int lqb_ampmodem_get_nco_u32(lqb_stage s, uint32_t *theta, uint32_t *d_theta, int n)
+{
+    LQB_GET(AmStage, q, s, K_AM);
+    if (n < 0 || n > q->C) return fail(LQB_EINVAL, "bad channel count");
+    LQB_TRY(q->ensure());
+    LQB_CUDA(cudaDeviceSynchronize());
+    if (theta) LQB_TRY(q->theta.download(theta, n));
+    if (d_theta) LQB_TRY(q->dtheta.download(d_theta, n));
+    return LQB_OK;
+}
+
+// ---- freqdem
+int lqb_freqdem_create(float kf, int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!out || !(kf > 0.f)) return fail(LQB_EINVAL, "freqdem: kf must be > 0");
+    FmStage *q = new FmStage(C);
+    q->kf = kf; q->ref = (float)(1.0f / (2 * design::kPi * kf));
+    *out = q; return LQB_OK;
+}
+
+// ---- chain
+int lqb_chain_create(lqb_chain *out) { if (!out) return fail(LQB_EINVAL, "null out"); *out = new lqb_chain_s(); return LQB_OK; }
+int lqb_chain_append(lqb_chain c, lqb_stage s) { if (!c || !s) return fail(LQB_EINVAL, "null handle"); c->stages.push_back(s); return LQB_OK; }
+int lqb_chain_destroy(lqb_chain c) { delete c; return LQB_OK; }
+int lqb_chain_out_len(lqb_chain c, size_t n, size_t *n_out) { if (!c || !n_out) return fail(LQB_EINVAL, "null handle"); return chain_out_len(c, n, n_out); }
+int lqb_chain_execute(lqb_chain c, const void *x, size_t n, void *y, size_t cap, size_t *n_out) { if (!c) return fail(LQB_EINVAL, "null chain"); return chain_execute_host(c, x, n, y, cap, n_out); }
+int lqb_chain_execute_dev(lqb_chain c, const void *x, size_t n, void *y, size_t cap, size_t *n_out, void *stream)
+{ if (!c) return fail(LQB_EINVAL, "null chain"); return chain_execute_dev(c, x, n, y, cap, n_out, (cudaStream_t)stream); }
+int lqb_chain_plan(lqb_chain c, char *buf, size_t len)
+{
+    if (!c || !buf || !len) return fail(LQB_EINVAL, "null argument");
+    LQB_TRY(chain_validate(c));
+    std::vector<Segment> segs; LQB_TRY(build_plan(c, segs));
+    snprintf(buf, len, "%s", c->plan.c_str());
+    return LQB_OK;
+}
+int lqb_chain_last_launches(lqb_chain c, int *n) { if (!c || !n) return fail(LQB_EINVAL, "null argument"); *n = c->last_launches; return LQB_OK; }
+int lqb_chain_set_fusion(lqb_chain c, int level) { if (!c || level < 0 || level > 2) return fail(LQB_EINVAL, "fusion level must be 0, 1 or 2"); c->fuse = level; return LQB_OK; }
+
+// ---- synthetic inputs
+int lqb_synth_fill(int kind, void *x, int C, int ch0, size_t n, uint64_t n0, uint64_t seed, void *stream)
+{
+    if (kind < 0 || kind > 3 || !x) return fail(LQB_EINVAL, "synth: kind must be 0..3");
+    LQB_CUDA(synth_launch(kind, (float2 *)x, C, ch0, (long long)n, n0, seed, (cudaStream_t)stream));
+    return LQB_OK;
+}
+
+}  // extern "C"

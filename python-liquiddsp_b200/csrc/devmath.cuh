@@ -1,0 +1,69 @@
+// devmath.cuh -- device helpers: packed f32x2 arithmetic (FFMA2/FMUL2/FADD2 on sm_100a),
+// cp.async staging, and the integer phase arithmetic of the oscillator.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lqb {
+
+typedef unsigned long long u64;
+
+// A complex sample rides in one 64-bit register pair (re, im).  The filters on this path have real
+// coefficients, so both lanes run the same recurrence and one FFMA2 does the work of two FFMAs.
+__device__ __forceinline__ u64 pk(float lo, float hi)
+{
+    u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ u64 pk(float2 v) { return pk(v.x, v.y); }
+__device__ __forceinline__ float2 upk(u64 v)
+{
+    float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
+// 16-byte async copy global -> shared; bytes beyond src_bytes are zero-filled.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// radians -> uint32 phase, the oscillator's own arithmetic (see design.hpp nco_constrain): the
+// 1/(2 pi) product is taken in double and rounded to float, everything after is float; a
+// fractional part that rounds up to 1.0f wraps to phase 0.
+__device__ __forceinline__ uint32_t nco_constrain_dev(float theta)
+{
+    float p = (float)((double)theta * 0.159154943091895);
+    float fpart = __fsub_rn(p, (float)((long long)p));
+    if (fpart < 0.f) fpart = __fadd_rn(fpart, 1.0f);
+    float scaled = __fmul_rn(fpart, 4294967296.0f);
+    return (uint32_t)(unsigned long long)(long long)scaled;
+}
+
+// y = x * exp(+j theta) or x * exp(-j theta) with (s, c) = (sin, cos):
+//   up  : re = fma(xr, c, -(xi*s))   im = fma(xi, c,   xr*s )
+//   down: re = fma(xr, c,   xi*s )   im = fma(xi, c, -(xr*s))
+__device__ __forceinline__ float2 mix_up(float2 x, float2 sc)
+{
+    return make_float2(__fmaf_rn(x.x, sc.y, -__fmul_rn(x.y, sc.x)), __fmaf_rn(x.y, sc.y, __fmul_rn(x.x, sc.x)));
+}
+__device__ __forceinline__ float2 mix_down(float2 x, float2 sc)
+{
+    return make_float2(__fmaf_rn(x.x, sc.y, __fmul_rn(x.y, sc.x)), __fmaf_rn(x.y, sc.y, -__fmul_rn(x.x, sc.x)));
+}
+__device__ __forceinline__ unsigned nco_index(uint32_t theta) { return ((theta + (1u << 21)) >> 22) & 0x3ffu; }
+
+}  // namespace lqb

@@ -1,0 +1,131 @@
+// fir.cu -- firfilt_crcf: y[n] = scale * sum_k h[k] x[n-k], real taps, complex samples.
+//
+// Stands in for the push/execute loop of firfilt_*_execute_block (reference call sites
+// firfilter.hpp:33, demod.hpp:135-136).  A FIR has no recurrence, so time is the parallel axis:
+// each CTA takes one [1 x TN] stretch of one channel, stages it (plus the ntaps-1 samples of
+// history in front of it) in shared memory with cp.async, and every thread produces R = 16
+// consecutive outputs from a register-resident sliding window -- per tap one broadcast tap load,
+// one new sample load and 16 FFMA2.  A per-channel FIR is a bandwidth-bound matrix-vector product
+// and stays on the FP32 pipe (no tensor cores).  History is carried between calls in a ping-pong
+// pair of [channel][ntaps-1] arrays.
+#include <cuda_runtime.h>
+#include "params.h"
+#include "devmath.cuh"
+#include "fir.h"
+
+namespace lqb {
+namespace {
+
+constexpr int R   = 16;            // outputs per thread
+constexpr int NT  = kFirThreads;   // threads per CTA
+constexpr int TN  = R * NT;        // outputs per CTA
+
+// one pad slot after every 16 samples: a thread's window starts 16 samples after its neighbour's,
+// so with the pad the 16 lanes of a half-warp land on 16 distinct bank pairs
+__device__ __forceinline__ int phys(int i) { return i + (i >> 4); }
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntiles, const int ntaps_pad)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int halo = ntaps_pad - 1;
+    float2 *s_x = (float2 *)smem_raw;                                  // phys(TN + halo) samples
+    float2 *s_h = s_x + phys(TN + halo) + 1;                           // ntaps_pad duplicated taps
+
+    const int tid = threadIdx.x;
+    const long long ch = blockIdx.x / ntiles;
+    const long long tile = blockIdx.x % ntiles;
+    const long long t0 = tile * TN;                                    // first output of this CTA
+    const long long gch = a.ch0 + ch;
+    const float2 *xrow = a.x + ch * a.n;
+    const float2 *hrow = a.hist_in + gch * (long long)(a.ntaps - 1);
+    const int nh = a.ntaps - 1;
+
+    for (int k = tid; k < ntaps_pad; k += NT) { const float h = k < a.ntaps ? a.taps[k] : 0.f; s_h[k] = make_float2(h, h); }
+    for (int i = tid; i < TN + halo; i += NT) {
+        const long long g = t0 - halo + i;                             // global sample index
+        float2 *dst = &s_x[phys(i)];
+        if (g >= 0) { if (g < a.n) cp_async8(dst, xrow + g); else *dst = make_float2(0.f, 0.f); }
+        else if (g + nh >= 0) cp_async8(dst, hrow + (g + nh));
+        else *dst = make_float2(0.f, 0.f);
+    }
+    cp_async_commit();
+
+    // the last CTA of a channel hands the newest ntaps-1 inputs to the next call
+    if (tile == ntiles - 1) {
+        float2 *ho = a.hist_out + gch * (long long)nh;
+        for (int j = tid; j < nh; j += NT) {
+            const long long g = a.n - nh + j;
+            ho[j] = g >= 0 ? xrow[g] : hrow[g + nh];
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // window W[q] holds the sample at logical index ibase + q; output r with tap k = kb + kk reads
+    // logical index o + r + halo - k = ibase + (r - kk + 15) with ibase = o + halo - kb - 15
+    u64 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = 0ull;
+    u64 W[2 * R - 1];
+    const int o = tid * R;
+    int ibase = o + halo - (R - 1);
+#pragma unroll
+    for (int q = 0; q < 2 * R - 1; q++) W[q] = pk(s_x[phys(ibase + q)]);
+    for (int kb = 0; kb < ntaps_pad; kb += R) {
+#pragma unroll
+        for (int kk = 0; kk < R; kk++) {
+            const u64 tap = pk(s_h[kb + kk]);
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = fma2(tap, W[r - kk + (R - 1)], acc[r]);
+        }
+        if (kb + R < ntaps_pad) {
+            ibase -= R;
+#pragma unroll
+            for (int q = 2 * R - 2; q >= R; q--) W[q] = W[q - R];
+#pragma unroll
+            for (int q = 0; q < R; q++) W[q] = pk(s_x[phys(ibase + q)]);
+        }
+    }
+    __syncthreads();
+    const u64 sc = pk(a.scale, a.scale);
+#pragma unroll
+    for (int r = 0; r < R; r++) s_x[phys(o + r)] = upk(mul2(acc[r], sc));
+    __syncthreads();
+    float2 *yrow = a.y + ch * a.n;
+    const bool vec = ((a.n & 1) == 0) && ((((size_t)a.y) & 15) == 0);
+    if (vec) {
+        for (int i = tid; i < TN / 2; i += NT) {
+            const long long g = t0 + 2 * i;
+            if (g < a.n) {
+                const float2 u = s_x[phys(2 * i)], v = s_x[phys(2 * i + 1)];
+                *(float4 *)(yrow + g) = make_float4(u.x, u.y, v.x, v.y);
+            }
+        }
+    } else {
+        for (int i = tid; i < TN; i += NT) { const long long g = t0 + i; if (g < a.n) yrow[g] = s_x[phys(i)]; }
+    }
+}
+
+}  // namespace
+
+cudaError_t fir_launch(const FirArgs &a, cudaStream_t stream)
+{
+    if (a.C <= 0 || a.n <= 0) return cudaSuccess;
+    const int ntaps_pad = (a.ntaps + R - 1) / R * R;
+    const int halo = ntaps_pad - 1;
+    const long long ntiles = (a.n + TN - 1) / TN;
+    const size_t smem = (size_t)(TN + halo + ((TN + halo) >> 4) + 2 + ntaps_pad) * sizeof(float2);
+    if (smem > 200 * 1024 || ntiles * (long long)a.C > 0x7fffffffLL) return cudaErrorInvalidValue;
+    cudaError_t rc = cudaFuncSetAttribute((const void *)fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc != cudaSuccess) return rc;
+    fir_kernel<<<(unsigned)(ntiles * a.C), NT, smem, stream>>>(a, (int)ntiles, ntaps_pad);
+    return cudaGetLastError();
+}
+
+}  // namespace lqb

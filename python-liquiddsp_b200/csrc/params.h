@@ -1,0 +1,91 @@
+// params.h -- plain-data kernel arguments shared by the host shim (capi.cu) and the kernels.
+//
+// Per-channel carried state lives in HBM as structure-of-arrays [slot][n_channels_total] so that a
+// warp of 32 adjacent channels reads and writes 32 adjacent words.  History rings (resampler
+// window, ampmodem windows, FIR history) are indexed by absolute sample count modulo the ring
+// length; the host tracks the count, the kernels never move ring contents.
+#pragma once
+#include <stdint.h>
+
+namespace lqb {
+
+constexpr int kMaxSos   = 8;     // sections per launch (longer cascades run as several launches)
+constexpr int kAmTaps   = 51;    // ampmodem: 2*m+1, m = 25
+constexpr int kAmDelay  = 25;
+constexpr int kAmRing   = 64;    // power-of-two ring >= kAmTaps
+constexpr int kMaxResampSub = 64; // resampler sub-filter length limit for the fused path (2*m)
+
+enum : unsigned {
+    F_NCO = 1u, F_IIR = 2u, F_RS = 4u, F_AGC = 8u, F_AM = 16u, F_FM = 32u, F_DE = 64u, F_INREAL = 128u
+};
+
+struct NcoP {
+    uint32_t *theta, *dtheta;      // [Ctot]
+    const float2 *sincos;          // device table [1024] of (sin, cos)
+    int type;                      // 0 table NCO, 1 VCO (sinf/cosf)
+    int dir;                       // 1 up, 2 down
+};
+
+struct IirP {
+    int nsos;
+    float b[kMaxSos][3];
+    float a[kMaxSos][3];           // a[.][0] == 1 after normalisation
+    float2 *v;                     // [nsos][2][Ctot] : v1, v2 per section (complex)
+};
+
+struct ResampP {
+    uint32_t step, phase;          // 8.24 fixed point; phase at the first input of this call
+    int bits, sublen, npfb;
+    const float *bank;             // device [npfb][sublen], sub-filters reversed
+    float2 *ring;                  // [sublen][Ctot] last sublen inputs, slot = count % sublen
+    uint32_t count;                // inputs consumed since reset, modulo sublen
+};
+
+struct AgcP {
+    float alpha, scale, threshold;
+    double one_minus_alpha;
+    int locked;
+    unsigned timeout;
+    float *g, *y2p;                // [Ctot]
+    int *mode;                     // [Ctot] squelch state 0..7
+    unsigned *timer;               // [Ctot]
+    unsigned *rise_count;          // single counter (atomicAdd)
+};
+
+struct AmP {
+    float mod_index, pll_alpha, pll_beta;
+    int suppressed;
+    float lp[kAmTaps];             // lowpass taps reversed: lp[i] multiplies the sample (50 - i) steps old
+    float dc[kAmTaps];             // dc-block taps reversed
+    const float2 *sincos;          // NCO table
+    float2 *lp_ring;               // [kAmRing][Ctot]
+    float *dc_ring;                // [kAmRing][Ctot]
+    uint32_t *theta, *dtheta;      // [Ctot]
+    uint32_t count;                // samples consumed since reset, modulo kAmRing
+};
+
+struct FmP { float ref; float2 *rprime; };          // [Ctot]
+struct DeP { float b0, a1; float *v1; };            // [Ctot]
+
+struct SeqArgs {
+    const void *x;                 // [C][n] input rows (complex64, or float32 when F_INREAL)
+    void *y;                       // [C][out_pitch] output rows
+    int C;                         // channels in this launch
+    int ch0;                       // first channel's index into the [.. ][Ctot] state arrays
+    int Ctot;                      // channel stride of the state arrays
+    int vec_in, vec_out;           // 1 when rows allow 16-byte vector access
+    long long n, out_pitch;
+    NcoP nco; IirP iir; ResampP rs; AgcP agc; AmP am; FmP fm; DeP de;
+};
+
+struct FirArgs {
+    const float2 *x; float2 *y;    // [C][n]
+    int C, ch0, Ctot, ntaps;
+    long long n;
+    float scale;
+    const float *taps;             // device [ntaps] in design order h[0..ntaps-1]
+    const float2 *hist_in;         // [Ctot][ntaps-1] last inputs before this call, oldest first
+    float2 *hist_out;              // written by the call (ping-pong with hist_in)
+};
+
+}  // namespace lqb

@@ -1,0 +1,16 @@
+// seq.h -- launcher of the channel-parallel sequential chain kernel (seq.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "params.h"
+
+namespace lqb {
+
+constexpr int kSeqBT  = 64;   // channels per CTA
+constexpr int kSeqTS  = 16;   // samples per staged tile row (128 B of complex64 per channel)
+constexpr int kSeqNST = 3;    // cp.async ring depth
+
+// true when a kernel for this stage mask / section count was compiled
+bool seq_supported(unsigned mask, int nsos);
+cudaError_t seq_launch(unsigned mask, int nsos, const SeqArgs &a, cudaStream_t stream);
+
+}  // namespace lqb

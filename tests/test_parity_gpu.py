@@ -1,0 +1,420 @@
+"""GPU parity: every stage of the hot path and the fused chains, called through
+the C ABI (ctypes module `liquiddsp`) and compared with the CPU oracle on identical inputs and
+identical coefficients.  Tolerances are BASELINE.json's: rel-L2 <= 1e-5 per stage, <= 1e-4 end to end;
+integer phase / output counts bit-exact.  Where the kernel evaluates the oracle's operations in the
+oracle's order the test demands bit equality.
+"""
+import numpy as np
+import pytest
+
+import liquiddsp as L
+from oracle import oracle as O
+from util import rel_l2, crandn, am_iq, fm_iq, split_points
+
+pytestmark = pytest.mark.gpu
+TOL_STAGE = 1e-5
+TOL_E2E = 1e-4
+
+
+# ------------------------------------------------------------------------------------------- a1
+@pytest.mark.parametrize("ft,bt,order", [("cheby2", "lowpass", 8), ("butter", "lowpass", 2), ("butter", "lowpass", 1),
+                                          ("cheby1", "highpass", 5), ("cheby2", "bandpass", 4), ("butter", "bandstop", 10)])
+def test_iir_single_channel_bit_exact(cuda, ft, bt, order):
+    rng = np.random.default_rng(1)
+    fc = 0.0075 if (ft, order) == ("cheby2", 8) else 0.1
+    g = L.ComplexIIRFilter(ft, bt, order=order, Fc=fc, F0=0.2, Ap=1.0, As=60.0)
+    o = O.ComplexIIRFilter(_sos=g.sos())
+    x = crandn(rng, 20000)
+    y, yo = g(x), o(x)
+    assert y.dtype == np.complex64 and y.shape == x.shape
+    assert np.array_equal(y.view(np.uint32), yo.view(np.uint32)), rel_l2(y, yo)
+
+
+@pytest.mark.parametrize("n", [1000, 1001, 7, 16, 17])
+def test_iir_batched_ragged(cuda, n):
+    rng = np.random.default_rng(2)
+    C = 130                                             # not a multiple of the 64-channel CTA
+    g = L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=C)
+    x = crandn(rng, C, n)
+    y = g(x)
+    for c in (0, 1, 63, 64, 129):
+        o = O.ComplexIIRFilter(_sos=g.sos())
+        assert np.array_equal(y[c].view(np.uint32), o(x[c]).view(np.uint32)), (c, n)
+
+
+def test_iir_streaming_invariance(cuda):
+    rng = np.random.default_rng(3)
+    x = crandn(rng, 3, 30011)
+    a = L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=3)
+    b = L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=3)
+    whole = a(x)
+    parts = np.concatenate([b(x[:, s:e]) for s, e in split_points(x.shape[1], 7, rng)], axis=1)
+    assert np.array_equal(whole.view(np.uint32), parts.view(np.uint32))
+    a.reset()
+    assert np.array_equal(a(x).view(np.uint32), whole.view(np.uint32))
+
+
+def test_iir_empty_and_dtype_cast(cuda):
+    g = L.ComplexIIRFilter("butter", order=2, Fc=0.2)
+    assert g(np.zeros(0, np.complex64)).shape == (0,)
+    x = np.linspace(0, 1, 64)                            # float64 -> forcecast to complex64, as pybind11 does
+    o = O.ComplexIIRFilter(_sos=g.sos())
+    assert np.array_equal(g(x), o(x))
+    with pytest.raises(ValueError):
+        g(np.zeros((2, 8), np.complex64))
+
+
+# ------------------------------------------------------------------------------------------- a2
+@pytest.mark.parametrize("ntaps,C,n", [(64, 3, 5000), (64, 1, 2047), (51, 2, 2049), (1, 2, 100), (17, 1, 5), (200, 1, 9000)])
+def test_fir_crcf(cuda, ntaps, C, n):
+    rng = np.random.default_rng(4)
+    h = O.firdes_kaiser(ntaps, 0.1, 60.0) if ntaps > 1 else np.array([0.5], np.float32)
+    g = L.FIRFilter(h, channels=C)
+    x = crandn(rng, C, n)
+    y = g(x) if C > 1 else g(x[0]).reshape(1, -1)
+    for c in range(C):
+        assert rel_l2(y[c], O.FIRFilter(h)(x[c])) <= TOL_STAGE
+
+
+def test_fir_streaming_invariance_and_scale(cuda):
+    rng = np.random.default_rng(5)
+    h = O.firdes_kaiser(64, 0.1, 60.0)
+    x = crandn(rng, 2, 12000)
+    a, b = L.FIRFilter(h, channels=2), L.FIRFilter(h, channels=2)
+    whole = a(x)
+    parts = np.concatenate([b(x[:, s:e]) for s, e in split_points(x.shape[1], 6, rng)], axis=1)
+    assert np.array_equal(whole.view(np.uint32), parts.view(np.uint32))
+    a.reset(); a.set_scale(0.25)
+    assert rel_l2(a(x), 0.25 * whole) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------- a3
+def test_resampler_readme_rate_counts_and_values(cuda):
+    rng = np.random.default_rng(6)
+    g = L.ComplexResampler(rate=48e3 / 2e6, Fc=48e3 / 2e6)
+    o = O.ComplexResampler(rate=48e3 / 2e6, Fc=48e3 / 2e6)
+    assert g.state()[0] == o.step == 0x29AAAAC0
+    counts = []
+    for blk in range(9):                                  # 64K blocks: 1573 x7 then 1572
+        x = crandn(rng, 65536)
+        y, yo = g(x), o(x)
+        counts.append(len(y))
+        assert len(y) == len(yo)
+        assert g.state()[1] == o.phase                    # fixed-point phase bit-exact after every block
+        assert rel_l2(y, yo) <= TOL_STAGE
+    assert counts[:8] == [1573] * 7 + [1572]
+
+
+@pytest.mark.parametrize("rate", [0.5, 1.7, 0.03, 0.024, 3.0, 0.0101])
+def test_resampler_general_rates(cuda, rate):
+    rng = np.random.default_rng(7)
+    g = L.ComplexResampler(rate=rate, Fc=min(0.45, 0.45 * rate) if rate < 1 else 0.45, channels=2)
+    o = [O.ComplexResampler(rate=rate, Fc=min(0.45, 0.45 * rate) if rate < 1 else 0.45) for _ in range(2)]
+    for n in (4000, 1, 39, 2500):
+        x = crandn(rng, 2, n)
+        y = g(x)
+        for c in range(2):
+            yo = o[c](x[c])
+            assert y.shape[1] == len(yo)
+            assert rel_l2(y[c], yo) <= TOL_STAGE if len(yo) else True
+        assert g.state()[1] == o[0].phase
+
+
+def test_resampler_set_rate_and_reset(cuda):
+    rng = np.random.default_rng(8)
+    g, o = L.ComplexResampler(0.024, Fc=0.024), O.ComplexResampler(0.024, Fc=0.024)
+    x = crandn(rng, 5000)
+    assert rel_l2(g(x), o(x)) <= TOL_STAGE
+    g.rate = 0.02; o.rate = 0.02                          # set_rate keeps the window (resampler.hpp:151-154)
+    assert g.state()[0] == o.step
+    assert rel_l2(g(x), o(x)) <= TOL_STAGE
+    g.reset(); o.reset()
+    assert rel_l2(g(x), o(x)) <= TOL_STAGE
+
+
+# ------------------------------------------------------------------------------------------- a4
+def test_nco_phase_bit_exact_and_mix(cuda):
+    rng = np.random.default_rng(9)
+    g, o = L.NCO(), O.NCO()
+    g.freq = 0.3; o.freq = 0.3
+    g.phase = 1.0; o.phase = 1.0
+    x = crandn(rng, 10001)
+    yu, you = g.mix_up(x), o.mix_up(x)
+    assert np.array_equal(yu.view(np.uint32), you.view(np.uint32))
+    t, d = g.u32(); assert (int(t[0]), int(d[0])) == (o.theta_u32, o.dtheta_u32)
+    yd, yod = g.mix_down(x), o.mix_down(x)
+    assert np.array_equal(yd.view(np.uint32), yod.view(np.uint32))
+    for df in (-1e-3, 1e-9, -1e-9, 0.5):                 # constrain() edge cases incl. the tiny-negative wrap
+        g.adjust_frequency(df); o.adjust_frequency(df)
+        g.adjust_phase(-df); o.adjust_phase(-df)
+    g.set_pll_bandwidth(0.05); o.set_pll_bandwidth(0.05); g.pll_step(0.01); o.pll_step(0.01)
+    t, d = g.u32(); assert (int(t[0]), int(d[0])) == (o.theta_u32, o.dtheta_u32)
+    assert abs(g.freq - o.freq) < 1e-6 and abs(g.phase - o.phase) < 1e-6
+
+
+def test_nco_batched_per_channel_closed_form(cuda):
+    C, n = 70, 3000
+    g = L.NCO(channels=C)
+    f = (2 * np.pi * (0.05 + 0.4 * np.arange(C) / C)).astype(np.float32)
+    g.set_frequencies(f)
+    x = np.ones((C, n), np.complex64)
+    g.set_direction(True); y = L._Stage.__call__(g, x)
+    t, d = g.u32()
+    assert np.array_equal(t, (d.astype(np.uint64) * n % (1 << 32)).astype(np.uint32))   # theta_n = n * d_theta mod 2^32
+    for c in (0, 33, 69):
+        o = O.NCO(); o.freq = float(f[c])
+        assert o.dtheta_u32 == int(d[c])
+        assert np.array_equal(y[c].view(np.uint32), o.mix_down(x[c]).view(np.uint32))
+
+
+def test_vco_type(cuda):
+    rng = np.random.default_rng(10)
+    g, o = L.NCO("vco"), O.NCO("vco")
+    g.freq = 0.123; o.freq = 0.123
+    x = crandn(rng, 4000)
+    assert rel_l2(g(x), o(x)) <= TOL_STAGE
+
+
+# ------------------------------------------------------------------------------------------- a5
+def test_agc_default_and_readme_settings(cuda):
+    rng = np.random.default_rng(11)
+    x = crandn(rng, 30000, scale=0.05)
+    x[15000:] *= 20
+    for scale, bw in ((1.0, 1e-2), (0.01, 1e-2), (1.0, 1e-3)):
+        g, o = L.AGC(), O.AGC()
+        g.lock = False; o.lock = False
+        g.scale = scale; o.scale = scale; g.bandwidth = bw; o.bandwidth = bw
+        y, yo = g(x), o(x)
+        assert rel_l2(y, yo) <= TOL_STAGE
+        assert abs(g.gain / o.gain - 1) < 1e-5 and abs(g.level_dB - o.level_dB) < 1e-3
+
+
+def test_agc_lock_and_properties(cuda):
+    rng = np.random.default_rng(12)
+    x = crandn(rng, 5000, scale=0.2)
+    g, o = L.AGC(), O.AGC()
+    g.gain = 3.0; o.gain = 3.0
+    g.lock = True; o.lock = True
+    assert rel_l2(g(x), o(x)) <= 1e-6                     # locked: y = x*g, no output scale applied
+    g.level = 0.5; o.level = 0.5
+    assert abs(g.gain - o.gain) < 1e-6
+    g.level_dB = -30.0; o.level_dB = -30.0
+    assert abs(g.gain / o.gain - 1) < 1e-6
+    g.reset(); o.reset()
+    assert g.gain == o.gain == 1.0
+    assert rel_l2(g(x), o(x)) <= TOL_STAGE
+
+
+def test_agc_squelch_states_and_on_rise(cuda):
+    rng = np.random.default_rng(13)
+    n = 6000
+    env = np.concatenate([np.full(1500, 1e-3), np.full(2000, 1.0), np.full(2500, 1e-3)])
+    x = (env * (rng.standard_normal(n) + 1j * rng.standard_normal(n)) / np.sqrt(2)).astype(np.complex64)
+    g, o = L.AGC(), O.AGC()
+    fired = []
+    g.onRise = lambda: fired.append(1)
+    for q in (g, o):
+        q.bandwidth = 0.05; q.squelch = True; q.threshold = -30.0
+    g.set_timeout(100); o.set_timeout(100)
+    y, yo = g(x), o(x)
+    assert np.array_equal(y == 0, yo == 0)                # zeroed in ENABLED / SIGNALLO (agc.hpp:124-125)
+    assert rel_l2(y, yo) <= TOL_STAGE
+    assert g.status == o.status
+    assert len(fired) == len(o.rise_indices) >= 1
+
+
+# ------------------------------------------------------------------------------------------- a6
+@pytest.mark.parametrize("carrier", [True, False])
+def test_ampmodem_dsb(cuda, carrier):
+    n = 20000
+    t = np.arange(n) / 48e3
+    m = 0.6 * np.sin(2 * np.pi * 1000 * t) + 0.4 * np.sin(2 * np.pi * 2500 * t)
+    rng = np.random.default_rng(14)
+    if carrier:
+        x = 0.01 * (1 + 0.5 * m) * np.exp(1j * (2 * np.pi * 5.0 * t + 0.4))
+    else:
+        x = 0.5 * m * np.exp(1j * (2 * np.pi * 2.0 * t + 0.2))
+    x = (x + 1e-4 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    g, o = L.AmpModem(0.5, "dsb", carrier), O.AmpModem(0.5, "dsb", carrier)
+    lp, dc = g.taps(); lpo, dco = o.taps()
+    assert np.array_equal(lp, lpo) and np.array_equal(dc, dco)
+    ys, yos = [], []
+    for s, e in split_points(n, 5, rng):                  # state carried across ragged calls
+        ys.append(g(x[s:e])); yos.append(o(x[s:e]))
+        tg, dg = g.nco_u32()
+        assert (int(tg[0]), int(dg[0])) == o.nco_u32()    # PLL phase and frequency words bit-exact
+    y, yo = np.concatenate(ys), np.concatenate(yos)
+    assert y.dtype == np.float32
+    assert rel_l2(y, yo) <= TOL_STAGE
+    g.reset(); o.reset()
+    assert rel_l2(g(x[:3000]), o(x[:3000])) <= TOL_STAGE
+    g.modulation = 0.8; o.modulation = 0.8                # setter rebuilds the modem (demod.hpp:258-262)
+    assert rel_l2(g(x[:3000]), o(x[:3000])) <= TOL_STAGE
+
+
+# ------------------------------------------------------------------------------------------- a7 / a8
+def test_freqdem(cuda):
+    x = fm_iq(50000)
+    g, o = L.FreqDem(0.1), O.FreqDem(0.1)
+    y = np.concatenate([g(x[:20001]), g(x[20001:])]); yo = o(x)
+    assert rel_l2(y, yo) <= TOL_STAGE
+    assert abs(np.mean(y[1000:] ** 2) - 0.5) < 0.05      # recovers the unit-amplitude 1 kHz tone
+
+
+def test_deemphasis_bit_exact(cuda):
+    rng = np.random.default_rng(15)
+    x = rng.standard_normal(10000).astype(np.float32)
+    g, o = L.DeemphasisFilter(48000), O.DeemphasisFilter(48000)
+    assert g.coeffs() == O.DeemphasisFilter.coeffs(48000)
+    y = np.concatenate([g(x[:4097]), g(x[4097:])])
+    assert np.array_equal(y.view(np.uint32), o(x).view(np.uint32))
+    gb = L.DeemphasisFilter(48000, channels=5)
+    yb = gb(np.tile(x, (5, 1)))
+    assert all(np.array_equal(yb[c], y) for c in range(5))
+
+
+# ------------------------------------------------------------------------------------------- chains
+def _amradio_stages(mod, channels=1):
+    return (mod.ComplexIIRFilter(filter_type="cheby2", order=8, Fc=15000 / 2e6, **({"channels": channels} if mod is L else {})),
+            mod.ComplexResampler(rate=48e3 / 2e6, Fc=48e3 / 2e6, **({"channels": channels} if mod is L else {})))
+
+
+class _Radio:
+    """README.md:41-58 AMRadio.__init__/__call__, parameterised by the module that provides the classes."""
+
+    def __init__(self, mod, channels=None):
+        kw = {} if channels is None else {"channels": channels}
+        self.bandpass = mod.ComplexIIRFilter(filter_type="cheby2", order=8, Fc=15000 / 2000000, **kw)
+        self.resample = mod.ComplexResampler(rate=48000 / 2000000, Fc=48000 / 2000000, **kw)
+        self.am = mod.AmpModem(modulation=0.5, type="dsb", carrier=True, **kw)
+        self.audio_filter = mod.DeemphasisFilter(48000, **kw)
+        self.agc = mod.AGC(**kw)
+        self.agc.lock = False
+        self.agc.scale = 0.01
+
+    def stages(self):
+        return (self.bandpass, self.resample, self.agc, self.am, self.audio_filter)
+
+    def __call__(self, iq):
+        return self.audio_filter(self.am(self.agc(self.resample(self.bandpass(iq)))))
+
+
+def _oracle_radio_with_product_coeffs(gr):
+    r = _Radio(O)
+    r.bandpass = O.ComplexIIRFilter(_sos=gr.bandpass.sos())
+    return r
+
+
+def test_readme_amradio_drop_in_config1(cuda):
+    """BASELINE config 1 (shortened): README AMRadio, one channel, 64K blocks, state carried."""
+    n, blk = 10 * 65536, 65536
+    x = am_iq(n)
+    gr = _Radio(L); orr = _oracle_radio_with_product_coeffs(gr)
+    pcm = np.concatenate([gr(x[i:i + blk]) for i in range(0, n, blk)])
+    ref = np.concatenate([orr(x[i:i + blk]) for i in range(0, n, blk)])
+    assert pcm.shape == ref.shape and pcm.dtype == np.float32
+    assert rel_l2(pcm, ref) <= TOL_E2E
+    seg = pcm[6000:] * np.hanning(len(pcm) - 6000)       # the two audio tones come out on top
+    spec = np.abs(np.fft.rfft(seg)); f = np.fft.rfftfreq(len(seg), 1 / 48e3)
+    top = sorted(f[np.argsort(spec)[-4:]])
+    assert abs(top[0] - 1000) < 5 and abs(top[-1] - 2500) < 5
+
+
+@pytest.mark.parametrize("fuse", [0, 1, 2])
+def test_fused_chain_matches_stagewise(cuda, fuse):
+    n, blk = 3 * 65536 + 1234, 65536
+    x = am_iq(n, seed=5)
+    a, b = _Radio(L), _Radio(L)
+    chain = L.Chain(*b.stages(), fuse=fuse)
+    expect = {0: 5, 1: 2, 2: 1}[fuse]
+    ys, yc = [], []
+    for i in range(0, n, blk):
+        ys.append(a(x[i:i + blk])); yc.append(chain(x[i:i + blk]))
+        assert chain.last_launches() == expect
+    ys, yc = np.concatenate(ys), np.concatenate(yc)
+    assert np.array_equal(ys.view(np.uint32), yc.view(np.uint32)), rel_l2(yc, ys)
+    assert b.resample.state() == a.resample.state()
+
+
+def test_batched_amradio_vs_oracle_subset(cuda):
+    """BASELINE config 5 in miniature: many channels, device-generated input, oracle on a channel subset."""
+    C, n = 200, 32768
+    r = _Radio(L, channels=C)
+    chain = L.Chain(*r.stages())
+    xb = L.DeviceBuffer(C * n * 8)
+    orr = {}
+    outs = []
+    for blk in range(3):
+        L.synth_fill(0, xb.ptr.value, C, n, n0=blk * n)
+        x = xb.download((C, n), np.complex64)
+        y = chain(x)
+        outs.append(y)
+        for c in (0, 1, 63, 64, 127, 199):
+            if c not in orr:
+                orr[c] = [_oracle_radio_with_product_coeffs(r), []]
+            orr[c][1].append(orr[c][0](x[c]))
+    y = np.concatenate(outs, axis=1)
+    for c, (_, parts) in orr.items():
+        assert rel_l2(y[c], np.concatenate(parts)) <= TOL_E2E, c
+    assert np.std(y[0][4000:]) > 1e-4                    # there is audio
+
+
+def test_config3_nco_resampler(cuda):
+    C, n = 96, 65536
+    nco = L.NCO(channels=C); rs = L.ComplexResampler(0.024, Fc=0.024, channels=C)
+    f = (2 * np.pi * (0.05 + 0.4 * np.arange(C) / 4096)).astype(np.float32)
+    nco.set_frequencies(f); nco.set_direction(True)
+    chain = L.Chain(nco, rs)
+    assert chain.plan() == "seq[nco+resamp]"
+    xb = L.DeviceBuffer(C * n * 8)
+    refs = {c: (O.NCO(), O.ComplexResampler(0.024, Fc=0.024)) for c in (0, 50, 95)}
+    for c, (on, _) in refs.items():
+        on.freq = float(f[c])
+    for blk in range(3):
+        L.synth_fill(2, xb.ptr.value, C, n, n0=blk * n)
+        x = xb.download((C, n), np.complex64)
+        y = chain(x)
+        for c, (on, ors) in refs.items():
+            yo = ors(on.mix_down(x[c]))
+            assert y.shape[1] == len(yo)
+            assert rel_l2(y[c], yo) <= TOL_STAGE
+        t, _ = nco.u32()
+        assert all(int(t[c]) == refs[c][0].theta_u32 for c in refs)   # oscillator phase bit-exact
+        assert rs.state()[1] == refs[0][1].phase
+
+
+def test_config4_iir_agc_fm(cuda):
+    C, n = 80, 20000
+    iir = L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=C)
+    agc = L.AGC(channels=C); fm = L.FreqDem(0.1, channels=C)
+    chain = L.Chain(iir, agc, fm)
+    assert chain.plan() == "seq[iir4+agc+freqdem]"
+    xb = L.DeviceBuffer(C * n * 8)
+    refs = {c: (O.ComplexIIRFilter(_sos=iir.sos()), O.AGC(), O.FreqDem(0.1)) for c in (0, 40, 79)}
+    for blk in range(2):
+        L.synth_fill(3, xb.ptr.value, C, n, n0=blk * n)
+        x = xb.download((C, n), np.complex64)
+        y = chain(x)
+        assert y.dtype == np.float32 and y.shape == (C, n)
+        for c, (oi, oa, of) in refs.items():
+            yo = of(oa(oi(x[c])))
+            # FM demod of a noisy narrow-band signal: compare on phase-difference scale (|y| <= 1/(2 kf) = 5)
+            assert np.linalg.norm(y[c] - yo) / np.sqrt(n) <= 5 * TOL_E2E, c
+
+
+def test_execute_dev_and_chunked_host_agree(cuda):
+    """Device-pointer entry point == host entry point (which chunks channels over three streams)."""
+    C, n = 300, 65536                                     # 157 MB of input -> 3 chunks
+    r1, r2 = _Radio(L, channels=C), _Radio(L, channels=C)
+    c1, c2 = L.Chain(*r1.stages()), L.Chain(*r2.stages())
+    xb = L.DeviceBuffer(C * n * 8)
+    L.synth_fill(0, xb.ptr.value, C, n)
+    x = xb.download((C, n), np.complex64)
+    y1 = c1(x)
+    n_out = c2.out_len(n)
+    yb = L.DeviceBuffer(C * n_out * 4)
+    got = c2.execute_dev(xb.ptr.value, n, yb.ptr.value, n_out, 0)
+    L.synchronize()
+    y2 = yb.download((C, got), np.float32)
+    assert got == n_out == y1.shape[1]
+    assert np.array_equal(y1.view(np.uint32), y2.view(np.uint32))
