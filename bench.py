@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--channels", type=int, default=65536, help="channels per GPU (config 5: 65536)")
     ap.add_argument("--e2e-channels", type=int, default=8192, help="channels per GPU of the host-buffer (e2e) leg")
     ap.add_argument("--fuse", type=int, default=1, help="chain fusion level (0, 1, 2)")
+    ap.add_argument("--block", type=int, default=BLOCK, help="samples per channel per step (profiling runs use a shorter block)")
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -143,7 +144,7 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = "config5: README AMRadio chain, %d channels/GPU x %d-sample blocks @ 2 MS/s, state carried" % (args.channels, BLOCK)
+    workload = "config5: README AMRadio chain, %d channels/GPU x %d-sample blocks @ 2 MS/s, state carried" % (args.channels, args.block)
 
     if args.impl == "reference":
         # the reference's CPU implementation of the path, restated (liquid-dsp is absent): all host cores,
@@ -197,7 +198,7 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
                "sample": "%d processes x 1 channel of config 1 (README AMRadio, 64K blocks) for %.0f s each; CPU restatement of liquid-dsp, not liquid-dsp" % (cores, args.cpu_seconds)}
 
-    C, n = args.channels, BLOCK
+    C, n = args.channels, args.block
     stream = torch.cuda.current_stream().cuda_stream
     x = torch.empty((C, n), dtype=torch.complex64, device=dev)
     stages = build_radio(L, C)

@@ -64,6 +64,21 @@ __device__ __forceinline__ float2 mix_down(float2 x, float2 sc)
 {
     return make_float2(__fmaf_rn(x.x, sc.y, __fmul_rn(x.y, sc.x)), __fmaf_rn(x.y, sc.y, -__fmul_rn(x.x, sc.x)));
 }
+// exp(a) rounded once to float.  The AGC multiplies its gain by exp(-alpha/2 * ln(y2')) every sample, a
+// factor within a few ulp of 1; a one-ulp bias there (CUDA's expf is allowed two) accumulates to
+// bias/alpha = 1e-5 in the gain.  For the small arguments the loop produces a degree-9 Taylor series in
+// double is exact far below float resolution; larger arguments take the double-precision library exp.
+__device__ __forceinline__ float exp_rn_small(float a)
+{
+    const double x = (double)a;
+    if (fabsf(a) > 0.125f) return (float)exp(x);
+    double p = 1.0 / 362880.0;
+    p = fma(p, x, 1.0 / 40320.0); p = fma(p, x, 1.0 / 5040.0); p = fma(p, x, 1.0 / 720.0);
+    p = fma(p, x, 1.0 / 120.0);   p = fma(p, x, 1.0 / 24.0);   p = fma(p, x, 1.0 / 6.0);
+    p = fma(p, x, 0.5);           p = fma(p, x, 1.0);          p = fma(p, x, 1.0);
+    return (float)p;
+}
+
 __device__ __forceinline__ unsigned nco_index(uint32_t theta) { return ((theta + (1u << 21)) >> 22) & 0x3ffu; }
 
 }  // namespace lqb

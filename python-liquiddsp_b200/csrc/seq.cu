@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(BT) seq_kernel(const __grid_constant__ SeqArgs
             float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
             agc_y2p = (float)fma(a.agc.one_minus_alpha, (double)agc_y2p, (double)__fmul_rn(a.agc.alpha, y2));
             if (!a.agc.locked) {
-                if (agc_y2p > 1e-6f) agc_g = __fmul_rn(agc_g, expf(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), logf(agc_y2p))));
+                if (agc_y2p > 1e-6f) agc_g = __fmul_rn(agc_g, exp_rn_small(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), logf(agc_y2p))));
                 if (agc_g > 1e6f) agc_g = 1e6f;
                 if (agc_mode != 7) {
                     const bool ex = (float)(-20.0 * log10((double)agc_g)) > a.agc.threshold;

@@ -1,0 +1,153 @@
+"""CPU: the C-ABI library loads and exports every symbol include/liquiddsp_b200.h declares, the host-side
+logic (design, planner, output-length bookkeeping, argument checking) behaves, and nothing computes
+without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import liquiddsp as L
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "liquiddsp_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lqb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = ctypes.CDLL(L.lib_path)
+    names = _declared()
+    assert len(names) > 70
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.lqb_version() >= 100
+
+
+def test_python_binding_covers_the_header():
+    bound = set(L._SIG) | {"lqb_last_error"}
+    assert set(_declared()) <= bound, sorted(set(_declared()) - bound)
+
+
+def test_reference_api_surface():
+    """Names, keyword arguments and defaults of wrapper.cpp."""
+    import inspect
+    sig = lambda c: {k: v.default for k, v in inspect.signature(c.__init__).parameters.items() if k not in ("self", "channels", "sos")}
+    assert sig(L.ComplexIIRFilter) == dict(filter_type="butter", band_type="lowpass", order=2, Fc=0.2, F0=0.3, Ap=0.7, As=60.0)
+    assert sig(L.ComplexResampler) == dict(rate=inspect._empty, len=20, Fc=None, As=60.0, nfilter=13)
+    assert sig(L.AmpModem) == dict(modulation=0.75, type="dsb", carrier=False)
+    assert sig(L.DeemphasisFilter) == dict(sample_rate=48000)
+    assert sig(L.NCO) == dict(type="nco") and sig(L.FreqDem) == dict(kd=inspect._empty) and sig(L.AGC) == {}
+    for name in ("squelch", "threshold", "bandwidth", "level", "level_dB", "lock", "gain", "scale", "status"):
+        assert isinstance(getattr(L.AGC, name), property)
+    for name in ("freq", "phase"):
+        assert isinstance(getattr(L.NCO, name), property)
+    for meth in ("adjust_frequency", "adjust_phase", "set_pll_bandwidth", "pll_step", "mix_up", "mix_down", "print"):
+        assert callable(getattr(L.NCO, meth))
+    with pytest.raises(TypeError):
+        L.ComplexResampler(0.024)                          # Fc has no default in the reference either
+    f = L.ComplexIIRFilter("nonsense", "whatever", order=2, Fc=0.2)    # silent fallback, empty property
+    assert f.filter_type == "" and f.band_type == ""
+    assert np.allclose(f.sos()[0], L.ComplexIIRFilter("butter", "lowpass", order=2, Fc=0.2).sos()[0])
+    assert L.NCO("anything").type == "vco"                 # nco.hpp:16-24
+
+
+@pytest.mark.parametrize("ft", ["butter", "cheby1", "cheby2"])
+@pytest.mark.parametrize("bt", ["lowpass", "highpass", "bandpass", "bandstop"])
+@pytest.mark.parametrize("order", [1, 2, 3, 5, 8])
+def test_product_design_equals_oracle_design(ft, bt, order):
+    g = L.ComplexIIRFilter(ft, bt, order=order, Fc=0.1, F0=0.2, Ap=1.0, As=40.0)
+    B, A = g.sos(); Bo, Ao = O.iirdes_sos(ft, bt, order, 0.1, 0.2, 1.0, 40.0)
+    assert B.shape == Bo.shape and np.max(np.abs(B - Bo)) < 2e-6 and np.max(np.abs(A - Ao)) < 2e-6
+    H, Ho = g.freqresponse(0.07), O.ComplexIIRFilter(ft, bt, order, 0.1, 0.2, 1.0, 40.0).freqresponse(0.07)
+    assert abs(H - Ho) < 1e-4 * max(1.0, abs(Ho))
+
+
+def test_product_tables_equal_oracle_tables():
+    r, ro = L.ComplexResampler(0.024, Fc=0.024), O.ComplexResampler(0.024, Fc=0.024)
+    assert r.state() == (0x29AAAAC0, 0) and np.array_equal(r.bank(), ro.bank())
+    for rate in (0.5, 1.7, 0.03, 0.0101, 3.0):
+        assert L.ComplexResampler(rate, Fc=0.1).state()[0] == O.ComplexResampler(rate, Fc=0.1).step
+    lp, dc = L.AmpModem(0.5, "dsb", True).taps(); lpo, dco = O.AmpModem(0.5, "dsb", True).taps()
+    assert np.array_equal(lp, lpo) and np.array_equal(dc, dco)
+    assert L.DeemphasisFilter(48000).coeffs() == O.DeemphasisFilter.coeffs(48000)
+    assert L.DeemphasisFilter(44100).coeffs() == O.DeemphasisFilter.coeffs(44100)
+    h = O.firdes_kaiser(64, 0.1, 60.0)
+    assert np.array_equal(L.FIRFilter(h).taps(), h)
+    assert abs(L.FIRFilter(h).freqresponse(0.05) - O.FIRFilter(h).freqresponse(0.05)) < 1e-5
+
+
+def _radio(ch=1):
+    return (L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=ch), L.ComplexResampler(0.024, Fc=0.024, channels=ch),
+            L.AGC(channels=ch), L.AmpModem(0.5, "dsb", True, channels=ch), L.DeemphasisFilter(48000, channels=ch))
+
+
+def test_planner():
+    assert L.Chain(*_radio(), fuse=0).plan() == "seq[iir4] -> seq[resamp] -> seq[agc] -> seq[ampmodem] -> seq[deemph]"
+    assert L.Chain(*_radio(), fuse=1).plan() == "seq[iir4+resamp] -> seq[agc+ampmodem+deemph]"
+    assert L.Chain(*_radio(), fuse=2).plan() == "seq[iir4+resamp+agc+ampmodem+deemph]"
+    assert L.Chain(L.NCO(), L.ComplexResampler(0.024, Fc=0.024)).plan() == "seq[nco+resamp]"
+    assert L.Chain(L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075), L.AGC(), L.FreqDem(0.1)).plan() == "seq[iir4+agc+freqdem]"
+    assert L.Chain(L.ComplexResampler(0.5, Fc=0.2)).plan() == "par[resamp]"          # not decimating enough to fuse
+    assert L.Chain(L.ComplexIIRFilter("butter", "bandpass", order=10, Fc=0.1, F0=0.2)).plan() == "seq[iir8] -> seq[iir2]"
+    h = np.ones(8, np.float32)
+    assert L.Chain(L.FIRFilter(h), L.ComplexIIRFilter(order=2), L.FIRFilter(h)).plan() == "fir -> seq[iir1] -> fir"
+    assert L.Chain(*_radio()).out_len(65536) == 1573
+    with pytest.raises(ValueError):                        # real-input stage after a complex-output stage
+        L.Chain(L.ComplexIIRFilter(order=2), L.DeemphasisFilter()).plan()
+    with pytest.raises(ValueError):
+        L.Chain(L.ComplexIIRFilter(order=2, channels=2), L.AGC(channels=3)).plan()
+
+
+def test_argument_checking():
+    with pytest.raises(ValueError):
+        L.ComplexIIRFilter("butter", order=0)
+    with pytest.raises(ValueError):
+        L.ComplexIIRFilter("butter", order=2, Fc=0.7)
+    with pytest.raises(NotImplementedError):
+        L.ComplexIIRFilter("ellip", order=4, Fc=0.1)
+    with pytest.raises(NotImplementedError):
+        L.AmpModem(0.5, "usb", True)
+    with pytest.raises(ValueError):
+        L.ComplexResampler(1e-4, Fc=0.1)
+    with pytest.raises(ValueError):
+        L.FreqDem(-1.0)
+    with pytest.raises(ValueError):
+        L.FIRFilter(np.zeros(0, np.float32))
+    with pytest.raises(ValueError):
+        L.AGC(channels=0)
+    a = L.AGC()
+    with pytest.raises(ValueError):
+        a.bandwidth = 2.0
+    with pytest.raises(ValueError):
+        a.scale = 0.0
+    a.bandwidth = 0.05; a.scale = 0.5; a.threshold = -12.0
+    assert (a.bandwidth, a.scale, a.threshold) == (np.float32(0.05), 0.5, -12.0)
+    a.squelch = True
+    assert a.squelch and a.status == 1
+    a.squelch = False
+    assert a.status == 7
+
+
+def test_no_compute_without_a_gpu():
+    """There is no CPU fallback: with no device every execute fails loudly (skipped where a GPU exists)."""
+    try:
+        if L.device_count() > 0:
+            pytest.skip("a CUDA device is present")
+    except RuntimeError:
+        pass
+    x = np.zeros(64, np.complex64)
+    for obj in (L.ComplexIIRFilter(order=2), L.FIRFilter(np.ones(4, np.float32)), L.ComplexResampler(0.024, Fc=0.024),
+                L.NCO(), L.AGC(), L.AmpModem(0.5, "dsb", True), L.FreqDem(0.1), L.Chain(*_radio())):
+        with pytest.raises(RuntimeError):
+            obj(x)
+    with pytest.raises(RuntimeError):
+        L.DeemphasisFilter()(np.zeros(8, np.float32))
+    with pytest.raises(RuntimeError):
+        L.NCO().freq = 0.1
