@@ -761,6 +761,9 @@ void orc_nco_mix_block_down(orc_nco q, const orc_cf *x, orc_cf *y, unsigned n)
  *  agc_crcf    liquid: src/agc/src/agc.proto.c
  *  reached from: AGC (agc.hpp:10-128)
  * ======================================================================================== */
+static inline float orc_logf_cr(float x) { return (float)log((double)x); }
+static inline float orc_expf_cr(float x) { return (float)exp((double)x); }
+
 struct orc_agc_s {
     float g, scale, bandwidth, alpha, y2_prime;
     int is_locked, squelch_mode;
@@ -809,8 +812,11 @@ void orc_agc_execute(orc_agc q, orc_cf x, orc_cf *y)
     /* (1.0-alpha)*y2_prime + alpha*y2 : the literal 1.0 promotes the first product to double */
     q->y2_prime = (float)FMAD(1.0 - (double)q->alpha, (double)q->y2_prime, (double)(q->alpha * y2));
     if (q->is_locked) { y->re = yr; y->im = yi; return; }           /* returns BEFORE the output scale */
+    /* liquid: g *= expf(-0.5f*alpha*logf(y2_prime)).  The last bit of logf/expf differs between C
+     * libraries (glibc, Apple libm, ...), so the reference's own result is platform dependent; the
+     * oracle takes the correctly rounded functions (double evaluation, one rounding to float). */
     if (q->y2_prime > 1e-6f)
-        q->g *= expf(-0.5f * q->alpha * logf(q->y2_prime));
+        q->g *= orc_expf_cr(-0.5f * q->alpha * orc_logf_cr(q->y2_prime));
     if (q->g > 1e6f) q->g = 1e6f;
     agc_squelch_update_mode(q);
     y->re = yr * q->scale; y->im = yi * q->scale;

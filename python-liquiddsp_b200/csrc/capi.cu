@@ -511,26 +511,37 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
     if (n == 0) return LQB_OK;
     const int C = c->stages[0]->C;
     const size_t ib = elem_bytes(c->stages.front()->in_real()), ob = elem_bytes(c->stages.back()->out_real());
-    // channel chunks of about 64 MB of input, three streams: H2D of chunk i+1 overlaps the kernels of chunk i
-    size_t chunk = std::max<size_t>(1, ((size_t)64 << 20) / std::max<size_t>(1, n * ib));
+    // Channel chunks on three streams: the H2D of chunk i+1 overlaps the kernels of chunk i.  A sequential
+    // kernel takes about as long for 64 channels as for 64K (it is bound by the per-channel recurrence), so
+    // chunks are few and large: an eighth of the call, at least 64 MB of input.
+    const size_t in_total = (size_t)C * n * ib;
+    size_t chunk = std::max<size_t>(1, std::max<size_t>((size_t)64 << 20, in_total / 8) / std::max<size_t>(1, n * ib));
     if (chunk >= 64) chunk = chunk / 64 * 64;
     chunk = std::min<size_t>(chunk, (size_t)C);
     for (int s = 0; s < lqb_chain_s::kStreams; s++) if (!c->streams[s]) LQB_CUDA(cudaStreamCreate(&c->streams[s]));
     const size_t nchunks = ((size_t)C + chunk - 1) / chunk;
     const size_t tmpb = max_intermediate_bytes(segs, n, chunk);
+    // A D2H into pageable memory blocks the host, which would serialise the chunks; when the whole output is
+    // small (decimating chains) it stays on the device until every chunk is enqueued and goes back in one copy.
+    const size_t out_total = (size_t)C * on * ob;
+    const bool deferred = out_total <= ((size_t)256 << 20);
+    if (deferred) LQB_TRY(c->h_out[0].reserve(std::max<size_t>(16, out_total)));
     for (size_t s = 0; s < std::min<size_t>(nchunks, lqb_chain_s::kStreams); s++) {
-        LQB_TRY(c->h_in[s].reserve(chunk * n * ib)); LQB_TRY(c->h_out[s].reserve(std::max<size_t>(16, chunk * on * ob)));
+        LQB_TRY(c->h_in[s].reserve(chunk * n * ib));
+        if (!deferred) LQB_TRY(c->h_out[s].reserve(std::max<size_t>(16, chunk * on * ob)));
         if (segs.size() > 1) LQB_TRY(c->h_tmp[s][0].reserve(tmpb));
         if (segs.size() > 2) LQB_TRY(c->h_tmp[s][1].reserve(tmpb));
     }
     for (size_t k = 0; k < nchunks; k++) {
         const int s = (int)(k % lqb_chain_s::kStreams);
         const size_t c0 = k * chunk, nc = std::min(chunk, (size_t)C - c0);
+        char *dst = deferred ? c->h_out[0].p + c0 * on * ob : c->h_out[s].p;
         LQB_CUDA(cudaMemcpyAsync(c->h_in[s].p, (const char *)x + c0 * n * ib, nc * n * ib, cudaMemcpyHostToDevice, c->streams[s]));
-        LQB_TRY(run_all(c, segs, c->h_in[s].p, c->h_out[s].p, n, (int)c0, (int)nc, c->h_tmp[s][0].p, c->h_tmp[s][1].p, c->streams[s], &c->last_launches));
-        if (on) LQB_CUDA(cudaMemcpyAsync((char *)y + c0 * on * ob, c->h_out[s].p, nc * on * ob, cudaMemcpyDeviceToHost, c->streams[s]));
+        LQB_TRY(run_all(c, segs, c->h_in[s].p, dst, n, (int)c0, (int)nc, c->h_tmp[s][0].p, c->h_tmp[s][1].p, c->streams[s], &c->last_launches));
+        if (on && !deferred) LQB_CUDA(cudaMemcpyAsync((char *)y + c0 * on * ob, dst, nc * on * ob, cudaMemcpyDeviceToHost, c->streams[s]));
     }
     for (int s = 0; s < lqb_chain_s::kStreams; s++) LQB_CUDA(cudaStreamSynchronize(c->streams[s]));
+    if (on && deferred) LQB_CUDA(cudaMemcpy(y, c->h_out[0].p, out_total, cudaMemcpyDeviceToHost));
     advance_all(c, n);
     return LQB_OK;
 }

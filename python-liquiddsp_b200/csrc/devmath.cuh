@@ -79,6 +79,9 @@ __device__ __forceinline__ float exp_rn_small(float a)
     return (float)p;
 }
 
+// ln(x) rounded once to float (double-precision library log, then one rounding)
+__device__ __forceinline__ float log_rn(float x) { return (float)log((double)x); }
+
 __device__ __forceinline__ unsigned nco_index(uint32_t theta) { return ((theta + (1u << 21)) >> 22) & 0x3ffu; }
 
 }  // namespace lqb

@@ -58,7 +58,7 @@ resamp_par_kernel(const ResampP p, const float2 *__restrict__ x, float2 *__restr
         const unsigned f = (unsigned)((P & 0xffffffull) >> (24 - p.bits));
         const float *h = s_b + f * L;
         u64 acc = 0ull;
-        for (int i = 0; i < L; i++) acc = fma2(pk(h[i], h[i]), pk(s_x[off + i]), acc);
+        for (int i = 0; i < L; i++) acc = add2(acc, mul2(pk(h[i], h[i]), pk(s_x[off + i])));   // dotprod_cccf order and rounding
         y[ch * n_out + k0 + tid] = upk(acc);
     }
 }

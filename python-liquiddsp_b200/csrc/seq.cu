@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(BT) seq_kernel(const __grid_constant__ SeqArgs
         for (long long j = nnext - (L - 1); j < 0; j++) {
             const int slot = (int)(((long long)a.rs.count + j + 4LL * L) % L);
             const int tap = (int)(j - nnext + L - 1);
-            rs_acc = fma2(pk(s_bank[f * L + tap]), pk(a.rs.ring[slot * CT + gch]), rs_acc);
+            rs_acc = add2(rs_acc, mul2(pk(s_bank[f * L + tap]), pk(a.rs.ring[slot * CT + gch])));
         }
     }
 
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(BT) seq_kernel(const __grid_constant__ SeqArgs
             float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
             agc_y2p = (float)fma(a.agc.one_minus_alpha, (double)agc_y2p, (double)__fmul_rn(a.agc.alpha, y2));
             if (!a.agc.locked) {
-                if (agc_y2p > 1e-6f) agc_g = __fmul_rn(agc_g, exp_rn_small(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), logf(agc_y2p))));
+                if (agc_y2p > 1e-6f) agc_g = __fmul_rn(agc_g, exp_rn_small(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), log_rn(agc_y2p))));
                 if (agc_g > 1e6f) agc_g = 1e6f;
                 if (agc_mode != 7) {
                     const bool ex = (float)(-20.0 * log10((double)agc_g)) > a.agc.threshold;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(BT) seq_kernel(const __grid_constant__ SeqArgs
             const unsigned cnt = rsP >> 24;
             if (cnt < (unsigned)L) {
                 const unsigned f = (rsP & 0xffffffu) >> (24 - a.rs.bits);
-                rs_acc = fma2(pk(s_bank[f * L + (L - 1 - cnt)]), x, rs_acc);
+                rs_acc = add2(rs_acc, mul2(pk(s_bank[f * L + (L - 1 - cnt)]), x));   // cccf: product rounded, then added
             }
             if (n >= a.n - L && active) a.rs.ring[(int)((a.rs.count + n) % L) * CT + gch] = upk(x);
             if (rsP <= 0x00ffffffu) { tail(upk(rs_acc), jtile); rs_acc = 0; rsP += a.rs.step; }
