@@ -179,7 +179,13 @@ struct ResampStage : lqb_stage_s {
     }
     void host_reset() override { phase = 0; count = 0; }
     int clear() override { return ring.zero(); }
-    bool decimating() const { return (uint64_t)step >= ((uint64_t)d.sublen << 24) && d.sublen <= (unsigned)kMaxResampSub; }
+    // the fused sequential path needs output windows that do not overlap and at most one output per
+    // staged tile, with the 32-bit phase arithmetic of the tap stream free of wrap-around
+    bool decimating() const
+    {
+        const uint64_t lo = (uint64_t)std::max<unsigned>(d.sublen, kSeqTS) << 24;
+        return (uint64_t)step >= lo && (uint64_t)step < (1ull << 32) - (1ull << 28) && d.sublen <= (unsigned)kMaxResampSub;
+    }
     size_t out_len(size_t n) const override
     {
         const uint64_t lim = ((uint64_t)n << 24);           // outputs while phase + k*step <= n*2^24 - 1

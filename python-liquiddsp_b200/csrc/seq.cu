@@ -9,10 +9,16 @@
 //
 // Data movement: rows are [channel][time] in HBM, so a thread-per-channel access would be strided
 // by a whole row.  Each CTA of BT channels instead stages [BT x TS] tiles through shared memory
-// with 16-byte cp.async in a NST-deep ring (each warp-wide copy reads whole 128-byte row segments),
+// with 16-byte cp.async, double buffered (each warp-wide copy reads whole 128-byte row segments),
 // and every thread then reads its own row with conflict-free 16-byte shared loads (row pitch is an
 // odd number of 16-byte units).  Full-rate outputs go back the same way; decimated outputs
 // (2.4 % of the samples) are stored directly.
+//
+// Instruction budget: the per-sample loop carries nothing but the arithmetic.  Everything that is the
+// same for all channels -- which polyphase tap multiplies this sample, whether an output falls on it,
+// whether the accumulator restarts -- is worked out once per tile by 16 lanes and left in shared
+// memory as a "tap stream"; load addresses are per-thread constants plus a running offset; bounds
+// checks and the history-ring save exist only in the checked path taken by the last tiles of a call.
 #include <cuda_runtime.h>
 #include <math.h>
 #include "params.h"
@@ -25,90 +31,40 @@ namespace {
 
 constexpr int BT  = kSeqBT;    // channels (threads) per CTA
 constexpr int TS  = kSeqTS;    // samples per tile row
-constexpr int NST = kSeqNST;   // cp.async ring depth
+constexpr int NST = 2;         // double buffer: one tile in flight while one is consumed
 
-template <int ELEM> struct Pitch { static constexpr int v = TS * ELEM + 16; };
-
-// ---- tile movers -------------------------------------------------------------------------------
-template <int ELEM>
-__device__ __forceinline__ void load_tile(const SeqArgs &a, unsigned char *stage, long long t0, int tid)
-{
-    constexpr int CH16 = TS * ELEM / 16;      // 16-byte chunks per row
-    constexpr int EPC  = 16 / ELEM;           // elements per chunk
-    const char *xg = (const char *)a.x;
-#pragma unroll
-    for (int c = tid; c < BT * CH16; c += BT) {
-        const int row = c / CH16, k = c % CH16;
-        const long long e0 = t0 + (long long)k * EPC;
-        const long long ch = (long long)blockIdx.x * BT + row;
-        unsigned char *dst = stage + row * Pitch<ELEM>::v + k * 16;
-        if (ch < a.C && e0 < a.n) {
-            const char *src = xg + (ch * a.n + e0) * ELEM;
-            const long long rem = (a.n - e0) * ELEM;
-            if (a.vec_in) {
-                cp_async16(dst, src, rem >= 16 ? 16 : (int)rem);
-            } else {
-#pragma unroll
-                for (int e = 0; e < EPC; e++) {
-                    if (e0 + e < a.n) {
-                        if (ELEM == 8) ((float2 *)dst)[e] = ((const float2 *)src)[e];
-                        else           ((float *)dst)[e]  = ((const float *)src)[e];
-                    }
-                }
-            }
-        }
-    }
-}
-
-template <int ELEM>
-__device__ __forceinline__ void store_tile(const SeqArgs &a, const unsigned char *tile, long long t0, int tid)
-{
-    constexpr int CH16 = TS * ELEM / 16;
-    constexpr int EPC  = 16 / ELEM;
-    char *yg = (char *)a.y;
-#pragma unroll
-    for (int c = tid; c < BT * CH16; c += BT) {
-        const int row = c / CH16, k = c % CH16;
-        const long long e0 = t0 + (long long)k * EPC;
-        const long long ch = (long long)blockIdx.x * BT + row;
-        const unsigned char *src = tile + row * Pitch<ELEM>::v + k * 16;
-        if (ch < a.C && e0 < a.n) {
-            char *dst = yg + (ch * a.out_pitch + e0) * ELEM;
-            if (a.vec_out && e0 + EPC <= a.n) {
-                *(float4 *)dst = *(const float4 *)src;
-            } else {
-#pragma unroll
-                for (int e = 0; e < EPC; e++) {
-                    if (e0 + e < a.n) {
-                        if (ELEM == 8) ((float2 *)dst)[e] = ((const float2 *)src)[e];
-                        else           ((float *)dst)[e]  = ((const float *)src)[e];
-                    }
-                }
-            }
-        }
-    }
-}
+template <int ELEM> struct Geo {
+    static constexpr int PITCH = TS * ELEM + 16;      // odd multiple of 16 bytes
+    static constexpr int CH16  = TS * ELEM / 16;      // 16-byte chunks per row == chunks per thread
+    static constexpr int RSTEP = BT / CH16;           // rows between a thread's consecutive chunks
+    static constexpr int EPC   = 16 / ELEM;           // elements per chunk
+};
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <unsigned M, int NSOS>
-__global__ void __launch_bounds__(BT) seq_kernel(const __grid_constant__ SeqArgs a)
+__global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __grid_constant__ SeqArgs a)
 {
     constexpr bool HAS_NCO = (M & F_NCO) != 0, HAS_IIR = (M & F_IIR) != 0, HAS_RS = (M & F_RS) != 0;
     constexpr bool HAS_AGC = (M & F_AGC) != 0, HAS_AM = (M & F_AM) != 0, HAS_FM = (M & F_FM) != 0;
     constexpr bool HAS_DE = (M & F_DE) != 0, IN_REAL = (M & F_INREAL) != 0;
     constexpr bool OUT_REAL = HAS_AM || HAS_FM || IN_REAL;
     constexpr int  IELEM = IN_REAL ? 4 : 8, OELEM = OUT_REAL ? 4 : 8;
-    constexpr int  PIN = Pitch<IELEM>::v, POUT = Pitch<OELEM>::v;
+    using GI = Geo<IELEM>; using GO = Geo<OELEM>;
+    constexpr int  PIN = GI::PITCH, POUT = GO::PITCH;
     constexpr int  NS = NSOS > 0 ? NSOS : 1;
-    constexpr int  UNR = HAS_AM ? 1 : TS / 2;      // the ampmodem body is large: keep one copy of it
+    constexpr bool BIG_TAIL = HAS_AM;               // keep one copy of the ampmodem body
     static_assert(HAS_IIR == (NSOS > 0), "section count and mask disagree");
 
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char *s_in  = smem;                                   // NST stages of [BT][PIN]
+    unsigned char *s_in  = smem;                                   // 2 stages of [BT][PIN]
     unsigned char *s_out = s_in + NST * BT * PIN;                  // [BT][POUT] when the output is full rate
     unsigned char *s_nxt = s_out + (HAS_RS ? 0 : BT * POUT);
-    float2 *s_bank = (float2 *)s_nxt;                              // duplicated taps (h, h)
-    s_nxt += HAS_RS ? (size_t)a.rs.npfb * a.rs.sublen * sizeof(float2) : 0;
+    float4 *s_tap = (float4 *)s_nxt;                               // [2][TS] (tap, tap, keep, keep)
+    s_nxt += HAS_RS ? NST * TS * sizeof(float4) : 0;
+    int *s_emit = (int *)s_nxt;                                    // [2] sample of the tile an output falls on, or -1
+    s_nxt += HAS_RS ? 16 : 0;
+    float *s_bank = (float *)s_nxt;                                // [npfb][sublen]
+    s_nxt += HAS_RS ? (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15) : 0;
     float2 *s_sincos = (float2 *)s_nxt;                            // oscillator table, full-rate mixing only
     s_nxt += HAS_NCO ? 1024 * sizeof(float2) : 0;
     float2 *s_lpr = (float2 *)s_nxt;                               // ampmodem rings [kAmRing][BT]
@@ -120,11 +76,12 @@ __global__ void __launch_bounds__(BT) seq_kernel(const __grid_constant__ SeqArgs
     const bool active = chl < a.C;
     const long long gch = a.ch0 + (active ? chl : 0);              // index into the state arrays
     const long long CT = a.Ctot;
+    const long long N = a.n;
 
     // ---- per-channel state into registers ----
     uint32_t nco_theta = 0, nco_dtheta = 0;
     u64 iv1[NS], iv2[NS], ca1[NS], ca2[NS], cb0[NS], cb1[NS], cb2[NS];
-    u64 rs_acc = 0; uint32_t rsP = a.rs.phase;
+    u64 rs_acc = 0;
     float agc_g = 1.f, agc_y2p = 1.f; int agc_mode = 7; unsigned agc_timer = 0, agc_rises = 0;
     uint32_t am_theta = 0, am_dtheta = 0, am_cnt = a.am.count;
     float2 fm_prev = make_float2(0.f, 0.f);
@@ -146,7 +103,7 @@ __global__ void __launch_bounds__(BT) seq_kernel(const __grid_constant__ SeqArgs
     }
     if constexpr (HAS_RS) {
         const int nb = a.rs.npfb * a.rs.sublen;
-        for (int i = tid; i < nb; i += BT) { float h = a.rs.bank[i]; s_bank[i] = make_float2(h, h); }
+        for (int i = tid; i < nb; i += BT) s_bank[i] = a.rs.bank[i];
     }
     if constexpr (HAS_AGC) {
         agc_g = a.agc.g[gch]; agc_y2p = a.agc.y2p[gch]; agc_mode = a.agc.mode[gch]; agc_timer = a.agc.timer[gch];
@@ -163,18 +120,113 @@ __global__ void __launch_bounds__(BT) seq_kernel(const __grid_constant__ SeqArgs
     __syncthreads();
 
     // resampler: the first output's window may start before this call; that part comes from the ring
+    // (dotprod_cccf arithmetic throughout: each product is rounded, then added -- oldest sample first)
+    const int L = HAS_RS ? a.rs.sublen : 0;
     if constexpr (HAS_RS) {
-        const int L = a.rs.sublen;
-        const long long nnext = rsP >> 24;
-        const unsigned f = (rsP & 0xffffffu) >> (24 - a.rs.bits);
+        const long long nnext = a.rs.phase >> 24;
+        const unsigned f = (a.rs.phase & 0xffffffu) >> (24 - a.rs.bits);
+        float ar = 0.f, ai = 0.f;
         for (long long j = nnext - (L - 1); j < 0; j++) {
             const int slot = (int)(((long long)a.rs.count + j + 4LL * L) % L);
-            const int tap = (int)(j - nnext + L - 1);
-            rs_acc = add2(rs_acc, mul2(pk(s_bank[f * L + tap]), pk(a.rs.ring[slot * CT + gch])));
+            const float h = s_bank[f * L + (int)(j - nnext + L - 1)];
+            const float2 w = a.rs.ring[slot * CT + gch];
+            ar = __fadd_rn(ar, __fmul_rn(h, w.x)); ai = __fadd_rn(ai, __fmul_rn(h, w.y));
         }
+        rs_acc = pk(ar, ai);
     }
 
-    // ---- what happens to one sample of the chain's decimated/demodulated side ----
+    // ---- the tap stream: lanes 0..TS-1 of warp 0 each follow one sample position of every tile ----
+    // gP = resampler phase (8.24) at this lane's sample of the tile being generated, liquid's own
+    // recurrence: an output falls on a sample iff P <= 0xffffff (then P += step); P -= 2^24 per sample.
+    uint32_t gP = a.rs.phase;
+    if constexpr (HAS_RS) {
+        if (tid < TS) for (int i = 0; i < tid; i++) { if (gP <= 0x00ffffffu) gP += a.rs.step; gP -= (1u << 24); }
+    }
+    auto gen_taps = [&](int stage, bool first_tile) {
+        if constexpr (HAS_RS) {
+            if (tid < 32) {
+                const bool lane_on = tid < TS;
+                const bool emit = lane_on && gP <= 0x00ffffffu;
+                if (lane_on) {
+                    const unsigned cnt = gP >> 24;
+                    const unsigned f = (gP & 0xffffffu) >> (24 - a.rs.bits);
+                    const float h = cnt < (unsigned)L ? s_bank[f * L + (L - 1 - (int)cnt)] : 0.f;
+                    // the sample after an output starts a new dot product: its accumulator is multiplied by 0
+                    // (never the first sample of a call: there the accumulator holds the ring's contribution)
+                    const float keep = (gP < a.rs.step - (1u << 24) || (first_tile && tid == 0)) ? 1.f : 0.f;
+                    s_tap[stage * TS + tid] = make_float4(h, h, keep, keep);
+                    // advance one tile (step >= TS * 2^24, so at most one output per tile)
+                    if (gP < ((unsigned)TS << 24)) gP += a.rs.step;
+                    gP -= ((unsigned)TS << 24);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, emit);
+                if (tid == 0) s_emit[stage] = m ? (__ffs(m) - 1) : -1;
+            }
+        }
+    };
+
+    // ---- tile loads: per-thread constants + a running byte offset ----
+    // thread -> chunk column lk of rows lrow0 + i*RSTEP; rows past the last channel are skipped
+    const int lk = tid % GI::CH16, lrow0 = tid / GI::CH16;
+    unsigned vmask = 0;
+#pragma unroll
+    for (int i = 0; i < GI::CH16; i++)
+        if ((long long)blockIdx.x * BT + lrow0 + i * GI::RSTEP < a.C) vmask |= 1u << i;
+    const char *gsrc = (const char *)a.x + (((long long)blockIdx.x * BT + lrow0) * N + (long long)lk * GI::EPC) * IELEM;
+    const long long grow = (long long)GI::RSTEP * N * IELEM;      // bytes between this thread's rows
+    const unsigned sdst0 = (unsigned)__cvta_generic_to_shared(s_in) + lrow0 * PIN + lk * 16;
+
+    auto load_tile = [&](long long t, int stage) {
+        const long long e0 = t * TS + (long long)lk * GI::EPC;    // first element of this thread's chunks
+        const char *src = gsrc + t * (TS * IELEM);
+        if (a.vec_in) {
+            const unsigned dst = sdst0 + stage * (BT * PIN);
+            const long long rem = (N - e0) * IELEM;
+            const int nb = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+            if (nb > 0) {
+#pragma unroll
+                for (int i = 0; i < GI::CH16; i++)
+                    if ((vmask >> i) & 1u)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::
+                                     "r"(dst + i * (GI::RSTEP * PIN)), "l"(src + i * grow), "r"(nb) : "memory");
+            }
+        } else {
+            unsigned char *d = s_in + stage * (BT * PIN) + lrow0 * PIN + lk * 16;
+#pragma unroll
+            for (int i = 0; i < GI::CH16; i++)
+                if ((vmask >> i) & 1u)
+                    for (int e = 0; e < GI::EPC; e++)
+                        if (e0 + e < N) {
+                            if (IELEM == 8) ((float2 *)(d + i * (GI::RSTEP * PIN)))[e] = ((const float2 *)(src + i * grow))[e];
+                            else            ((float *)(d + i * (GI::RSTEP * PIN)))[e]  = ((const float *)(src + i * grow))[e];
+                        }
+        }
+    };
+
+    // full-rate output tile back to HBM, same chunk geometry
+    const int ok = tid % GO::CH16, orow0 = tid / GO::CH16;
+    auto store_tile = [&](long long t) {
+        const long long e0 = t * TS + (long long)ok * GO::EPC;
+#pragma unroll
+        for (int i = 0; i < GO::CH16; i++) {
+            const long long ch = (long long)blockIdx.x * BT + orow0 + i * GO::RSTEP;
+            if (ch < a.C && e0 < N) {
+                const unsigned char *src = s_out + (orow0 + i * GO::RSTEP) * POUT + ok * 16;
+                char *dst = (char *)a.y + (ch * a.out_pitch + e0) * OELEM;
+                if (a.vec_out && e0 + GO::EPC <= N) {
+                    *(float4 *)dst = *(const float4 *)src;
+                } else {
+                    for (int e = 0; e < GO::EPC; e++)
+                        if (e0 + e < N) {
+                            if (OELEM == 8) ((float2 *)dst)[e] = ((const float2 *)src)[e];
+                            else            ((float *)dst)[e]  = ((const float *)src)[e];
+                        }
+                }
+            }
+        }
+    };
+
+    // ---- what happens to one sample on the decimated / demodulated side of the chain ----
     auto tail = [&](float2 z, int jtile) {
         float r = 0.f;
         if constexpr (HAS_AGC) {
@@ -267,8 +319,8 @@ __global__ void __launch_bounds__(BT) seq_kernel(const __grid_constant__ SeqArgs
         }
     };
 
-    // ---- one full-rate input sample ----
-    auto front = [&](float2 xin, long long n, int jtile) {
+    // ---- one full-rate sample: oscillator and IIR; returns the (complex) value handed on ----
+    auto head = [&](float2 xin) -> u64 {
         u64 x = pk(xin);
         if constexpr (HAS_NCO) {
             float2 sc;
@@ -290,65 +342,88 @@ __global__ void __launch_bounds__(BT) seq_kernel(const __grid_constant__ SeqArgs
                 iv2[s] = iv1[s]; iv1[s] = v0; x = y;
             }
         }
-        if constexpr (HAS_RS) {
-            // resamp_execute with step >= sublen * 2^24: the windows of consecutive outputs do not
-            // overlap, so the dot product of the pending output accumulates as its samples go by.
-            const int L = a.rs.sublen;
-            const unsigned cnt = rsP >> 24;
-            if (cnt < (unsigned)L) {
-                const unsigned f = (rsP & 0xffffffu) >> (24 - a.rs.bits);
-                rs_acc = add2(rs_acc, mul2(pk(s_bank[f * L + (L - 1 - cnt)]), x));   // cccf: product rounded, then added
-            }
-            if (n >= a.n - L && active) a.rs.ring[(int)((a.rs.count + n) % L) * CT + gch] = upk(x);
-            if (rsP <= 0x00ffffffu) { tail(upk(rs_acc), jtile); rs_acc = 0; rsP += a.rs.step; }
-            rsP -= (1u << 24);
-        } else {
-            tail(upk(x), jtile);
-        }
+        return x;
     };
+    // resampler step for one sample: acc = acc*keep + round(tap*x).  keep is 1 (0 right after an
+    // output) and comes from shared memory, so the two roundings of liquid's complex-tap dot product
+    // (product, then sum) survive as FMUL2 + FFMA2; ptxas contracts a plain mul.f32x2 + add.f32x2 pair
+    // into one FFMA2 even with .rn and -fmad=false.
+    auto rs_step = [&](u64 x, const float4 tk) { rs_acc = fma2(rs_acc, pk(tk.z, tk.w), mul2(pk(tk.x, tk.y), x)); };
 
     // ---- stream the tiles ----
-    const long long ntiles = (a.n + TS - 1) / TS;
-    for (int p = 0; p < NST - 1; p++) {
-        if (p < ntiles) load_tile<IELEM>(a, s_in + p * BT * PIN, (long long)p * TS, tid);
-        cp_async_commit();
-    }
+    const long long ntiles = (N + TS - 1) / TS;
+    // tiles [0, nfast) are complete and need no ring save; the rest take the checked path
+    const long long nfast = HAS_RS ? ((N - L) > 0 ? (N - L) / TS : 0) : N / TS;
+    load_tile(0, 0);
+    gen_taps(0, true);
+    cp_async_commit();
     for (long long t = 0; t < ntiles; t++) {
-        const long long tn = t + NST - 1;
-        if (tn < ntiles) load_tile<IELEM>(a, s_in + (int)(tn % NST) * BT * PIN, tn * TS, tid);
+        const int stage = (int)(t & 1);
+        cp_async_wait<0>();
+        __syncthreads();                       // tile t is in shared memory; everyone is done with tile t-1
+        if (t + 1 < ntiles) { load_tile(t + 1, stage ^ 1); gen_taps(stage ^ 1, false); }
         cp_async_commit();
-        cp_async_wait<NST - 1>();
-        __syncthreads();
-        const unsigned char *row = s_in + (int)(t % NST) * BT * PIN + tid * PIN;
-        const long long n0 = t * TS;
-        const int nv = (int)((a.n - n0) < TS ? (a.n - n0) : TS);
-        if (nv == TS) {
+        const unsigned char *row = s_in + stage * (BT * PIN) + tid * PIN;
+        const float4 *tk = s_tap + stage * TS;
+        int e = -1;
+        if constexpr (HAS_RS) e = s_emit[stage];
+        if (t < nfast) {
             if constexpr (IN_REAL) {
 #pragma unroll
                 for (int j = 0; j < TS; j += 4) {
                     const float4 v = *(const float4 *)(row + j * 4);
-                    front(make_float2(v.x, 0.f), n0 + j, j);     front(make_float2(v.y, 0.f), n0 + j + 1, j + 1);
-                    front(make_float2(v.z, 0.f), n0 + j + 2, j + 2); front(make_float2(v.w, 0.f), n0 + j + 3, j + 3);
+                    tail(make_float2(v.x, 0.f), j);     tail(make_float2(v.y, 0.f), j + 1);
+                    tail(make_float2(v.z, 0.f), j + 2); tail(make_float2(v.w, 0.f), j + 3);
                 }
-            } else {
-#pragma unroll UNR
+            } else if constexpr (HAS_RS && !BIG_TAIL) {
+#pragma unroll
                 for (int j = 0; j < TS; j += 2) {
                     const float4 v = *(const float4 *)(row + j * 8);
-                    front(make_float2(v.x, v.y), n0 + j, j);
-                    front(make_float2(v.z, v.w), n0 + j + 1, j + 1);
+                    rs_step(head(make_float2(v.x, v.y)), tk[j]);
+                    if (j == e) tail(upk(rs_acc), j);
+                    rs_step(head(make_float2(v.z, v.w)), tk[j + 1]);
+                    if (j + 1 == e) tail(upk(rs_acc), j + 1);
+                }
+            } else if constexpr (HAS_RS) {
+#pragma unroll 1
+                for (int j = 0; j < TS; j++) {
+                    rs_step(head(*(const float2 *)(row + j * 8)), tk[j]);
+                    if (j == e) tail(upk(rs_acc), j);
+                }
+            } else if constexpr (BIG_TAIL) {
+#pragma unroll 1
+                for (int j = 0; j < TS; j++) tail(upk(head(*(const float2 *)(row + j * 8))), j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < TS; j += 2) {
+                    const float4 v = *(const float4 *)(row + j * 8);
+                    tail(upk(head(make_float2(v.x, v.y))), j);
+                    tail(upk(head(make_float2(v.z, v.w))), j + 1);
                 }
             }
         } else {
+            const long long n0 = t * TS;
+            const int nv = (int)((N - n0) < TS ? (N - n0) : TS);
+#pragma unroll 1
             for (int j = 0; j < nv; j++) {
-                if constexpr (IN_REAL) front(make_float2(*(const float *)(row + j * 4), 0.f), n0 + j, j);
-                else                   front(*(const float2 *)(row + j * 8), n0 + j, j);
+                if constexpr (IN_REAL) {
+                    tail(make_float2(*(const float *)(row + j * 4), 0.f), j);
+                } else {
+                    const u64 x = head(*(const float2 *)(row + j * 8));
+                    if constexpr (HAS_RS) {
+                        rs_step(x, tk[j]);
+                        if (n0 + j >= N - L && active) a.rs.ring[(int)((a.rs.count + n0 + j) % L) * CT + gch] = upk(x);
+                        if (j == e) tail(upk(rs_acc), j);
+                    } else {
+                        tail(upk(x), j);
+                    }
+                }
             }
         }
         if constexpr (!HAS_RS) {
             __syncthreads();
-            store_tile<OELEM>(a, s_out, n0, tid);
+            store_tile(t);
         }
-        __syncthreads();
     }
 
     // ---- carried state back to HBM ----
@@ -411,7 +486,7 @@ size_t smem_bytes(unsigned m, const SeqArgs &a)
     const int pin = TS * (in_real ? 4 : 8) + 16, pout = TS * (out_real ? 4 : 8) + 16;
     size_t b = (size_t)NST * BT * pin;
     if (!(m & F_RS)) b += (size_t)BT * pout;
-    if (m & F_RS)  b += (size_t)a.rs.npfb * a.rs.sublen * sizeof(float2);
+    if (m & F_RS)  b += NST * TS * sizeof(float4) + 16 + (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15);
     if (m & F_NCO) b += 1024 * sizeof(float2);
     if (m & F_AM)  b += (size_t)kAmRing * BT * (sizeof(float2) + sizeof(float));
     return b;

@@ -7,7 +7,6 @@ namespace lqb {
 
 constexpr int kSeqBT  = 64;   // channels per CTA
 constexpr int kSeqTS  = 16;   // samples per staged tile row (128 B of complex64 per channel)
-constexpr int kSeqNST = 2;    // cp.async ring depth (one tile in flight while one is consumed)
 
 // true when a kernel for this stage mask / section count was compiled
 bool seq_supported(unsigned mask, int nsos);

@@ -356,7 +356,7 @@ def test_batched_amradio_vs_oracle_subset(cuda):
     y = np.concatenate(outs, axis=1)
     for c, (_, parts) in orr.items():
         assert rel_l2(y[c], np.concatenate(parts)) <= TOL_E2E, c
-    assert np.std(y[0][4000:]) > 1e-4                    # there is audio
+    assert np.std(y[0][1500:]) > 1e-4                    # there is audio
 
 
 def test_config3_nco_resampler(cuda):
