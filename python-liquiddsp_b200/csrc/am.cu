@@ -1,0 +1,232 @@
+// am.cu -- the decimated-rate tail of the AM receiver: [AGC ->] ampmodem (DSB) [-> de-emphasis].
+//
+// Stands in for the reference's per-sample loops AGC::execute (agc.hpp:109-128),
+// ampmodem_demodulate_block (demod.hpp:294) and DeemphasisFilter::execute (iirfilter.hpp:384-391).
+// The AGC and the carrier PLL are nonlinear feedback loops, so one thread owns one channel and walks
+// it in time; what can be restructured without touching the arithmetic is everything around them:
+//   * samples are taken G = 8 at a time: AGC x8, lowpass FIR x8, PLL x8, DC-block FIR x8, de-emphasis x8.
+//     The two 51-tap FIRs are feed-forward, so the 8 outputs of a group share every window load
+//     (58 loads feed 8 x 51 multiply-adds) and give the scheduler 8 independent accumulation chains.
+//     Each output still sums its taps oldest-first into one accumulator: bit-identical to the
+//     sample-by-sample order;
+//   * the windows are linear per-thread columns in shared memory (no ring index arithmetic); they slide
+//     after every two groups.  A thread touches only its own column, so the sample loop has no barrier;
+//   * input arrives time-major [sample][channel] from the full-rate kernel (coalesced 8-byte loads, no
+//     staging) or row-major from a caller; output goes out 8 floats (one 32-byte sector) per thread.
+// Between calls the windows live in the 64-slot rings of params.h, indexed by absolute sample count.
+#include <cuda_runtime.h>
+#include <math.h>
+#include "params.h"
+#include "devmath.cuh"
+#include "am.h"
+
+namespace lqb {
+namespace {
+
+constexpr int BT = kAmBT;
+constexpr int G  = 8;                // samples per register-blocked group
+constexpr int NG = 2;                // groups between window slides
+constexpr int H  = kAmTaps - 1;      // history samples a window needs: 50
+constexpr int W  = H + NG * G;       // window length: 66
+
+template <bool HAS_AGC, bool HAS_DE>
+__global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ AmTailArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2 *s_lp  = (float2 *)smem;                       // [W][BT]
+    float  *s_dc  = (float *)(s_lp + W * BT);             // [W][BT]
+    float  *s_sin = s_dc + W * BT;                        // [1024]
+
+    const int tid = threadIdx.x;
+    const long long chl = (long long)blockIdx.x * BT + tid;
+    const bool active = chl < a.C;
+    const long long cl = active ? chl : 0;                // inactive lanes shadow channel 0 and store nothing
+    const long long gch = a.ch0 + cl;
+    const long long CT = a.Ctot, N = a.n;
+
+    for (int i = tid; i < 1024; i += BT) s_sin[i] = a.am.sincos[i].x;
+    float agc_g = 1.f, agc_y2p = 1.f; int agc_mode = 7; unsigned agc_timer = 0, agc_rises = 0;
+    if (HAS_AGC) { agc_g = a.agc.g[gch]; agc_y2p = a.agc.y2p[gch]; agc_mode = a.agc.mode[gch]; agc_timer = a.agc.timer[gch]; }
+    uint32_t theta = a.am.theta[gch], dtheta = a.am.dtheta[gch];
+    float de_v1 = HAS_DE ? a.de.v1[gch] : 0.f;
+    // history: the H samples before this call, oldest first, from the rings
+    float2 *lp = s_lp + tid; float *dc = s_dc + tid;
+    if (!a.am.suppressed) {
+        for (int i = 0; i < H; i++) {
+            const unsigned slot = (a.am.count + (unsigned)(kAmRing - H) + i) & (kAmRing - 1);
+            lp[i * BT] = a.am.lp_ring[slot * CT + gch];
+            dc[i * BT] = a.am.dc_ring[slot * CT + gch];
+        }
+    }
+    __syncthreads();                                      // the sine table; the only barrier
+
+    auto load_x = [&](long long k) -> float2 {
+        return a.in_tmajor ? a.x[k * a.in_pitch + cl] : a.x[cl * a.in_pitch + k];
+    };
+    auto agc_step = [&](float2 z) -> float2 {
+        // agc_crcf_execute (liquid agc.proto.c) then the wrapper's status poll, agc.hpp:115-125
+        float yr = __fmul_rn(z.x, agc_g), yi = __fmul_rn(z.y, agc_g);
+        const float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
+        agc_y2p = (float)fma(a.agc.one_minus_alpha, (double)agc_y2p, (double)__fmul_rn(a.agc.alpha, y2));
+        if (!a.agc.locked) {
+            if (agc_y2p > 1e-6f) agc_g = __fmul_rn(agc_g, exp_rn_small(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), log_rn(agc_y2p))));
+            if (agc_g > 1e6f) agc_g = 1e6f;
+            if (agc_mode != 7) {
+                const bool ex = (float)(-20.0 * log10((double)agc_g)) > a.agc.threshold;
+                const int before = agc_mode;
+                switch (agc_mode) {
+                case 1: agc_mode = ex ? 2 : 1; break;
+                case 2: agc_mode = ex ? 3 : 4; break;
+                case 3: agc_mode = ex ? 3 : 4; break;
+                case 4: agc_timer = a.agc.timeout; agc_mode = ex ? 3 : 5; break;
+                case 5: agc_timer--; if (agc_timer == 0) agc_mode = 6; else if (ex) agc_mode = 3; break;
+                case 6: agc_mode = 1; break;
+                default: break;
+                }
+                if (agc_mode == 2 && before != 2) agc_rises++;
+            }
+            yr = __fmul_rn(yr, a.agc.scale); yi = __fmul_rn(yi, a.agc.scale);
+        }
+        if (agc_mode == 5 || agc_mode == 1) { yr = __fmul_rn(yr, 0.0f); yi = __fmul_rn(yi, 0.0f); }
+        return make_float2(yr, yi);
+    };
+    auto nco_sc = [&]() -> float2 {
+        const unsigned idx = nco_index(theta);
+        return make_float2(s_sin[idx], s_sin[(idx + 256) & 0x3ffu]);
+    };
+    auto pll = [&](float pe) {
+        dtheta += nco_constrain_dev(__fmul_rn(pe, a.am.pll_alpha));
+        theta  += nco_constrain_dev(__fmul_rn(pe, a.am.pll_beta));
+        theta  += dtheta;
+    };
+    auto deemph = [&](float r) -> float {
+        if (!HAS_DE) return r;
+        de_v1 = __fmaf_rn(-a.de.a1, de_v1, r);
+        return __fmul_rn(a.de.b0, de_v1);
+    };
+    float *yrow = a.y + cl * a.out_pitch;
+
+    if (a.am.suppressed) {
+        // ampmodem_demod_dsb_pll_costas: no filters, one sample at a time
+        for (long long k = 0; k < N; k++) {
+            float2 z = load_x(k);
+            if (HAS_AGC) z = agc_step(z);
+            const float2 v = mix_down(z, nco_sc());
+            pll(__fmul_rn(v.y, v.x > 0.f ? 1.f : -1.f));
+            const float r = deemph(__fdiv_rn(v.x, a.am.mod_index));
+            if (active) yrow[k] = r;
+        }
+    } else {
+        // ampmodem_demod_dsb_pll_carrier, G samples per pass, NG passes per window slide
+        for (long long kk = 0; kk < N; kk += NG * G) {
+            const int consumed = (int)((N - kk) < NG * G ? (N - kk) : NG * G);
+#pragma unroll 1
+            for (int gi = 0; gi < NG; gi++) {
+                const int ng = consumed - gi * G < G ? consumed - gi * G : G;
+                if (ng <= 0) break;
+                const long long k0 = kk + gi * G;
+                float2 *lw = lp + gi * G * BT; float *dw = dc + gi * G * BT;     // this group's window base
+                float2 z[G];
+#pragma unroll
+                for (int g = 0; g < G; g++) z[g] = g < ng ? load_x(k0 + g) : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    if (HAS_AGC && g < ng) z[g] = agc_step(z[g]);
+                    lw[(H + g) * BT] = z[g];
+                }
+                // lowpass: x0[g] = sum_i lp[i] * window[g + i], i ascending (oldest sample first)
+                float sr[G], si[G];
+#pragma unroll
+                for (int g = 0; g < G; g++) { sr[g] = 0.f; si[g] = 0.f; }
+#pragma unroll
+                for (int i = 0; i < H + G; i++) {
+                    const float2 w = lw[i * BT];
+#pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        const int t = i - g;
+                        if (t >= 0 && t < kAmTaps) { sr[g] = __fmaf_rn(a.am.lp[t], w.x, sr[g]); si[g] = __fmaf_rn(a.am.lp[t], w.y, si[g]); }
+                    }
+                }
+                // carrier PLL on the filtered branch, mix the delayed branch with the same phase
+                float m[G];
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    m[g] = 0.f;
+                    if (g < ng) {
+                        const float2 sc = nco_sc();
+                        const float2 x1 = lw[(H + g - kAmDelay) * BT];
+                        const float2 v0 = mix_down(make_float2(sr[g], si[g]), sc), v1 = mix_down(x1, sc);
+                        pll(v0.y);
+                        m[g] = __fdiv_rn(v1.x, a.am.mod_index);
+                    }
+                    dw[(H + g) * BT] = m[g];
+                }
+                // dc blocker, same blocking
+                float acc[G];
+#pragma unroll
+                for (int g = 0; g < G; g++) acc[g] = 0.f;
+#pragma unroll
+                for (int i = 0; i < H + G; i++) {
+                    const float w = dw[i * BT];
+#pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        const int t = i - g;
+                        if (t >= 0 && t < kAmTaps) acc[g] = __fmaf_rn(a.am.dc[t], w, acc[g]);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) if (g < ng) acc[g] = deemph(acc[g]);
+                if (active) {
+                    float *yo = yrow + k0;
+                    if (ng == G && ((((size_t)yo) & 15) == 0)) {
+                        *(float4 *)yo = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        *(float4 *)(yo + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < G; g++) if (g < ng) yo[g] = acc[g];
+                    }
+                }
+            }
+            // slide both windows by the samples consumed
+            const float2 *ls = lp + consumed * BT; const float *ds = dc + consumed * BT;
+#pragma unroll
+            for (int i = 0; i < H; i++) { lp[i * BT] = ls[i * BT]; dc[i * BT] = ds[i * BT]; }
+        }
+    }
+
+    if (active) {
+        if (HAS_AGC) {
+            a.agc.g[gch] = agc_g; a.agc.y2p[gch] = agc_y2p; a.agc.mode[gch] = agc_mode; a.agc.timer[gch] = agc_timer;
+            if (agc_rises) atomicAdd(a.agc.rise_count, agc_rises);
+        }
+        a.am.theta[gch] = theta; a.am.dtheta[gch] = dtheta;
+        if (HAS_DE) a.de.v1[gch] = de_v1;
+        if (!a.am.suppressed) {
+            // the windows now hold the last H samples; park them in the rings by absolute index
+            const unsigned base = a.am.count + (unsigned)(N % kAmRing) + (unsigned)(kAmRing - H);
+            for (int i = 0; i < H; i++) {
+                const unsigned slot = (base + i) & (kAmRing - 1);
+                a.am.lp_ring[slot * CT + gch] = lp[i * BT];
+                a.am.dc_ring[slot * CT + gch] = dc[i * BT];
+            }
+        }
+    }
+}
+
+typedef void (*AmFn)(const AmTailArgs);
+
+}  // namespace
+
+cudaError_t amtail_launch(bool has_agc, bool has_de, const AmTailArgs &a, cudaStream_t stream)
+{
+    if (a.C <= 0 || a.n <= 0) return cudaSuccess;
+    AmFn fn = has_agc ? (has_de ? amtail_kernel<true, true> : amtail_kernel<true, false>)
+                      : (has_de ? amtail_kernel<false, true> : amtail_kernel<false, false>);
+    const size_t smem = (size_t)W * BT * (sizeof(float2) + sizeof(float)) + 1024 * sizeof(float);
+    cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc != cudaSuccess) return rc;
+    fn<<<(unsigned)((a.C + BT - 1) / BT), BT, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace lqb

@@ -21,6 +21,7 @@
 #include "params.h"
 #include "seq.h"
 #include "fir.h"
+#include "am.h"
 #include "par.h"
 #include "synth.h"
 
@@ -285,7 +286,7 @@ struct FmStage : lqb_stage_s {
 
 // ------------------------------------------------------------------------------------ chain
 struct Segment {
-    enum Type { SEQ, FIR, RESAMP_PAR } type = SEQ;
+    enum Type { SEQ, FIR, RESAMP_PAR, AMTAIL } type = SEQ;
     unsigned mask = 0; int nsos = 0, sos0 = 0;
     std::vector<lqb_stage_s *> st;
     std::string name;
@@ -358,7 +359,8 @@ static bool run_fusable(const std::vector<lqb_stage_s *> &st, size_t i0, size_t 
     }
     // level 1 keeps the ampmodem's shared-memory windows out of the full-rate kernel: they would cut
     // its occupancy four-fold, while the decimated hand-off they avoid is 2.4 % of the traffic
-    if (level < 2 && has_rs && has_am) return false;
+    if (level < 2 && has_am) return false;    // below level 2 the ampmodem always runs in its own tail kernel
+    (void)has_rs;
     int nsos; const unsigned m = run_mask(st, i0, len, &nsos);
     return seq_supported(m, nsos);
 }
@@ -370,6 +372,17 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
     for (size_t i = 0; i < st.size();) {
         Segment g;
         if (st[i]->kind == K_FIR) { g.type = Segment::FIR; g.st = { st[i] }; g.name = "fir"; segs.push_back(g); i++; continue; }
+        // [AGC ->] ampmodem [-> de-emphasis] : the decimated-rate tail kernel (am.cu)
+        if (c->fuse < 2) {
+            size_t j = i; std::string nm;
+            if (c->fuse >= 1 && st[j]->kind == K_AGC && j + 1 < st.size() && st[j + 1]->kind == K_AM) { g.st.push_back(st[j++]); nm = "agc+"; }
+            if (st[j]->kind == K_AM) {
+                g.type = Segment::AMTAIL; g.st.push_back(st[j++]); nm += "ampmodem";
+                if (c->fuse >= 1 && j < st.size() && st[j]->kind == K_DEEMPH) { g.st.push_back(st[j++]); nm += "+deemph"; }
+                g.name = "am[" + nm + "]"; segs.push_back(g); i = j; continue;
+            }
+            g.st.clear();
+        }
         size_t best = 1;
         if (c->fuse) for (size_t len = std::min<size_t>(6, st.size() - i); len >= 2; len--) if (run_fusable(st, i, len, c->fuse)) { best = len; break; }
         if (best == 1) {
@@ -404,9 +417,23 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
 static size_t seg_out_len(const Segment &g, size_t n) { for (auto *s : g.st) n = s->out_len(n); return n; }
 
 // run one segment on channels [ch0, ch0 + nch) of the chain; x/y point at the first of those rows
-static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_t n_out, int ch0, int nch, cudaStream_t stream)
+static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_t n_out, int ch0, int nch, cudaStream_t stream,
+                       bool in_tmajor, bool out_tmajor)
 {
     const lqb_stage_s *first = g.st.front();
+    if (g.type == Segment::AMTAIL) {
+        AmTailArgs a{};
+        bool has_agc = false, has_de = false;
+        a.x = (const float2 *)x; a.y = (float *)y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.in_tmajor = in_tmajor ? 1 : 0;
+        a.n = (long long)n; a.in_pitch = in_tmajor ? (long long)nch : (long long)n; a.out_pitch = (long long)n_out;
+        for (lqb_stage_s *s : g.st) {
+            if (s->kind == K_AGC) { static_cast<AgcStage *>(s)->fill(a.agc); has_agc = true; }
+            else if (s->kind == K_AM) LQB_TRY(static_cast<AmStage *>(s)->fill(a.am));
+            else if (s->kind == K_DEEMPH) { static_cast<DeemphStage *>(s)->fill(a.de); has_de = true; }
+        }
+        LQB_CUDA(amtail_launch(has_agc, has_de, a, stream));
+        return LQB_OK;
+    }
     if (g.type == Segment::FIR) {
         const FirStage *f = static_cast<const FirStage *>(first);
         FirArgs a{};
@@ -423,7 +450,8 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
     }
     SeqArgs a{};
     const bool in_real = (g.mask & F_INREAL) != 0, out_real = (g.mask & (F_AM | F_FM | F_INREAL)) != 0;
-    a.x = x; a.y = y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.n = (long long)n; a.out_pitch = (long long)n_out;
+    a.x = x; a.y = y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.n = (long long)n;
+    a.out_tmajor = out_tmajor ? 1 : 0; a.out_pitch = out_tmajor ? (long long)nch : (long long)n_out;
     a.vec_in  = ((n * (in_real ? 4 : 8)) % 16 == 0) && (((size_t)x) % 16 == 0);
     a.vec_out = ((n_out * (out_real ? 4 : 8)) % 16 == 0) && (((size_t)y) % 16 == 0);
     for (lqb_stage_s *s : g.st) {
@@ -460,13 +488,16 @@ static int chain_validate(lqb_chain_s *c)
 static int run_all(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, void *y, size_t n, int ch0, int nch,
                    char *tmp0, char *tmp1, cudaStream_t stream, int *launches)
 {
-    const void *cur = x; size_t cur_n = n; int flip = 0;
+    const void *cur = x; size_t cur_n = n; int flip = 0; bool in_tm = false;
     for (size_t k = 0; k < segs.size(); k++) {
         const size_t on = seg_out_len(segs[k], cur_n);
         void *dst = (k + 1 == segs.size()) ? y : (void *)(flip ? tmp1 : tmp0);
         // a segment of the same IIR stage split by section offset keeps the sample count
-        if (on > 0 || cur_n > 0) { LQB_TRY(run_segment(segs[k], cur, dst, cur_n, on, ch0, nch, stream)); (*launches)++; }
-        cur = dst; cur_n = on; flip ^= 1;
+        // a decimating sequential kernel hands its output to the AM tail kernel time-major [sample][channel]:
+        // both sides then touch HBM with warp-contiguous accesses and neither needs a staging tile
+        const bool out_tm = k + 1 < segs.size() && segs[k].type == Segment::SEQ && (segs[k].mask & F_RS) && segs[k + 1].type == Segment::AMTAIL;
+        if (on > 0 || cur_n > 0) { LQB_TRY(run_segment(segs[k], cur, dst, cur_n, on, ch0, nch, stream, in_tm, out_tm)); (*launches)++; }
+        cur = dst; cur_n = on; flip ^= 1; in_tm = out_tm;
     }
     (void)c;
     return LQB_OK;

@@ -57,9 +57,14 @@ resamp_par_kernel(const ResampP p, const float2 *__restrict__ x, float2 *__restr
         const int off = (int)((long long)(P >> 24) - (L - 1) - i_lo);
         const unsigned f = (unsigned)((P & 0xffffffull) >> (24 - p.bits));
         const float *h = s_b + f * L;
-        u64 acc = 0ull;
-        for (int i = 0; i < L; i++) acc = add2(acc, mul2(pk(h[i], h[i]), pk(s_x[off + i])));   // dotprod_cccf order and rounding
-        y[ch * n_out + k0 + tid] = upk(acc);
+        // dotprod_cccf order and rounding: product rounded, then added, oldest sample first (scalar intrinsics:
+        // ptxas contracts a packed mul.f32x2 + add.f32x2 pair into FFMA2 even with .rn)
+        float ar = 0.f, ai = 0.f;
+        for (int i = 0; i < L; i++) {
+            const float2 w = s_x[off + i];
+            ar = __fadd_rn(ar, __fmul_rn(h[i], w.x)); ai = __fadd_rn(ai, __fmul_rn(h[i], w.y));
+        }
+        y[ch * n_out + k0 + tid] = make_float2(ar, ai);
     }
 }
 

@@ -74,8 +74,17 @@ struct SeqArgs {
     int ch0;                       // first channel's index into the [.. ][Ctot] state arrays
     int Ctot;                      // channel stride of the state arrays
     int vec_in, vec_out;           // 1 when rows allow 16-byte vector access
+    int out_tmajor;                // decimated output stored [sample][channel] (hand-off to the AM tail kernel)
     long long n, out_pitch;
     NcoP nco; IirP iir; ResampP rs; AgcP agc; AmP am; FmP fm; DeP de;
+};
+
+struct AmTailArgs {
+    const float2 *x;               // input, row-major [C][in_pitch] or time-major [n][in_pitch]
+    float *y;                      // [C][out_pitch]
+    int C, ch0, Ctot, in_tmajor;
+    long long n, in_pitch, out_pitch;
+    AgcP agc; AmP am; DeP de;
 };
 
 struct FirArgs {

@@ -309,8 +309,9 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
         }
         if constexpr (HAS_RS) {
             if (active) {
-                if constexpr (OUT_REAL) ((float *)a.y)[chl * a.out_pitch + kout] = r;
-                else                    ((float2 *)a.y)[chl * a.out_pitch + kout] = z;
+                const long long o = a.out_tmajor ? kout * a.out_pitch + chl : chl * a.out_pitch + kout;
+                if constexpr (OUT_REAL) ((float *)a.y)[o] = r;
+                else                    ((float2 *)a.y)[o] = z;
             }
             kout++;
         } else {
@@ -374,6 +375,38 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                     const float4 v = *(const float4 *)(row + j * 4);
                     tail(make_float2(v.x, 0.f), j);     tail(make_float2(v.y, 0.f), j + 1);
                     tail(make_float2(v.z, 0.f), j + 2); tail(make_float2(v.w, 0.f), j + 3);
+                }
+            } else if constexpr (HAS_RS && !BIG_TAIL && HAS_IIR && !HAS_NCO) {
+                // Biquad cascade, skewed: at step k section s works on sample k-s, so the NS section updates of
+                // one step are independent of each other (each consumes what the previous section produced one
+                // step earlier).  Same operations on the same operands as the sample-by-sample order -- only
+                // the issue order changes, which gives the scheduler NS chains to interleave instead of one.
+                u64 xs[TS];
+#pragma unroll
+                for (int j = 0; j < TS; j += 2) {
+                    const float4 v = *(const float4 *)(row + j * 8);
+                    xs[j] = pk(v.x, v.y); xs[j + 1] = pk(v.z, v.w);
+                }
+                u64 yy[NS];
+#pragma unroll
+                for (int k = 0; k < TS + NS - 1; k++) {
+#pragma unroll
+                    for (int sct = NS - 1; sct >= 0; sct--) {
+                        const int j = k - sct;
+                        if (j >= 0 && j < TS) {
+                            const u64 in = sct == 0 ? xs[j] : yy[sct - 1];
+                            const u64 t  = fma2(ca1[sct], iv1[sct], in);
+                            const u64 v0 = fma2(ca2[sct], iv2[sct], t);
+                            u64 y = mul2(cb1[sct], iv1[sct]);
+                            y = fma2(cb0[sct], v0, y);
+                            y = fma2(cb2[sct], iv2[sct], y);
+                            iv2[sct] = iv1[sct]; iv1[sct] = v0; yy[sct] = y;
+                            if (sct == NS - 1) {
+                                rs_step(y, tk[j]);
+                                if (j == e) tail(upk(rs_acc), j);
+                            }
+                        }
+                    }
                 }
             } else if constexpr (HAS_RS && !BIG_TAIL) {
 #pragma unroll
@@ -459,13 +492,12 @@ struct Entry { unsigned mask; int nsos; SeqFn fn; };
 #define LQB_E_IIR(M) LQB_E(M, 1), LQB_E(M, 2), LQB_E(M, 3), LQB_E(M, 4)
 const Entry kTable[] = {
     // single stages
-    LQB_E(F_NCO, 0), LQB_E(F_RS, 0), LQB_E(F_AGC, 0), LQB_E(F_AM, 0), LQB_E(F_FM, 0), LQB_E(F_DE | F_INREAL, 0),
+    LQB_E(F_NCO, 0), LQB_E(F_RS, 0), LQB_E(F_AGC, 0), LQB_E(F_FM, 0), LQB_E(F_DE | F_INREAL, 0),
     LQB_E_IIR(F_IIR), LQB_E(F_IIR, 5), LQB_E(F_IIR, 6), LQB_E(F_IIR, 7), LQB_E(F_IIR, 8),
     // fused runs
     LQB_E(F_NCO | F_RS, 0),
     LQB_E_IIR(F_IIR | F_RS),
     LQB_E_IIR(F_NCO | F_IIR | F_RS),
-    LQB_E(F_AGC | F_AM, 0), LQB_E(F_AM | F_DE, 0), LQB_E(F_AGC | F_AM | F_DE, 0),
     LQB_E(F_AGC | F_FM, 0), LQB_E(F_FM | F_DE, 0), LQB_E(F_AGC | F_FM | F_DE, 0),
     LQB_E_IIR(F_IIR | F_AGC),
     LQB_E_IIR(F_IIR | F_AGC | F_FM),

@@ -89,8 +89,8 @@ def _radio(ch=1):
 
 
 def test_planner():
-    assert L.Chain(*_radio(), fuse=0).plan() == "seq[iir4] -> seq[resamp] -> seq[agc] -> seq[ampmodem] -> seq[deemph]"
-    assert L.Chain(*_radio(), fuse=1).plan() == "seq[iir4+resamp] -> seq[agc+ampmodem+deemph]"
+    assert L.Chain(*_radio(), fuse=0).plan() == "seq[iir4] -> seq[resamp] -> seq[agc] -> am[ampmodem] -> seq[deemph]"
+    assert L.Chain(*_radio(), fuse=1).plan() == "seq[iir4+resamp] -> am[agc+ampmodem+deemph]"
     assert L.Chain(*_radio(), fuse=2).plan() == "seq[iir4+resamp+agc+ampmodem+deemph]"
     assert L.Chain(L.NCO(), L.ComplexResampler(0.024, Fc=0.024)).plan() == "seq[nco+resamp]"
     assert L.Chain(L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075), L.AGC(), L.FreqDem(0.1)).plan() == "seq[iir4+agc+freqdem]"
