@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     load_tile(0, 0);
     gen_taps(0, true);
     cp_async_commit();
+#pragma unroll 1
     for (long long t = 0; t < ntiles; t++) {
         const int stage = (int)(t & 1);
         cp_async_wait<0>();
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                     const float4 v = *(const float4 *)(row + j * 8);
                     xs[j] = pk(v.x, v.y); xs[j + 1] = pk(v.z, v.w);
                 }
-                u64 yy[NS];
+                u64 yy[NS], outv = 0;
 #pragma unroll
                 for (int k = 0; k < TS + NS - 1; k++) {
 #pragma unroll
@@ -403,20 +404,23 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                             iv2[sct] = iv1[sct]; iv1[sct] = v0; yy[sct] = y;
                             if (sct == NS - 1) {
                                 rs_step(y, tk[j]);
-                                if (j == e) tail(upk(rs_acc), j);
+                                if (j == e) outv = rs_acc;       // at most one output per tile: handed on below
                             }
                         }
                     }
                 }
+                if (e >= 0) tail(upk(outv), e);
             } else if constexpr (HAS_RS && !BIG_TAIL) {
+                u64 outv = 0;
 #pragma unroll
                 for (int j = 0; j < TS; j += 2) {
                     const float4 v = *(const float4 *)(row + j * 8);
                     rs_step(head(make_float2(v.x, v.y)), tk[j]);
-                    if (j == e) tail(upk(rs_acc), j);
+                    if (j == e) outv = rs_acc;
                     rs_step(head(make_float2(v.z, v.w)), tk[j + 1]);
-                    if (j + 1 == e) tail(upk(rs_acc), j + 1);
+                    if (j + 1 == e) outv = rs_acc;
                 }
+                if (e >= 0) tail(upk(outv), e);
             } else if constexpr (HAS_RS) {
 #pragma unroll 1
                 for (int j = 0; j < TS; j++) {
