@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
         }
     } else {
         // ampmodem_demod_dsb_pll_carrier, G samples per pass, NG passes per window slide
+        float2 zn[G];                           // next group's input, fetched one group ahead
+#pragma unroll
+        for (int g = 0; g < G; g++) zn[g] = g < N ? load_x(g) : make_float2(0.f, 0.f);
         for (long long kk = 0; kk < N; kk += NG * G) {
             const int consumed = (int)((N - kk) < NG * G ? (N - kk) : NG * G);
 #pragma unroll 1
@@ -128,23 +131,23 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
                 float2 *lw = lp + gi * G * BT; float *dw = dc + gi * G * BT;     // this group's window base
                 float2 z[G];
 #pragma unroll
-                for (int g = 0; g < G; g++) z[g] = g < ng ? load_x(k0 + g) : make_float2(0.f, 0.f);
+                for (int g = 0; g < G; g++) { z[g] = zn[g]; zn[g] = k0 + G + g < N ? load_x(k0 + G + g) : make_float2(0.f, 0.f); }
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     if (HAS_AGC && g < ng) z[g] = agc_step(z[g]);
                     lw[(H + g) * BT] = z[g];
                 }
                 // lowpass: x0[g] = sum_i lp[i] * window[g + i], i ascending (oldest sample first)
-                float sr[G], si[G];
+                u64 s2[G];                      // (re, im) accumulators: one FFMA2 per tap and output
 #pragma unroll
-                for (int g = 0; g < G; g++) { sr[g] = 0.f; si[g] = 0.f; }
+                for (int g = 0; g < G; g++) s2[g] = 0ull;
 #pragma unroll
                 for (int i = 0; i < H + G; i++) {
-                    const float2 w = lw[i * BT];
+                    const u64 w = pk(lw[i * BT]);
 #pragma unroll
                     for (int g = 0; g < G; g++) {
                         const int t = i - g;
-                        if (t >= 0 && t < kAmTaps) { sr[g] = __fmaf_rn(a.am.lp[t], w.x, sr[g]); si[g] = __fmaf_rn(a.am.lp[t], w.y, si[g]); }
+                        if (t >= 0 && t < kAmTaps) s2[g] = fma2(pk(a.am.lp[t], a.am.lp[t]), w, s2[g]);
                     }
                 }
                 // carrier PLL on the filtered branch, mix the delayed branch with the same phase
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
                     if (g < ng) {
                         const float2 sc = nco_sc();
                         const float2 x1 = lw[(H + g - kAmDelay) * BT];
-                        const float2 v0 = mix_down(make_float2(sr[g], si[g]), sc), v1 = mix_down(x1, sc);
+                        const float2 v0 = mix_down(upk(s2[g]), sc), v1 = mix_down(x1, sc);
                         pll(v0.y);
                         m[g] = __fdiv_rn(v1.x, a.am.mod_index);
                     }
@@ -188,9 +191,16 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
                 }
             }
             // slide both windows by the samples consumed
+            // (loads in batches ahead of the stores: the source lies above everything a batch writes)
             const float2 *ls = lp + consumed * BT; const float *ds = dc + consumed * BT;
 #pragma unroll
-            for (int i = 0; i < H; i++) { lp[i * BT] = ls[i * BT]; dc[i * BT] = ds[i * BT]; }
+            for (int i0 = 0; i0 < H; i0 += 10) {
+                float2 tl[10]; float td[10];
+#pragma unroll
+                for (int i = 0; i < 10; i++) { tl[i] = ls[(i0 + i) * BT]; td[i] = ds[(i0 + i) * BT]; }
+#pragma unroll
+                for (int i = 0; i < 10; i++) { lp[(i0 + i) * BT] = tl[i]; dc[(i0 + i) * BT] = td[i]; }
+            }
         }
     }
 

@@ -31,7 +31,7 @@ namespace {
 
 constexpr int BT  = kSeqBT;    // channels (threads) per CTA
 constexpr int TS  = kSeqTS;    // samples per tile row
-constexpr int NST = 2;         // double buffer: one tile in flight while one is consumed
+constexpr int NST = 3;         // staging ring: two tiles in flight while one is consumed
 
 template <int ELEM> struct Geo {
     static constexpr int PITCH = TS * ELEM + 16;      // odd multiple of 16 bytes
@@ -56,12 +56,12 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     static_assert(HAS_IIR == (NSOS > 0), "section count and mask disagree");
 
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char *s_in  = smem;                                   // 2 stages of [BT][PIN]
+    unsigned char *s_in  = smem;                                   // NST stages of [BT][PIN]
     unsigned char *s_out = s_in + NST * BT * PIN;                  // [BT][POUT] when the output is full rate
     unsigned char *s_nxt = s_out + (HAS_RS ? 0 : BT * POUT);
-    float4 *s_tap = (float4 *)s_nxt;                               // [2][TS] (tap, tap, keep, keep)
-    s_nxt += HAS_RS ? NST * TS * sizeof(float4) : 0;
-    int *s_emit = (int *)s_nxt;                                    // [2] sample of the tile an output falls on, or -1
+    float2 *s_tap = (float2 *)s_nxt;                               // [NST][TS] (tap, keep)
+    s_nxt += HAS_RS ? NST * TS * sizeof(float2) : 0;
+    int *s_emit = (int *)s_nxt;                                    // [NST] sample of the tile an output falls on, or -1
     s_nxt += HAS_RS ? 16 : 0;
     float *s_bank = (float *)s_nxt;                                // [npfb][sublen]
     s_nxt += HAS_RS ? (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15) : 0;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                     // the sample after an output starts a new dot product: its accumulator is multiplied by 0
                     // (never the first sample of a call: there the accumulator holds the ring's contribution)
                     const float keep = (gP < a.rs.step - (1u << 24) || (first_tile && tid == 0)) ? 1.f : 0.f;
-                    s_tap[stage * TS + tid] = make_float4(h, h, keep, keep);
+                    s_tap[stage * TS + tid] = make_float2(h, keep);
                     // advance one tile (step >= TS * 2^24, so at most one output per tile)
                     if (gP < ((unsigned)TS << 24)) gP += a.rs.step;
                     gP -= ((unsigned)TS << 24);
@@ -176,7 +176,21 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     const long long grow = (long long)GI::RSTEP * N * IELEM;      // bytes between this thread's rows
     const unsigned sdst0 = (unsigned)__cvta_generic_to_shared(s_in) + lrow0 * PIN + lk * 16;
 
+    // the common case -- every row of the CTA exists, the tile is complete, rows are 16-byte aligned -- needs no
+    // predicate and no size: eight copies at a running row pointer
+    const bool fast_cta = a.vec_in && (long long)(blockIdx.x + 1) * BT <= (long long)a.C;
+    const long long nfull = N / TS;
+    auto load_tile_fast = [&](long long t, int stage) {
+        const char *src = gsrc + t * (TS * IELEM);
+        const unsigned dst = sdst0 + stage * (BT * PIN);
+#pragma unroll
+        for (int i = 0; i < GI::CH16; i++) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + i * (GI::RSTEP * PIN)), "l"(src) : "memory");
+            src += grow;
+        }
+    };
     auto load_tile = [&](long long t, int stage) {
+        if (fast_cta && t < nfull) { load_tile_fast(t, stage); return; }
         const long long e0 = t * TS + (long long)lk * GI::EPC;    // first element of this thread's chunks
         const char *src = gsrc + t * (TS * IELEM);
         if (a.vec_in) {
@@ -349,24 +363,28 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     // output) and comes from shared memory, so the two roundings of liquid's complex-tap dot product
     // (product, then sum) survive as FMUL2 + FFMA2; ptxas contracts a plain mul.f32x2 + add.f32x2 pair
     // into one FFMA2 even with .rn and -fmad=false.
-    auto rs_step = [&](u64 x, const float4 tk) { rs_acc = fma2(rs_acc, pk(tk.z, tk.w), mul2(pk(tk.x, tk.y), x)); };
+    auto rs_step = [&](u64 x, const float2 tk) { rs_acc = fma2(rs_acc, pk(tk.y, tk.y), mul2(pk(tk.x, tk.x), x)); };
 
     // ---- stream the tiles ----
     const long long ntiles = (N + TS - 1) / TS;
     // tiles [0, nfast) are complete and need no ring save; the rest take the checked path
     const long long nfast = HAS_RS ? ((N - L) > 0 ? (N - L) / TS : 0) : N / TS;
-    load_tile(0, 0);
-    gen_taps(0, true);
-    cp_async_commit();
+    for (int p = 0; p < NST - 1; p++) {
+        if (p < ntiles) { load_tile(p, p); gen_taps(p, p == 0); }
+        cp_async_commit();
+    }
+    int stage = 0;
 #pragma unroll 1
     for (long long t = 0; t < ntiles; t++) {
-        const int stage = (int)(t & 1);
-        cp_async_wait<0>();
+        cp_async_wait<NST - 2>();
         __syncthreads();                       // tile t is in shared memory; everyone is done with tile t-1
-        if (t + 1 < ntiles) { load_tile(t + 1, stage ^ 1); gen_taps(stage ^ 1, false); }
-        cp_async_commit();
+        {
+            const int sn = stage == 0 ? NST - 1 : stage - 1;        // the stage tile t-1 occupied
+            if (t + NST - 1 < ntiles) { load_tile(t + NST - 1, sn); gen_taps(sn, false); }
+            cp_async_commit();
+        }
         const unsigned char *row = s_in + stage * (BT * PIN) + tid * PIN;
-        const float4 *tk = s_tap + stage * TS;
+        const float2 *tk = s_tap + stage * TS;
         int e = -1;
         if constexpr (HAS_RS) e = s_emit[stage];
         if (t < nfast) {
@@ -461,6 +479,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             __syncthreads();
             store_tile(t);
         }
+        stage = stage + 1 == NST ? 0 : stage + 1;
     }
 
     // ---- carried state back to HBM ----
@@ -522,7 +541,7 @@ size_t smem_bytes(unsigned m, const SeqArgs &a)
     const int pin = TS * (in_real ? 4 : 8) + 16, pout = TS * (out_real ? 4 : 8) + 16;
     size_t b = (size_t)NST * BT * pin;
     if (!(m & F_RS)) b += (size_t)BT * pout;
-    if (m & F_RS)  b += NST * TS * sizeof(float4) + 16 + (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15);
+    if (m & F_RS)  b += NST * TS * sizeof(float2) + 16 + (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15);
     if (m & F_NCO) b += 1024 * sizeof(float2);
     if (m & F_AM)  b += (size_t)kAmRing * BT * (sizeof(float2) + sizeof(float));
     return b;
