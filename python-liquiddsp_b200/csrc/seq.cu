@@ -9,9 +9,10 @@
 //
 // Data movement: rows are [channel][time] in HBM, so a thread-per-channel access would be strided
 // by a whole row.  Each CTA of BT channels instead stages [BT x TS] tiles through shared memory
-// with 16-byte cp.async, double buffered (each warp-wide copy reads whole 128-byte row segments),
+// with 16-byte cp.async in a 3-deep ring (each warp-wide copy reads whole 128-byte row segments),
 // and every thread then reads its own row with conflict-free 16-byte shared loads (row pitch is an
-// odd number of 16-byte units).  Full-rate outputs go back the same way; decimated outputs
+// odd number of 16-byte units).  Each warp stages exactly the 32 rows its own lanes consume and keeps
+// its own copy of the tap stream, so the sample loop synchronises warps, never the CTA.  Full-rate outputs go back the same way; decimated outputs
 // (2.4 % of the samples) are stored directly.
 //
 // Instruction budget: the per-sample loop carries nothing but the arithmetic.  Everything that is the
@@ -36,7 +37,7 @@ constexpr int NST = 3;         // staging ring: two tiles in flight while one is
 template <int ELEM> struct Geo {
     static constexpr int PITCH = TS * ELEM + 16;      // odd multiple of 16 bytes
     static constexpr int CH16  = TS * ELEM / 16;      // 16-byte chunks per row == chunks per thread
-    static constexpr int RSTEP = BT / CH16;           // rows between a thread's consecutive chunks
+    static constexpr int RSTEP = 32 / CH16;           // rows between a lane's consecutive chunks (a warp loads its own 32 rows)
     static constexpr int EPC   = 16 / ELEM;           // elements per chunk
 };
 
@@ -59,10 +60,10 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     unsigned char *s_in  = smem;                                   // NST stages of [BT][PIN]
     unsigned char *s_out = s_in + NST * BT * PIN;                  // [BT][POUT] when the output is full rate
     unsigned char *s_nxt = s_out + (HAS_RS ? 0 : BT * POUT);
-    float2 *s_tap = (float2 *)s_nxt;                               // [NST][TS] (tap, keep)
-    s_nxt += HAS_RS ? NST * TS * sizeof(float2) : 0;
-    int *s_emit = (int *)s_nxt;                                    // [NST] sample of the tile an output falls on, or -1
-    s_nxt += HAS_RS ? 16 : 0;
+    float2 *s_tap = (float2 *)s_nxt;                               // [warp][NST][TS] (tap, keep)
+    s_nxt += HAS_RS ? (BT / 32) * NST * TS * sizeof(float2) : 0;
+    int *s_emit = (int *)s_nxt;                                    // [warp][NST] sample of the tile an output falls on, or -1
+    s_nxt += HAS_RS ? 32 : 0;
     float *s_bank = (float *)s_nxt;                                // [npfb][sublen]
     s_nxt += HAS_RS ? (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15) : 0;
     float2 *s_sincos = (float2 *)s_nxt;                            // oscillator table, full-rate mixing only
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     s_nxt += HAS_AM ? (size_t)kAmRing * BT * sizeof(float2) : 0;
     float *s_dcr = (float *)s_nxt;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const long long chl = (long long)blockIdx.x * BT + tid;        // channel within this launch
     const bool active = chl < a.C;
     const long long gch = a.ch0 + (active ? chl : 0);              // index into the state arrays
@@ -135,17 +136,17 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
         rs_acc = pk(ar, ai);
     }
 
-    // ---- the tap stream: lanes 0..TS-1 of warp 0 each follow one sample position of every tile ----
+    // ---- the tap stream: lanes 0..TS-1 of each warp follow one sample position of every tile ----
     // gP = resampler phase (8.24) at this lane's sample of the tile being generated, liquid's own
     // recurrence: an output falls on a sample iff P <= 0xffffff (then P += step); P -= 2^24 per sample.
     uint32_t gP = a.rs.phase;
     if constexpr (HAS_RS) {
-        if (tid < TS) for (int i = 0; i < tid; i++) { if (gP <= 0x00ffffffu) gP += a.rs.step; gP -= (1u << 24); }
+        if (lane < TS) for (int i = 0; i < lane; i++) { if (gP <= 0x00ffffffu) gP += a.rs.step; gP -= (1u << 24); }
     }
     auto gen_taps = [&](int stage, bool first_tile) {
         if constexpr (HAS_RS) {
-            if (tid < 32) {
-                const bool lane_on = tid < TS;
+            {
+                const bool lane_on = lane < TS;
                 const bool emit = lane_on && gP <= 0x00ffffffu;
                 if (lane_on) {
                     const unsigned cnt = gP >> 24;
@@ -153,21 +154,21 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                     const float h = cnt < (unsigned)L ? s_bank[f * L + (L - 1 - (int)cnt)] : 0.f;
                     // the sample after an output starts a new dot product: its accumulator is multiplied by 0
                     // (never the first sample of a call: there the accumulator holds the ring's contribution)
-                    const float keep = (gP < a.rs.step - (1u << 24) || (first_tile && tid == 0)) ? 1.f : 0.f;
-                    s_tap[stage * TS + tid] = make_float2(h, keep);
+                    const float keep = (gP < a.rs.step - (1u << 24) || (first_tile && lane == 0)) ? 1.f : 0.f;
+                    s_tap[(wid * NST + stage) * TS + lane] = make_float2(h, keep);
                     // advance one tile (step >= TS * 2^24, so at most one output per tile)
                     if (gP < ((unsigned)TS << 24)) gP += a.rs.step;
                     gP -= ((unsigned)TS << 24);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, emit);
-                if (tid == 0) s_emit[stage] = m ? (__ffs(m) - 1) : -1;
+                if (lane == 0) s_emit[wid * NST + stage] = m ? (__ffs(m) - 1) : -1;
             }
         }
     };
 
     // ---- tile loads: per-thread constants + a running byte offset ----
     // thread -> chunk column lk of rows lrow0 + i*RSTEP; rows past the last channel are skipped
-    const int lk = tid % GI::CH16, lrow0 = tid / GI::CH16;
+    const int lk = lane % GI::CH16, lrow0 = wid * 32 + lane / GI::CH16;
     unsigned vmask = 0;
 #pragma unroll
     for (int i = 0; i < GI::CH16; i++)
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     };
 
     // full-rate output tile back to HBM, same chunk geometry
-    const int ok = tid % GO::CH16, orow0 = tid / GO::CH16;
+    const int ok = lane % GO::CH16, orow0 = wid * 32 + lane / GO::CH16;
     auto store_tile = [&](long long t) {
         const long long e0 = t * TS + (long long)ok * GO::EPC;
 #pragma unroll
@@ -377,16 +378,16 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
 #pragma unroll 1
     for (long long t = 0; t < ntiles; t++) {
         cp_async_wait<NST - 2>();
-        __syncthreads();                       // tile t is in shared memory; everyone is done with tile t-1
+        __syncwarp();                          // this warp's rows of tile t are in shared memory; its lanes are done with tile t-1
         {
             const int sn = stage == 0 ? NST - 1 : stage - 1;        // the stage tile t-1 occupied
             if (t + NST - 1 < ntiles) { load_tile(t + NST - 1, sn); gen_taps(sn, false); }
             cp_async_commit();
         }
         const unsigned char *row = s_in + stage * (BT * PIN) + tid * PIN;
-        const float2 *tk = s_tap + stage * TS;
+        const float2 *tk = s_tap + (wid * NST + stage) * TS;
         int e = -1;
-        if constexpr (HAS_RS) e = s_emit[stage];
+        if constexpr (HAS_RS) e = s_emit[wid * NST + stage];
         if (t < nfast) {
             if constexpr (IN_REAL) {
 #pragma unroll
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             }
         }
         if constexpr (!HAS_RS) {
-            __syncthreads();
+            __syncwarp();
             store_tile(t);
         }
         stage = stage + 1 == NST ? 0 : stage + 1;
@@ -541,7 +542,7 @@ size_t smem_bytes(unsigned m, const SeqArgs &a)
     const int pin = TS * (in_real ? 4 : 8) + 16, pout = TS * (out_real ? 4 : 8) + 16;
     size_t b = (size_t)NST * BT * pin;
     if (!(m & F_RS)) b += (size_t)BT * pout;
-    if (m & F_RS)  b += NST * TS * sizeof(float2) + 16 + (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15);
+    if (m & F_RS)  b += (BT / 32) * NST * TS * sizeof(float2) + 32 + (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15);
     if (m & F_NCO) b += 1024 * sizeof(float2);
     if (m & F_AM)  b += (size_t)kAmRing * BT * (sizeof(float2) + sizeof(float));
     return b;
