@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
     float2 *s_lp  = (float2 *)smem;                       // [W][BT]
     float  *s_dc  = (float *)(s_lp + W * BT);             // [W][BT]
     float  *s_sin = s_dc + W * BT;                        // [1024]
+    double2 *s_log = (double2 *)(s_sin + 1024);           // [128] (only with the AGC)
 
     const int tid = threadIdx.x;
     const long long chl = (long long)blockIdx.x * BT + tid;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
     const long long CT = a.Ctot, N = a.n;
 
     for (int i = tid; i < 1024; i += BT) s_sin[i] = a.am.sincos[i].x;
+    if (HAS_AGC) for (int i = tid; i < 128; i += BT) s_log[i] = a.agc.logtab[i];
     float agc_g = 1.f, agc_y2p = 1.f; int agc_mode = 7; unsigned agc_timer = 0, agc_rises = 0;
     if (HAS_AGC) { agc_g = a.agc.g[gch]; agc_y2p = a.agc.y2p[gch]; agc_mode = a.agc.mode[gch]; agc_timer = a.agc.timer[gch]; }
     uint32_t theta = a.am.theta[gch], dtheta = a.am.dtheta[gch];
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
         const float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
         agc_y2p = (float)fma(a.agc.one_minus_alpha, (double)agc_y2p, (double)__fmul_rn(a.agc.alpha, y2));
         if (!a.agc.locked) {
-            if (agc_y2p > 1e-6f) agc_g = __fmul_rn(agc_g, exp_rn_small(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), log_rn(agc_y2p))));
+            if (agc_y2p > 1e-6f) agc_g = __fmul_rn(agc_g, exp_rn_small(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), log_rn(agc_y2p, s_log))));
             if (agc_g > 1e6f) agc_g = 1e6f;
             if (agc_mode != 7) {
                 const bool ex = (float)(-20.0 * log10((double)agc_g)) > a.agc.threshold;
@@ -232,7 +234,7 @@ cudaError_t amtail_launch(bool has_agc, bool has_de, const AmTailArgs &a, cudaSt
     if (a.C <= 0 || a.n <= 0) return cudaSuccess;
     AmFn fn = has_agc ? (has_de ? amtail_kernel<true, true> : amtail_kernel<true, false>)
                       : (has_de ? amtail_kernel<false, true> : amtail_kernel<false, false>);
-    const size_t smem = (size_t)W * BT * (sizeof(float2) + sizeof(float)) + 1024 * sizeof(float);
+    const size_t smem = (size_t)W * BT * (sizeof(float2) + sizeof(float)) + 1024 * sizeof(float) + (has_agc ? 128 * sizeof(double2) : 0);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     fn<<<(unsigned)((a.C + BT - 1) / BT), BT, smem, stream>>>(a);

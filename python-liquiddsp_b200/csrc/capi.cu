@@ -92,6 +92,23 @@ static int sincos_table(const float2 **out)
     return LQB_OK;
 }
 
+static std::map<int, double2 *> g_logtab;
+static int log_table_dev(const double2 **out)
+{
+    int dev = 0; LQB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    auto it = g_logtab.find(dev);
+    if (it == g_logtab.end()) {
+        std::vector<double> t = design::log_table();
+        double2 *d = nullptr;
+        LQB_CUDA(cudaMalloc((void **)&d, 128 * sizeof(double2)));
+        LQB_CUDA(cudaMemcpy(d, t.data(), 128 * sizeof(double2), cudaMemcpyHostToDevice));
+        it = g_logtab.emplace(dev, d).first;
+    }
+    *out = it->second;
+    return LQB_OK;
+}
+
 // ------------------------------------------------------------------------------------ stages
 enum Kind { K_NCO = 0, K_IIR, K_RESAMP, K_AGC, K_AM, K_FM, K_DEEMPH, K_FIR };
 
@@ -245,11 +262,13 @@ struct AgcStage : lqb_stage_s {
         LQB_TRY(g.fill(1.0f)); LQB_TRY(y2p.fill(1.0f));
         return mode.fill(squelch ? 1 : 7);
     }
-    void fill(AgcP &p) const
+    int fill(AgcP &p) const
     {
+        LQB_TRY(log_table_dev(&p.logtab));
         p.alpha = alpha; p.scale = scale; p.threshold = threshold; p.one_minus_alpha = 1.0 - (double)alpha;
         p.locked = locked; p.timeout = timeout; p.g = g.p; p.y2p = y2p.p; p.mode = mode.p; p.timer = timer.p;
         p.rise_count = rise.p;
+        return LQB_OK;
     }
 };
 
@@ -427,7 +446,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         a.x = (const float2 *)x; a.y = (float *)y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.in_tmajor = in_tmajor ? 1 : 0;
         a.n = (long long)n; a.in_pitch = in_tmajor ? (long long)nch : (long long)n; a.out_pitch = (long long)n_out;
         for (lqb_stage_s *s : g.st) {
-            if (s->kind == K_AGC) { static_cast<AgcStage *>(s)->fill(a.agc); has_agc = true; }
+            if (s->kind == K_AGC) { LQB_TRY(static_cast<AgcStage *>(s)->fill(a.agc)); has_agc = true; }
             else if (s->kind == K_AM) LQB_TRY(static_cast<AmStage *>(s)->fill(a.am));
             else if (s->kind == K_DEEMPH) { static_cast<DeemphStage *>(s)->fill(a.de); has_de = true; }
         }
@@ -459,7 +478,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         case K_NCO:    LQB_TRY(static_cast<NcoStage *>(s)->fill(a.nco)); break;
         case K_IIR:    static_cast<IirStage *>(s)->fill(a.iir, g.sos0, g.nsos); break;
         case K_RESAMP: static_cast<ResampStage *>(s)->fill(a.rs); break;
-        case K_AGC:    static_cast<AgcStage *>(s)->fill(a.agc); break;
+        case K_AGC:    LQB_TRY(static_cast<AgcStage *>(s)->fill(a.agc)); break;
         case K_AM:     LQB_TRY(static_cast<AmStage *>(s)->fill(a.am)); break;
         case K_FM:     static_cast<FmStage *>(s)->fill(a.fm); break;
         case K_DEEMPH: static_cast<DeemphStage *>(s)->fill(a.de); break;

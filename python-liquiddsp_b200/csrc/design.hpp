@@ -338,6 +338,18 @@ inline void deemph_coeffs(float sample_rate, float &b0, float &a1)
     b0 = (float)(1.0 - (double)x);
 }
 
+// ------------------------------------------------------------------ AGC logarithm table
+// 128 pairs (inv_i, -ln(inv_i)), inv_i = 1/(1 + (i + 0.5)/128) rounded to double; see devmath.cuh log_rn
+inline std::vector<double> log_table()
+{
+    std::vector<double> t(256);
+    for (int i = 0; i < 128; i++) {
+        const double inv = 1.0 / (1.0 + (i + 0.5) / 128.0);
+        t[2 * i] = inv; t[2 * i + 1] = -std::log(inv);
+    }
+    return t;
+}
+
 // ------------------------------------------------------------------ oscillator
 // radians -> 32-bit phase.  float product with 1/(2 pi) held in double, fractional part in float,
 // scale by 2^32 in float; a fractional part that rounds up to 1.0f wraps to 0 (what the x86-64

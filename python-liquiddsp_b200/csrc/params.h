@@ -50,6 +50,7 @@ struct AgcP {
     int *mode;                     // [Ctot] squelch state 0..7
     unsigned *timer;               // [Ctot]
     unsigned *rise_count;          // single counter (atomicAdd)
+    const double2 *logtab;         // device [128] (inv, -ln inv) for the gain update's logarithm
 };
 
 struct AmP {

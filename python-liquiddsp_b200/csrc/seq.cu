@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     s_nxt += HAS_RS ? (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15) : 0;
     float2 *s_sincos = (float2 *)s_nxt;                            // oscillator table, full-rate mixing only
     s_nxt += HAS_NCO ? 1024 * sizeof(float2) : 0;
+    double2 *s_log = (double2 *)s_nxt;                             // AGC logarithm table
+    s_nxt += HAS_AGC ? 128 * sizeof(double2) : 0;
     float2 *s_lpr = (float2 *)s_nxt;                               // ampmodem rings [kAmRing][BT]
     s_nxt += HAS_AM ? (size_t)kAmRing * BT * sizeof(float2) : 0;
     float *s_dcr = (float *)s_nxt;
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
         for (int i = tid; i < nb; i += BT) s_bank[i] = a.rs.bank[i];
     }
     if constexpr (HAS_AGC) {
+        for (int i = tid; i < 128; i += BT) s_log[i] = a.agc.logtab[i];
         agc_g = a.agc.g[gch]; agc_y2p = a.agc.y2p[gch]; agc_mode = a.agc.mode[gch]; agc_timer = a.agc.timer[gch];
     }
     if constexpr (HAS_AM) {
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
             agc_y2p = (float)fma(a.agc.one_minus_alpha, (double)agc_y2p, (double)__fmul_rn(a.agc.alpha, y2));
             if (!a.agc.locked) {
-                if (agc_y2p > 1e-6f) agc_g = __fmul_rn(agc_g, exp_rn_small(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), log_rn(agc_y2p))));
+                if (agc_y2p > 1e-6f) agc_g = __fmul_rn(agc_g, exp_rn_small(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), log_rn(agc_y2p, s_log))));
                 if (agc_g > 1e6f) agc_g = 1e6f;
                 if (agc_mode != 7) {
                     const bool ex = (float)(-20.0 * log10((double)agc_g)) > a.agc.threshold;
@@ -544,6 +547,7 @@ size_t smem_bytes(unsigned m, const SeqArgs &a)
     if (!(m & F_RS)) b += (size_t)BT * pout;
     if (m & F_RS)  b += (BT / 32) * NST * TS * sizeof(float2) + 32 + (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15);
     if (m & F_NCO) b += 1024 * sizeof(float2);
+    if (m & F_AGC) b += 128 * sizeof(double2);
     if (m & F_AM)  b += (size_t)kAmRing * BT * (sizeof(float2) + sizeof(float));
     return b;
 }
