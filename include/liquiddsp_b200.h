@@ -179,6 +179,11 @@ int lqb_chain_execute_dev(lqb_chain c, const void *x_dev, size_t n, void *y_dev,
  * launches the last execute issued */
 int lqb_chain_plan(lqb_chain c, char *buf, size_t buf_len);
 int lqb_chain_last_launches(lqb_chain c, int *n_launches);
+/* Per-segment device timing of lqb_chain_execute_dev: while enabled, every call records one CUDA-event pair per
+ * launch-plan segment on the caller's stream (up to 1024 calls).  get_timing waits for the recorded events and
+ * returns, per segment, the elapsed milliseconds summed over the recorded calls. */
+int lqb_chain_set_timing(lqb_chain c, int enabled);
+int lqb_chain_get_timing(lqb_chain c, float *ms_per_segment, int capacity, int *n_segments, int *n_calls);
 /* 0 = one kernel per stage, 1 = default (full-rate front and decimated tail as two kernels),
  * 2 = longest possible runs (whole AM receiver in one kernel); results are identical */
 int lqb_chain_set_fusion(lqb_chain c, int level);

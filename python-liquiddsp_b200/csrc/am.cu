@@ -225,6 +225,62 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
     }
 }
 
+// AGC alone over a time-major [sample][channel] block, in place.  The gain loop is one long dependent chain per
+// sample (double-precision smoothing, log, exp); on its own it needs no shared-memory windows, so all 2048
+// threads of an SM can be resident and the chains of ~14 warps hide each other.
+__global__ void __launch_bounds__(128) agc_tmajor_kernel(const __grid_constant__ AmTailArgs a)
+{
+    __shared__ double2 s_log[128];
+    const int tid = threadIdx.x;
+    const long long chl = (long long)blockIdx.x * blockDim.x + tid;
+    for (int i = tid; i < 128; i += blockDim.x) s_log[i] = a.agc.logtab[i];
+    __syncthreads();
+    if (chl >= a.C) return;
+    const long long gch = a.ch0 + chl, N = a.n, P = a.in_pitch;
+    float agc_g = a.agc.g[gch], agc_y2p = a.agc.y2p[gch]; int agc_mode = a.agc.mode[gch]; unsigned agc_timer = a.agc.timer[gch], agc_rises = 0;
+    float2 *x = const_cast<float2 *>(a.x) + chl;
+    constexpr int U = 4;
+    float2 zn[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) zn[u] = u < N ? x[u * P] : make_float2(0.f, 0.f);
+    for (long long k0 = 0; k0 < N; k0 += U) {
+        float2 z[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { z[u] = zn[u]; zn[u] = k0 + U + u < N ? x[(k0 + U + u) * P] : make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (k0 + u < N) {
+                float yr = __fmul_rn(z[u].x, agc_g), yi = __fmul_rn(z[u].y, agc_g);
+                const float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
+                agc_y2p = (float)fma(a.agc.one_minus_alpha, (double)agc_y2p, (double)__fmul_rn(a.agc.alpha, y2));
+                if (!a.agc.locked) {
+                    if (agc_y2p > 1e-6f) agc_g = __fmul_rn(agc_g, exp_rn_small(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), log_rn(agc_y2p, s_log))));
+                    if (agc_g > 1e6f) agc_g = 1e6f;
+                    if (agc_mode != 7) {
+                        const bool ex = (float)(-20.0 * log10((double)agc_g)) > a.agc.threshold;
+                        const int before = agc_mode;
+                        switch (agc_mode) {
+                        case 1: agc_mode = ex ? 2 : 1; break;
+                        case 2: agc_mode = ex ? 3 : 4; break;
+                        case 3: agc_mode = ex ? 3 : 4; break;
+                        case 4: agc_timer = a.agc.timeout; agc_mode = ex ? 3 : 5; break;
+                        case 5: agc_timer--; if (agc_timer == 0) agc_mode = 6; else if (ex) agc_mode = 3; break;
+                        case 6: agc_mode = 1; break;
+                        default: break;
+                        }
+                        if (agc_mode == 2 && before != 2) agc_rises++;
+                    }
+                    yr = __fmul_rn(yr, a.agc.scale); yi = __fmul_rn(yi, a.agc.scale);
+                }
+                if (agc_mode == 5 || agc_mode == 1) { yr = __fmul_rn(yr, 0.0f); yi = __fmul_rn(yi, 0.0f); }
+                x[(k0 + u) * P] = make_float2(yr, yi);
+            }
+        }
+    }
+    a.agc.g[gch] = agc_g; a.agc.y2p[gch] = agc_y2p; a.agc.mode[gch] = agc_mode; a.agc.timer[gch] = agc_timer;
+    if (agc_rises) atomicAdd(a.agc.rise_count, agc_rises);
+}
+
 typedef void (*AmFn)(const AmTailArgs);
 
 }  // namespace
@@ -232,6 +288,14 @@ typedef void (*AmFn)(const AmTailArgs);
 cudaError_t amtail_launch(bool has_agc, bool has_de, const AmTailArgs &a, cudaStream_t stream)
 {
     if (a.C <= 0 || a.n <= 0) return cudaSuccess;
+    if (has_agc && a.in_tmajor) {
+        // time-major hand-off buffer (chain-internal scratch): gain control in place at full occupancy, then the
+        // window-bound demodulator without it
+        agc_tmajor_kernel<<<(unsigned)((a.C + 127) / 128), 128, 0, stream>>>(a);
+        cudaError_t rc0 = cudaGetLastError();
+        if (rc0 != cudaSuccess) return rc0;
+        has_agc = false;
+    }
     AmFn fn = has_agc ? (has_de ? amtail_kernel<true, true> : amtail_kernel<true, false>)
                       : (has_de ? amtail_kernel<false, true> : amtail_kernel<false, false>);
     const size_t smem = (size_t)W * BT * (sizeof(float2) + sizeof(float)) + 1024 * sizeof(float) + (has_agc ? 128 * sizeof(double2) : 0);

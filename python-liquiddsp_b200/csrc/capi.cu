@@ -324,7 +324,15 @@ struct lqb_chain_s {
     lqb::DevArr<char> h_in[kStreams], h_out[kStreams], h_tmp[kStreams][2];
     // device-execute scratch
     lqb::DevArr<char> d_tmp[2];
-    ~lqb_chain_s() { for (auto &s : streams) if (s) cudaStreamDestroy(s); }
+    // optional per-segment timing of execute_dev: one event pair per segment per call, on the caller's stream
+    bool timing = false;
+    std::vector<std::vector<std::pair<cudaEvent_t, cudaEvent_t>>> timed_calls;
+    void clear_timing()
+    {
+        for (auto &call : timed_calls) for (auto &p : call) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+        timed_calls.clear();
+    }
+    ~lqb_chain_s() { clear_timing(); for (auto &s : streams) if (s) cudaStreamDestroy(s); }
 };
 
 lqb_stage_s::~lqb_stage_s() { delete self_chain; }
@@ -437,8 +445,9 @@ static size_t seg_out_len(const Segment &g, size_t n) { for (auto *s : g.st) n =
 
 // run one segment on channels [ch0, ch0 + nch) of the chain; x/y point at the first of those rows
 static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_t n_out, int ch0, int nch, cudaStream_t stream,
-                       bool in_tmajor, bool out_tmajor)
+                       bool in_tmajor, bool out_tmajor, int *launches)
 {
+    (*launches)++;
     const lqb_stage_s *first = g.st.front();
     if (g.type == Segment::AMTAIL) {
         AmTailArgs a{};
@@ -451,6 +460,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
             else if (s->kind == K_DEEMPH) { static_cast<DeemphStage *>(s)->fill(a.de); has_de = true; }
         }
         LQB_CUDA(amtail_launch(has_agc, has_de, a, stream));
+        *launches += amtail_launch_count(has_agc, a) - 1;
         return LQB_OK;
     }
     if (g.type == Segment::FIR) {
@@ -465,6 +475,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         const ResampStage *r = static_cast<const ResampStage *>(first);
         ResampP p{}; r->fill(p);
         LQB_CUDA(resamp_par_launch(p, (const float2 *)x, (float2 *)y, nch, ch0, r->C, (long long)n, (long long)n_out, stream));
+        if (n_out > 0) (*launches)++;              // the ring-update kernel
         return LQB_OK;
     }
     SeqArgs a{};
@@ -505,8 +516,13 @@ static int chain_validate(lqb_chain_s *c)
 
 // all segments over channel range [ch0, ch0+nch); tmp0/tmp1 hold intermediates
 static int run_all(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, void *y, size_t n, int ch0, int nch,
-                   char *tmp0, char *tmp1, cudaStream_t stream, int *launches)
+                   char *tmp0, char *tmp1, cudaStream_t stream, int *launches, bool timed = false)
 {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+    if (timed && c->timed_calls.size() < 1024) {
+        evs.resize(segs.size());
+        for (auto &p : evs) { LQB_CUDA(cudaEventCreate(&p.first)); LQB_CUDA(cudaEventCreate(&p.second)); }
+    }
     const void *cur = x; size_t cur_n = n; int flip = 0; bool in_tm = false;
     for (size_t k = 0; k < segs.size(); k++) {
         const size_t on = seg_out_len(segs[k], cur_n);
@@ -515,10 +531,12 @@ static int run_all(lqb_chain_s *c, const std::vector<Segment> &segs, const void 
         // a decimating sequential kernel hands its output to the AM tail kernel time-major [sample][channel]:
         // both sides then touch HBM with warp-contiguous accesses and neither needs a staging tile
         const bool out_tm = k + 1 < segs.size() && segs[k].type == Segment::SEQ && (segs[k].mask & F_RS) && segs[k + 1].type == Segment::AMTAIL;
-        if (on > 0 || cur_n > 0) { LQB_TRY(run_segment(segs[k], cur, dst, cur_n, on, ch0, nch, stream, in_tm, out_tm)); (*launches)++; }
+        if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[k].first, stream));
+        if (on > 0 || cur_n > 0) LQB_TRY(run_segment(segs[k], cur, dst, cur_n, on, ch0, nch, stream, in_tm, out_tm, launches));
+        if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[k].second, stream));
         cur = dst; cur_n = on; flip ^= 1; in_tm = out_tm;
     }
-    (void)c;
+    if (!evs.empty()) c->timed_calls.push_back(std::move(evs));
     return LQB_OK;
 }
 
@@ -550,7 +568,7 @@ static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, s
     const size_t tmpb = max_intermediate_bytes(segs, n, (size_t)C);
     if (segs.size() > 1) LQB_TRY(c->d_tmp[0].reserve(tmpb));
     if (segs.size() > 2) LQB_TRY(c->d_tmp[1].reserve(tmpb));
-    LQB_TRY(run_all(c, segs, x, y, n, 0, C, c->d_tmp[0].p, c->d_tmp[1].p, stream, &c->last_launches));
+    LQB_TRY(run_all(c, segs, x, y, n, 0, C, c->d_tmp[0].p, c->d_tmp[1].p, stream, &c->last_launches, c->timing));
     advance_all(c, n);
     return LQB_OK;
 }
@@ -934,6 +952,26 @@ int lqb_chain_plan(lqb_chain c, char *buf, size_t len)
     return LQB_OK;
 }
 int lqb_chain_last_launches(lqb_chain c, int *n) { if (!c || !n) return fail(LQB_EINVAL, "null argument"); *n = c->last_launches; return LQB_OK; }
+int lqb_chain_set_timing(lqb_chain c, int enabled)
+{
+    if (!c) return fail(LQB_EINVAL, "null chain");
+    c->clear_timing(); c->timing = enabled != 0;
+    return LQB_OK;
+}
+int lqb_chain_get_timing(lqb_chain c, float *ms, int cap, int *n_segments, int *n_calls)
+{
+    if (!c || !ms || !n_segments || !n_calls) return fail(LQB_EINVAL, "null argument");
+    *n_calls = (int)c->timed_calls.size();
+    *n_segments = c->timed_calls.empty() ? 0 : (int)c->timed_calls[0].size();
+    for (int k = 0; k < cap; k++) ms[k] = 0.f;
+    for (auto &call : c->timed_calls)
+        for (size_t k = 0; k < call.size() && (int)k < cap; k++) {
+            LQB_CUDA(cudaEventSynchronize(call[k].second));
+            float t = 0.f; LQB_CUDA(cudaEventElapsedTime(&t, call[k].first, call[k].second));
+            ms[k] += t;
+        }
+    return LQB_OK;
+}
 int lqb_chain_set_fusion(lqb_chain c, int level) { if (!c || level < 0 || level > 2) return fail(LQB_EINVAL, "fusion level must be 0, 1 or 2"); c->fuse = level; return LQB_OK; }
 
 // ---- synthetic inputs

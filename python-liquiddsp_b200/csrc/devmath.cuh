@@ -71,7 +71,15 @@ __device__ __forceinline__ float2 mix_down(float2 x, float2 sc)
 __device__ __forceinline__ float exp_rn_small(float a)
 {
     const double x = (double)a;
-    if (fabsf(a) > 0.125f) return (float)exp(x);
+    const float aa = fabsf(a);
+    if (aa <= 0.0078125f) {
+        // the settled loop: |a| <= 2^-7, six terms leave 2^-42/720 -- evaluated as two short chains
+        const double x2 = x * x;
+        const double lo = fma(x, fma(x, 0.5, 1.0), 1.0);                          // 1 + x + x^2/2
+        const double hi = fma(x, fma(x, 1.0 / 120.0, 1.0 / 24.0), 1.0 / 6.0);     // 1/6 + x/24 + x^2/120
+        return (float)fma(x2 * x, hi, lo);
+    }
+    if (aa > 0.125f) return (float)exp(x);
     double p = 1.0 / 362880.0;
     p = fma(p, x, 1.0 / 40320.0); p = fma(p, x, 1.0 / 5040.0); p = fma(p, x, 1.0 / 720.0);
     p = fma(p, x, 1.0 / 120.0);   p = fma(p, x, 1.0 / 24.0);   p = fma(p, x, 1.0 / 6.0);
@@ -92,8 +100,11 @@ __device__ __forceinline__ float log_rn(float x, const double2 *__restrict__ tab
     const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
     const double2 t = tab[idx];
     const double r = fma(m, t.x, -1.0);
-    double p = 0.2;
-    p = fma(p, r, -0.25); p = fma(p, r, 1.0 / 3.0); p = fma(p, r, -0.5); p = fma(p, r, 1.0);
+    // r - r^2/2 + r^3/3 - r^4/4 + r^5/5 as two short chains
+    const double r2 = r * r;
+    const double lo = fma(r, -0.5, 1.0);                                          // 1 - r/2
+    const double hi = fma(r, fma(r, 0.2, -0.25), 1.0 / 3.0);                      // 1/3 - r/4 + r^2/5
+    const double p = fma(r2, hi, lo);                                             // ln(1+r) / r
     return (float)fma(p, r, fma((double)e, 0.6931471805599453094, t.y));
 }
 

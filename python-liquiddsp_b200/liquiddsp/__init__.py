@@ -79,6 +79,7 @@ _SIG = {
     "lqb_chain_out_len": [_P, _SZ, C.POINTER(_SZ)],
     "lqb_chain_execute": [_P, _P, _SZ, _P, _SZ, C.POINTER(_SZ)],
     "lqb_chain_execute_dev": [_P, _P, _SZ, _P, _SZ, C.POINTER(_SZ), _P],
+    "lqb_chain_set_timing": [_P, _I], "lqb_chain_get_timing": [_P, _P, _I, C.POINTER(_I), C.POINTER(_I)],
     "lqb_chain_plan": [_P, C.c_char_p, _SZ], "lqb_chain_last_launches": [_P, C.POINTER(_I)], "lqb_chain_set_fusion": [_P, _I],
     "lqb_synth_fill": [_I, _P, _I, _I, _SZ, _U64, _U64, _P],
 }
@@ -458,6 +459,16 @@ class Chain(_Stage):
 
     def last_launches(self):
         n = _I(); _ck(_lib.lqb_chain_last_launches(self._h, C.byref(n))); return n.value
+
+    def set_timing(self, enabled=True):
+        """Record a CUDA-event pair per plan segment on every execute_dev call (see segment_ms)."""
+        _ck(_lib.lqb_chain_set_timing(self._h, int(bool(enabled))))
+
+    def segment_ms(self):
+        """(per-segment milliseconds summed over the recorded execute_dev calls, number of calls)."""
+        ms = np.zeros(16, np.float32); ns, nc = _I(), _I()
+        _ck(_lib.lqb_chain_get_timing(self._h, _ptr(ms), 16, C.byref(ns), C.byref(nc)))
+        return ms[:ns.value].tolist(), nc.value
 
     def out_len(self, n):
         self._sync()
