@@ -22,6 +22,7 @@
 // checks and the history-ring save exist only in the checked path taken by the last tiles of a call.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <type_traits>
 #include "params.h"
 #include "devmath.cuh"
 #include "seq.h"
@@ -404,34 +405,39 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 // one step are independent of each other (each consumes what the previous section produced one
                 // step earlier).  Same operations on the same operands as the sample-by-sample order -- only
                 // the issue order changes, which gives the scheduler NS chains to interleave instead of one.
-                u64 xs[TS];
+                // 62 % of the tiles carry no output (one every 41.67 samples): they run a copy of the body without
+                // the per-sample capture of the finished dot product.
+                auto body = [&](auto with_emit) {
+                    u64 xs[TS];
 #pragma unroll
-                for (int j = 0; j < TS; j += 2) {
-                    const float4 v = *(const float4 *)(row + j * 8);
-                    xs[j] = pk(v.x, v.y); xs[j + 1] = pk(v.z, v.w);
-                }
-                u64 yy[NS], outv = 0;
+                    for (int j = 0; j < TS; j += 2) {
+                        const float4 v = *(const float4 *)(row + j * 8);
+                        xs[j] = pk(v.x, v.y); xs[j + 1] = pk(v.z, v.w);
+                    }
+                    u64 yy[NS], outv = 0;
 #pragma unroll
-                for (int k = 0; k < TS + NS - 1; k++) {
+                    for (int k = 0; k < TS + NS - 1; k++) {
 #pragma unroll
-                    for (int sct = NS - 1; sct >= 0; sct--) {
-                        const int j = k - sct;
-                        if (j >= 0 && j < TS) {
-                            const u64 in = sct == 0 ? xs[j] : yy[sct - 1];
-                            const u64 t  = fma2(ca1[sct], iv1[sct], in);
-                            const u64 v0 = fma2(ca2[sct], iv2[sct], t);
-                            u64 y = mul2(cb1[sct], iv1[sct]);
-                            y = fma2(cb0[sct], v0, y);
-                            y = fma2(cb2[sct], iv2[sct], y);
-                            iv2[sct] = iv1[sct]; iv1[sct] = v0; yy[sct] = y;
-                            if (sct == NS - 1) {
-                                rs_step(y, tk[j]);
-                                if (j == e) outv = rs_acc;       // at most one output per tile: handed on below
+                        for (int sct = NS - 1; sct >= 0; sct--) {
+                            const int j = k - sct;
+                            if (j >= 0 && j < TS) {
+                                const u64 in = sct == 0 ? xs[j] : yy[sct - 1];
+                                const u64 t  = fma2(ca1[sct], iv1[sct], in);
+                                const u64 v0 = fma2(ca2[sct], iv2[sct], t);
+                                u64 y = mul2(cb1[sct], iv1[sct]);
+                                y = fma2(cb0[sct], v0, y);
+                                y = fma2(cb2[sct], iv2[sct], y);
+                                iv2[sct] = iv1[sct]; iv1[sct] = v0; yy[sct] = y;
+                                if (sct == NS - 1) {
+                                    rs_step(y, tk[j]);
+                                    if constexpr (decltype(with_emit)::value) { if (j == e) outv = rs_acc; }
+                                }
                             }
                         }
                     }
-                }
-                if (e >= 0) tail(upk(outv), e);
+                    if constexpr (decltype(with_emit)::value) tail(upk(outv), e);     // at most one output per tile
+                };
+                if (e < 0) body(std::false_type{}); else body(std::true_type{});
             } else if constexpr (HAS_RS && !BIG_TAIL) {
                 u64 outv = 0;
 #pragma unroll
