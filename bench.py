@@ -123,6 +123,56 @@ def build_radio(L, channels):
     return iir, rs, agc, am, de
 
 
+def side_config(args, L, torch, dev, rank, world, barrier, max_over_ranks):
+    """Configs 2-4 of BASELINE.json: device-resident throughput of the plan the C ABI builds, same timing rules."""
+    import numpy as np
+    stream = torch.cuda.current_stream().cuda_stream
+    if args.config == 2:
+        C, n, kind, bps = 1024, 1 << 20, 1, 16.0
+        from oracle import oracle as O
+        chain = L.Chain(L.FIRFilter(O.firdes_kaiser(64, 0.1, 60.0), channels=C))
+        name, out_real = "config2: FIRFilter 64-tap crcf, 1024 channels x 1M samples", False
+    elif args.config == 3:
+        C, n, kind, bps = 4096, 65536, 2, 8.192
+        nco = L.NCO(channels=C); nco.set_frequencies((2 * np.pi * (0.05 + 0.4 * np.arange(C) / 4096)).astype(np.float32)); nco.set_direction(True)
+        chain = L.Chain(nco, L.ComplexResampler(0.024, Fc=0.024, channels=C))
+        name, out_real = "config3: NCO mix-down + ComplexResampler 2e6->48e3, 4096 channels x 64K blocks", False
+    else:
+        C, n, kind, bps = 16384, 65536, 3, 12.0
+        chain = L.Chain(L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=C), L.AGC(channels=C), L.FreqDem(0.1, channels=C))
+        name, out_real = "config4: ComplexIIRFilter cheby2-8 + AGC + FreqDem, 16384 channels x 64K blocks", True
+    x = torch.empty((C, n), dtype=torch.complex64, device=dev)
+    cap = chain.out_len(n) + 2
+    y = torch.empty((C, cap), dtype=torch.float32 if out_real else torch.complex64, device=dev)
+    L.synth_fill(kind, x.data_ptr(), C, n, channel0=rank * C, stream=stream)
+    # inputs smaller than L2 (config 3: 2.1 GB, fine; all are > 126 MB) -- every config streams > L2 per step
+    for _ in range(max(args.warmup, 3)):
+        chain.execute_dev(x.data_ptr(), n, y.data_ptr(), cap, stream)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    chain.set_timing(True)
+    launches = 0
+    e0.record()
+    for _ in range(args.steps):
+        chain.execute_dev(x.data_ptr(), n, y.data_ptr(), cap, stream); launches += chain.last_launches()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    seg, calls = chain.segment_ms()
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = peaks.get("hbm_gbs", 6650.0)
+    val = world * C * n / (ms * 1e-3) / 1e6
+    if rank == 0:
+        print(json.dumps({"metric": METRIC.replace("AM-chain", "config %d" % args.config), "value": val, "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": name, "plan": chain.plan(), "l2": "%.1f GB streamed per step, larger than L2" % (C * n * bps / 1e9)},
+                          "gpu_launches": launches,
+                          "roofline": {"bound": "hbm", "achieved": C * n * bps / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": C * n * bps / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_sample": bps,
+                                       "segments_ms": [t / max(calls, 1) for t in seg], "traffic": None}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -133,6 +183,8 @@ def main():
     ap.add_argument("--e2e-channels", type=int, default=8192, help="channels per GPU of the host-buffer (e2e) leg")
     ap.add_argument("--fuse", type=int, default=1, help="chain fusion level (0, 1, 2)")
     ap.add_argument("--block", type=int, default=BLOCK, help="samples per channel per step (profiling runs use a shorter block)")
+    ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 5 (default, the headline AM receiver), 2 FIR, 3 NCO+resampler, 4 IIR+AGC+FM")
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -197,6 +249,12 @@ def main():
         v = run_cpu_pool(args.cpu_seconds, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
                "sample": "%d processes x 1 channel of config 1 (README AMRadio, 64K blocks) for %.0f s each; CPU restatement of liquid-dsp, not liquid-dsp" % (cores, args.cpu_seconds)}
+
+    if args.config != 5:
+        side_config(args, L, torch, dev, rank, world, barrier, max_over_ranks)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     C, n = args.channels, args.block
     stream = torch.cuda.current_stream().cuda_stream
