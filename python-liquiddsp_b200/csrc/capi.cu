@@ -303,9 +303,12 @@ struct FmStage : lqb_stage_s {
     void fill(FmP &p) const { p.ref = ref; p.rprime = rprime.p; }
 };
 
+// channel count below which closed-form stages run time-parallel instead of one thread per channel
+constexpr int kParChannels = 16384;
+
 // ------------------------------------------------------------------------------------ chain
 struct Segment {
-    enum Type { SEQ, FIR, RESAMP_PAR, AMTAIL } type = SEQ;
+    enum Type { SEQ, FIR, RESAMP_PAR, AMTAIL, NCO_PAR } type = SEQ;
     unsigned mask = 0; int nsos = 0, sos0 = 0;
     std::vector<lqb_stage_s *> st;
     std::string name;
@@ -410,12 +413,20 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
             }
             g.st.clear();
         }
+        // Few channels cannot fill the GPU one thread per channel.  The oscillator (closed-form phase) and the
+        // resampler (closed-form output positions) have no loop-carried dependence, so below kParChannels they run
+        // time-parallel, the mixer applied while the resampler stages its input.
+        if (st[i]->C < kParChannels || (st[i]->kind == K_RESAMP && !static_cast<ResampStage *>(st[i])->decimating()) ||
+            (st[i]->kind == K_NCO && i + 1 < st.size() && st[i + 1]->kind == K_RESAMP && !static_cast<ResampStage *>(st[i + 1])->decimating())) {
+            if (st[i]->kind == K_NCO && c->fuse >= 1 && i + 1 < st.size() && st[i + 1]->kind == K_RESAMP) {
+                g.type = Segment::RESAMP_PAR; g.st = { st[i], st[i + 1] }; g.name = "par[nco+resamp]"; segs.push_back(g); i += 2; continue;
+            }
+            if (st[i]->kind == K_RESAMP) { g.type = Segment::RESAMP_PAR; g.st = { st[i] }; g.name = "par[resamp]"; segs.push_back(g); i++; continue; }
+            if (st[i]->kind == K_NCO && st[i]->C < kParChannels) { g.type = Segment::NCO_PAR; g.st = { st[i] }; g.name = "par[nco]"; segs.push_back(g); i++; continue; }
+        }
         size_t best = 1;
         if (c->fuse) for (size_t len = std::min<size_t>(6, st.size() - i); len >= 2; len--) if (run_fusable(st, i, len, c->fuse)) { best = len; break; }
         if (best == 1) {
-            if (st[i]->kind == K_RESAMP && !static_cast<ResampStage *>(st[i])->decimating()) {
-                g.type = Segment::RESAMP_PAR; g.st = { st[i] }; g.name = "par[resamp]"; segs.push_back(g); i++; continue;
-            }
             if (st[i]->kind == K_IIR) {              // long cascades: kMaxSos sections per launch
                 IirStage *q = static_cast<IirStage *>(st[i]);
                 for (int s0 = 0; s0 < q->nsos; s0 += kMaxSos) {
@@ -472,10 +483,18 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         return LQB_OK;
     }
     if (g.type == Segment::RESAMP_PAR) {
-        const ResampStage *r = static_cast<const ResampStage *>(first);
+        const ResampStage *r = static_cast<const ResampStage *>(g.st.back());
         ResampP p{}; r->fill(p);
-        LQB_CUDA(resamp_par_launch(p, (const float2 *)x, (float2 *)y, nch, ch0, r->C, (long long)n, (long long)n_out, stream));
-        if (n_out > 0) (*launches)++;              // the ring-update kernel
+        NcoP q{}; const bool has_nco = g.st.size() == 2;
+        if (has_nco) LQB_TRY(static_cast<NcoStage *>(g.st.front())->fill(q));
+        LQB_CUDA(resamp_par_launch(p, has_nco ? &q : nullptr, (const float2 *)x, (float2 *)y, nch, ch0, r->C, (long long)n, (long long)n_out, stream));
+        *launches += resamp_par_launch_count(has_nco, (long long)n_out) - 1;
+        return LQB_OK;
+    }
+    if (g.type == Segment::NCO_PAR) {
+        NcoP q{}; LQB_TRY(static_cast<NcoStage *>(g.st.front())->fill(q));
+        LQB_CUDA(nco_par_launch(q, (const float2 *)x, (float2 *)y, nch, ch0, (long long)n, stream));
+        (*launches)++;
         return LQB_OK;
     }
     SeqArgs a{};

@@ -12,6 +12,7 @@
 #include "params.h"
 #include "devmath.cuh"
 #include "par.h"
+#include <algorithm>
 
 namespace lqb {
 namespace {
@@ -24,13 +25,25 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
 }
 
+// oscillator value for absolute sample g of this call: theta_g = theta_0 + g * d_theta (mod 2^32) -- closed form
+__device__ __forceinline__ float2 nco_at(const NcoP &q, const float2 *tab, uint32_t th0, uint32_t dth, long long g)
+{
+    const uint32_t th = th0 + (uint32_t)g * dth;
+    if (q.type == 0) return tab[nco_index(th)];
+    float2 sc; const float f = (float)(6.283185307179586 * (double)(float)th / 4294967296.0);
+    sincosf(f, &sc.x, &sc.y);
+    return sc;
+}
+
+template <bool HAS_NCO>
 __global__ void __launch_bounds__(NT)
-resamp_par_kernel(const ResampP p, const float2 *__restrict__ x, float2 *__restrict__ y, int ch0, int Ctot,
+resamp_par_kernel(const ResampP p, const NcoP q, const float2 *__restrict__ x, float2 *__restrict__ y, int ch0, int Ctot,
                   long long n, long long n_out, int KT, int ntiles, int span_max)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *s_x = (float2 *)smem_raw;                   // span_max samples
     float  *s_b = (float *)(s_x + span_max);            // bank [npfb][sublen]
+    float2 *s_t = (float2 *)(s_b + ((p.npfb * p.sublen + 3) & ~3));   // oscillator table (HAS_NCO)
     const int tid = threadIdx.x, L = p.sublen;
     const long long ch = blockIdx.x / ntiles, tile = blockIdx.x % ntiles;
     const long long k0 = tile * KT;
@@ -49,8 +62,19 @@ resamp_par_kernel(const ResampP p, const float2 *__restrict__ x, float2 *__restr
         else if (g >= -(long long)L) s_x[i] = p.ring[(long long)(((long long)p.count + g + 4LL * L) % L) * Ctot + gch];
         else s_x[i] = make_float2(0.f, 0.f);
     }
+    if (HAS_NCO) for (int i = tid; i < 1024; i += NT) s_t[i] = q.sincos[i];
     cp_async_commit(); cp_async_wait<0>();
     __syncthreads();
+    if (HAS_NCO) {
+        // the mixer runs in front of the filter: rotate the staged samples of this call in place (history samples
+        // in the ring were rotated by the call that saw them)
+        const uint32_t th0 = q.theta[gch], dth = q.dtheta[gch];
+        for (int i = tid; i < span; i += NT) {
+            const long long g = i_lo + i;
+            if (g >= 0) { const float2 sc = nco_at(q, s_t, th0, dth, g); s_x[i] = q.dir == 2 ? mix_down(s_x[i], sc) : mix_up(s_x[i], sc); }
+        }
+        __syncthreads();
+    }
 
     if (tid < nk) {
         const unsigned long long P = P0 + (unsigned long long)tid * p.step;
@@ -69,22 +93,63 @@ resamp_par_kernel(const ResampP p, const float2 *__restrict__ x, float2 *__restr
 }
 
 // the newest min(n, sublen) inputs of the call go into the history ring
-__global__ void ring_update_kernel(const ResampP p, const float2 *__restrict__ x, int nch, int ch0, int Ctot, long long n)
+template <bool HAS_NCO>
+__global__ void ring_update_kernel(const ResampP p, const NcoP q, const float2 *__restrict__ x, int nch, int ch0, int Ctot, long long n)
 {
     const int L = p.sublen;
     const long long first = n > L ? n - L : 0, cnt = n - first;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cnt * nch; i += (long long)gridDim.x * blockDim.x) {
         const long long j = first + i / nch, ch = i % nch;
-        p.ring[(long long)((p.count + j) % L) * Ctot + ch0 + ch] = x[ch * n + j];
+        float2 v = x[ch * n + j];
+        if (HAS_NCO) {
+            const float2 sc = nco_at(q, q.sincos, q.theta[ch0 + ch], q.dtheta[ch0 + ch], j);
+            v = q.dir == 2 ? mix_down(v, sc) : mix_up(v, sc);
+        }
+        p.ring[(long long)((p.count + j) % L) * Ctot + ch0 + ch] = v;
+    }
+}
+
+// after a time-parallel pass over n samples every oscillator has advanced n steps
+__global__ void nco_advance_kernel(const NcoP q, int nch, int ch0, long long n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nch) q.theta[ch0 + i] += (uint32_t)n * q.dtheta[ch0 + i];
+}
+
+// y[ch][k] = x[ch][k] * exp(+-j theta_k): nco_crcf_mix_block_up/down (nco.hpp:70,78) with the phase in closed form
+__global__ void nco_par_kernel(const NcoP q, const float2 *__restrict__ x, float2 *__restrict__ y, int nch, int ch0, long long n)
+{
+    __shared__ float2 s_t[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_t[i] = q.sincos[i];
+    __syncthreads();
+    const long long total = (long long)nch * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long ch = i / n, k = i % n;
+        const float2 sc = nco_at(q, s_t, q.theta[ch0 + ch], q.dtheta[ch0 + ch], k);
+        const float2 v = x[i];
+        y[i] = q.dir == 2 ? mix_down(v, sc) : mix_up(v, sc);
     }
 }
 
 }  // namespace
 
-cudaError_t resamp_par_launch(const ResampP &p, const float2 *x, float2 *y, int nch, int ch0, int Ctot,
+cudaError_t nco_par_launch(const NcoP &q, const float2 *x, float2 *y, int nch, int ch0, long long n, cudaStream_t stream)
+{
+    if (nch <= 0 || n <= 0) return cudaSuccess;
+    const long long total = (long long)nch * n;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+    nco_par_kernel<<<blocks, 256, 0, stream>>>(q, x, y, nch, ch0, n);
+    cudaError_t rc = cudaGetLastError();
+    if (rc != cudaSuccess) return rc;
+    nco_advance_kernel<<<(nch + 255) / 256, 256, 0, stream>>>(q, nch, ch0, n);
+    return cudaGetLastError();
+}
+
+cudaError_t resamp_par_launch(const ResampP &p, const NcoP *nco, const float2 *x, float2 *y, int nch, int ch0, int Ctot,
                               long long n, long long n_out, cudaStream_t stream)
 {
     if (nch <= 0 || n <= 0) return cudaSuccess;
+    const NcoP q = nco ? *nco : NcoP{};
     if (n_out > 0) {
         // outputs per CTA: as many as keep the staged input span within ~48 KB
         const int span_budget = 6000;
@@ -93,17 +158,22 @@ cudaError_t resamp_par_launch(const ResampP &p, const float2 *x, float2 *y, int 
         const int span_max = (int)((((unsigned long long)KT * p.step) >> 24) + p.sublen + 3);
         const long long ntiles = (n_out + KT - 1) / KT;
         if (ntiles * (long long)nch > 0x7fffffffLL) return cudaErrorInvalidValue;
-        const size_t smem = (size_t)span_max * sizeof(float2) + (size_t)p.npfb * p.sublen * sizeof(float);
+        const size_t smem = (size_t)span_max * sizeof(float2) + (size_t)((p.npfb * p.sublen + 3) & ~3) * sizeof(float) + (nco ? 1024 * sizeof(float2) : 0);
         if (smem > 200 * 1024) return cudaErrorInvalidValue;
-        cudaError_t rc = cudaFuncSetAttribute((const void *)resamp_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto fn = nco ? resamp_par_kernel<true> : resamp_par_kernel<false>;
+        cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (rc != cudaSuccess) return rc;
-        resamp_par_kernel<<<(unsigned)(ntiles * nch), NT, smem, stream>>>(p, x, y, ch0, Ctot, n, n_out, KT, (int)ntiles, span_max);
+        fn<<<(unsigned)(ntiles * nch), NT, smem, stream>>>(p, q, x, y, ch0, Ctot, n, n_out, KT, (int)ntiles, span_max);
         rc = cudaGetLastError();
         if (rc != cudaSuccess) return rc;
     }
     const long long work = (n < p.sublen ? n : p.sublen) * (long long)nch;
     const unsigned blocks = (unsigned)((work + 255) / 256 < 1184 ? (work + 255) / 256 : 1184);
-    ring_update_kernel<<<blocks, 256, 0, stream>>>(p, x, nch, ch0, Ctot, n);
+    if (nco) ring_update_kernel<true><<<blocks, 256, 0, stream>>>(p, q, x, nch, ch0, Ctot, n);
+    else     ring_update_kernel<false><<<blocks, 256, 0, stream>>>(p, q, x, nch, ch0, Ctot, n);
+    cudaError_t rc = cudaGetLastError();
+    if (rc != cudaSuccess || !nco) return rc;
+    nco_advance_kernel<<<(nch + 255) / 256, 256, 0, stream>>>(q, nch, ch0, n);
     return cudaGetLastError();
 }
 

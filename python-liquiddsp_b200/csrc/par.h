@@ -5,6 +5,10 @@
 
 namespace lqb {
 // arbitrary-rate polyphase resampler, one thread per output sample; x [nch][n] -> y [nch][n_out]
-cudaError_t resamp_par_launch(const ResampP &p, const float2 *x, float2 *y, int nch, int ch0, int Ctot,
+// nco (optional) is the mixer in front of the resampler, applied while the input is staged
+cudaError_t resamp_par_launch(const ResampP &p, const NcoP *nco, const float2 *x, float2 *y, int nch, int ch0, int Ctot,
                               long long n, long long n_out, cudaStream_t stream);
+inline int resamp_par_launch_count(bool has_nco, long long n_out) { return (n_out > 0 ? 1 : 0) + 1 + (has_nco ? 1 : 0); }
+// oscillator mix alone, phase in closed form (theta_0 + k * d_theta mod 2^32)
+cudaError_t nco_par_launch(const NcoP &q, const float2 *x, float2 *y, int nch, int ch0, long long n, cudaStream_t stream);
 }  // namespace lqb

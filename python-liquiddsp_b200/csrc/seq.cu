@@ -458,6 +458,46 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             } else if constexpr (BIG_TAIL) {
 #pragma unroll 1
                 for (int j = 0; j < TS; j++) tail(upk(head(*(const float2 *)(row + j * 8))), j);
+            } else if constexpr (HAS_IIR && !HAS_NCO) {
+                // full-rate chains behind the biquad cascade: the cascade runs skewed over the tile (see above) and
+                // leaves its outputs in the thread's own staged row; the stages after it then walk the row in a
+                // rolled loop -- the AGC / discriminator bodies are long, 16 unrolled copies would not fit the
+                // instruction cache
+                {
+                    u64 xs[TS], yy[NS];
+#pragma unroll
+                    for (int j = 0; j < TS; j += 2) {
+                        const float4 v = *(const float4 *)(row + j * 8);
+                        xs[j] = pk(v.x, v.y); xs[j + 1] = pk(v.z, v.w);
+                    }
+#pragma unroll
+                    for (int k = 0; k < TS + NS - 1; k++) {
+#pragma unroll
+                        for (int sct = NS - 1; sct >= 0; sct--) {
+                            const int j = k - sct;
+                            if (j >= 0 && j < TS) {
+                                const u64 in = sct == 0 ? xs[j] : yy[sct - 1];
+                                const u64 t  = fma2(ca1[sct], iv1[sct], in);
+                                const u64 v0 = fma2(ca2[sct], iv2[sct], t);
+                                u64 y = mul2(cb1[sct], iv1[sct]);
+                                y = fma2(cb0[sct], v0, y);
+                                y = fma2(cb2[sct], iv2[sct], y);
+                                iv2[sct] = iv1[sct]; iv1[sct] = v0; yy[sct] = y;
+                                if (sct == NS - 1) {
+                                    if constexpr (HAS_AGC || HAS_FM) *(float2 *)(const_cast<unsigned char *>(row) + j * 8) = upk(y);
+                                    else tail(upk(y), j);
+                                }
+                            }
+                        }
+                    }
+                }
+                if constexpr (HAS_AGC || HAS_FM) {
+#pragma unroll 2
+                    for (int j = 0; j < TS; j++) tail(*(const float2 *)(row + j * 8), j);
+                }
+            } else if constexpr (HAS_AGC || HAS_FM) {
+#pragma unroll 2
+                for (int j = 0; j < TS; j++) tail(upk(head(*(const float2 *)(row + j * 8))), j);
             } else {
 #pragma unroll
                 for (int j = 0; j < TS; j += 2) {

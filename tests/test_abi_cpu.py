@@ -89,10 +89,14 @@ def _radio(ch=1):
 
 
 def test_planner():
-    assert L.Chain(*_radio(), fuse=0).plan() == "seq[iir4] -> seq[resamp] -> seq[agc] -> am[ampmodem] -> seq[deemph]"
+    assert L.Chain(*_radio(), fuse=0).plan() == "seq[iir4] -> par[resamp] -> seq[agc] -> am[ampmodem] -> seq[deemph]"
     assert L.Chain(*_radio(), fuse=1).plan() == "seq[iir4+resamp] -> am[agc+ampmodem+deemph]"
     assert L.Chain(*_radio(), fuse=2).plan() == "seq[iir4+resamp+agc+ampmodem+deemph]"
-    assert L.Chain(L.NCO(), L.ComplexResampler(0.024, Fc=0.024)).plan() == "seq[nco+resamp]"
+    assert L.Chain(L.NCO(), L.ComplexResampler(0.024, Fc=0.024)).plan() == "par[nco+resamp]"          # few channels: time-parallel
+    big = 32768
+    assert L.Chain(L.NCO(channels=big), L.ComplexResampler(0.024, Fc=0.024, channels=big)).plan() == "seq[nco+resamp]"
+    assert L.Chain(L.NCO(channels=big), L.ComplexResampler(0.5, Fc=0.2, channels=big)).plan() == "par[nco+resamp]"
+    assert L.Chain(L.NCO()).plan() == "par[nco]" and L.Chain(L.NCO(channels=big)).plan() == "seq[nco]"
     assert L.Chain(L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075), L.AGC(), L.FreqDem(0.1)).plan() == "seq[iir4+agc+freqdem]"
     assert L.Chain(L.ComplexResampler(0.5, Fc=0.2)).plan() == "par[resamp]"          # not decimating enough to fuse
     assert L.Chain(L.ComplexIIRFilter("butter", "bandpass", order=10, Fc=0.1, F0=0.2)).plan() == "seq[iir8] -> seq[iir2]"

@@ -326,7 +326,7 @@ def test_fused_chain_matches_stagewise(cuda, fuse):
     x = am_iq(n, seed=5)
     a, b = _Radio(L), _Radio(L)
     chain = L.Chain(*b.stages(), fuse=fuse)
-    expect = {0: 5, 1: 3, 2: 1}[fuse]        # level 1: full-rate kernel, AGC in place on the hand-off, AM tail
+    expect = {0: 6, 1: 3, 2: 1}[fuse]        # level 1: full-rate kernel, AGC in place on the hand-off, AM tail
     ys, yc = [], []
     for i in range(0, n, blk):
         ys.append(a(x[i:i + blk])); yc.append(chain(x[i:i + blk]))
@@ -365,7 +365,7 @@ def test_config3_nco_resampler(cuda):
     f = (2 * np.pi * (0.05 + 0.4 * np.arange(C) / 4096)).astype(np.float32)
     nco.set_frequencies(f); nco.set_direction(True)
     chain = L.Chain(nco, rs)
-    assert chain.plan() == "seq[nco+resamp]"
+    assert chain.plan() == "par[nco+resamp]"             # 96 channels: time-parallel, mixer applied while staging
     xb = L.DeviceBuffer(C * n * 8)
     refs = {c: (O.NCO(), O.ComplexResampler(0.024, Fc=0.024)) for c in (0, 50, 95)}
     for c, (on, _) in refs.items():
@@ -381,6 +381,31 @@ def test_config3_nco_resampler(cuda):
         t, _ = nco.u32()
         assert all(int(t[c]) == refs[c][0].theta_u32 for c in refs)   # oscillator phase bit-exact
         assert rs.state()[1] == refs[0][1].phase
+
+
+def test_nco_resampler_sequential_equals_time_parallel(cuda):
+    """The channel-parallel sequential kernel (many channels) and the time-parallel kernels (few) agree bit for bit."""
+    C, n = 16384 + 64, 4096
+    nco = L.NCO(channels=C); rs = L.ComplexResampler(0.024, Fc=0.024, channels=C)
+    f = (2 * np.pi * (0.05 + 0.4 * (np.arange(C) % 4096) / 4096)).astype(np.float32)
+    nco.set_frequencies(f); nco.set_direction(True)
+    big = L.Chain(nco, rs)
+    assert big.plan() == "seq[nco+resamp]"
+    xb = L.DeviceBuffer(C * n * 8)
+    small = {c: L.Chain(L.NCO(), L.ComplexResampler(0.024, Fc=0.024)) for c in (0, 4095, C - 1)}
+    for c, ch in small.items():
+        ch.stages[0].freq = float(f[c]); ch.stages[0].set_direction(True)
+        assert ch.plan() == "par[nco+resamp]"
+    for blk in range(3):
+        L.synth_fill(2, xb.ptr.value, C, n, n0=blk * n)
+        x = xb.download((C, n), np.complex64)
+        y = big(x)
+        for c, ch in small.items():
+            yc = ch(x[c])
+            assert np.array_equal(y[c].view(np.uint32), yc.view(np.uint32)), (blk, c)
+    t, _ = nco.u32()
+    for c, ch in small.items():
+        assert int(t[c]) == int(ch.stages[0].u32()[0][0])
 
 
 def test_config4_iir_agc_fm(cuda):
