@@ -75,6 +75,7 @@ struct SeqArgs {
     int ch0;                       // first channel's index into the [.. ][Ctot] state arrays
     int Ctot;                      // channel stride of the state arrays
     int vec_in, vec_out;           // 1 when rows allow 16-byte vector access
+    int cpw;                       // channels per warp: 32, or 16 / 8 to spread few channels over more warps
     int out_tmajor;                // decimated output stored [sample][channel] (hand-off to the AM tail kernel)
     long long n, out_pitch;
     NcoP nco; IirP iir; ResampP rs; AgcP agc; AmP am; FmP fm; DeP de;

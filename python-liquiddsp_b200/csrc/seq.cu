@@ -57,10 +57,14 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     constexpr bool BIG_TAIL = HAS_AM;               // keep one copy of the ampmodem body
     static_assert(HAS_IIR == (NSOS > 0), "section count and mask disagree");
 
+    // Channels per warp.  With few channels the kernel is bound by the latency of each channel's recurrence, not by
+    // throughput, so the same channels are spread over more warps (8 or 16 working lanes each) and the schedulers
+    // get 2-4x as many independent chains to interleave.  The idle lanes still help stage the tiles.
+    const int cpw = a.cpw, RCTA = (BT / 32) * cpw;                 // rows (channels) per CTA
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char *s_in  = smem;                                   // NST stages of [BT][PIN]
-    unsigned char *s_out = s_in + NST * BT * PIN;                  // [BT][POUT] when the output is full rate
-    unsigned char *s_nxt = s_out + (HAS_RS ? 0 : BT * POUT);
+    unsigned char *s_in  = smem;                                   // NST stages of [RCTA][PIN]
+    unsigned char *s_out = s_in + NST * RCTA * PIN;                // [RCTA][POUT] when the output is full rate
+    unsigned char *s_nxt = s_out + (HAS_RS ? 0 : RCTA * POUT);
     float2 *s_tap = (float2 *)s_nxt;                               // [warp][NST][TS] (tap, keep)
     s_nxt += HAS_RS ? (BT / 32) * NST * TS * sizeof(float2) : 0;
     int *s_emit = (int *)s_nxt;                                    // [warp][NST] sample of the tile an output falls on, or -1
@@ -76,8 +80,10 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     float *s_dcr = (float *)s_nxt;
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const long long chl = (long long)blockIdx.x * BT + tid;        // channel within this launch
-    const bool active = chl < a.C;
+    const int myrow = wid * cpw + lane;                            // this lane's row of the CTA's tile
+    const bool worker = lane < cpw;
+    const long long chl = (long long)blockIdx.x * RCTA + myrow;    // channel within this launch
+    const bool active = worker && chl < a.C;
     const long long gch = a.ch0 + (active ? chl : 0);              // index into the state arrays
     const long long CT = a.Ctot;
     const long long N = a.n;
@@ -172,25 +178,26 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
 
     // ---- tile loads: per-thread constants + a running byte offset ----
     // thread -> chunk column lk of rows lrow0 + i*RSTEP; rows past the last channel are skipped
-    const int lk = lane % GI::CH16, lrow0 = wid * 32 + lane / GI::CH16;
+    const int lk = lane % GI::CH16, lrow0 = wid * cpw + lane / GI::CH16;
+    const int npass = cpw / GI::RSTEP;                            // copies per lane per tile (CH16 when cpw = 32)
     unsigned vmask = 0;
 #pragma unroll
     for (int i = 0; i < GI::CH16; i++)
-        if ((long long)blockIdx.x * BT + lrow0 + i * GI::RSTEP < a.C) vmask |= 1u << i;
-    const char *gsrc = (const char *)a.x + (((long long)blockIdx.x * BT + lrow0) * N + (long long)lk * GI::EPC) * IELEM;
+        if (i < npass && (long long)blockIdx.x * RCTA + lrow0 + i * GI::RSTEP < a.C) vmask |= 1u << i;
+    const char *gsrc = (const char *)a.x + (((long long)blockIdx.x * RCTA + lrow0) * N + (long long)lk * GI::EPC) * IELEM;
     const long long grow = (long long)GI::RSTEP * N * IELEM;      // bytes between this thread's rows
     const unsigned sdst0 = (unsigned)__cvta_generic_to_shared(s_in) + lrow0 * PIN + lk * 16;
 
     // the common case -- every row of the CTA exists, the tile is complete, rows are 16-byte aligned -- needs no
     // predicate and no size: eight copies at a running row pointer
-    const bool fast_cta = a.vec_in && (long long)(blockIdx.x + 1) * BT <= (long long)a.C;
+    const bool fast_cta = a.vec_in && (long long)(blockIdx.x + 1) * RCTA <= (long long)a.C;
     const long long nfull = N / TS;
     auto load_tile_fast = [&](long long t, int stage) {
         const char *src = gsrc + t * (TS * IELEM);
-        const unsigned dst = sdst0 + stage * (BT * PIN);
+        const unsigned dst = sdst0 + stage * (RCTA * PIN);
 #pragma unroll
         for (int i = 0; i < GI::CH16; i++) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + i * (GI::RSTEP * PIN)), "l"(src) : "memory");
+            if (i < npass) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + i * (GI::RSTEP * PIN)), "l"(src) : "memory");
             src += grow;
         }
     };
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
         const long long e0 = t * TS + (long long)lk * GI::EPC;    // first element of this thread's chunks
         const char *src = gsrc + t * (TS * IELEM);
         if (a.vec_in) {
-            const unsigned dst = sdst0 + stage * (BT * PIN);
+            const unsigned dst = sdst0 + stage * (RCTA * PIN);
             const long long rem = (N - e0) * IELEM;
             const int nb = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
             if (nb > 0) {
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                                      "r"(dst + i * (GI::RSTEP * PIN)), "l"(src + i * grow), "r"(nb) : "memory");
             }
         } else {
-            unsigned char *d = s_in + stage * (BT * PIN) + lrow0 * PIN + lk * 16;
+            unsigned char *d = s_in + stage * (RCTA * PIN) + lrow0 * PIN + lk * 16;
 #pragma unroll
             for (int i = 0; i < GI::CH16; i++)
                 if ((vmask >> i) & 1u)
@@ -223,13 +230,13 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     };
 
     // full-rate output tile back to HBM, same chunk geometry
-    const int ok = lane % GO::CH16, orow0 = wid * 32 + lane / GO::CH16;
+    const int ok = lane % GO::CH16, orow0 = wid * cpw + lane / GO::CH16, opass = cpw / GO::RSTEP;
     auto store_tile = [&](long long t) {
         const long long e0 = t * TS + (long long)ok * GO::EPC;
 #pragma unroll
         for (int i = 0; i < GO::CH16; i++) {
-            const long long ch = (long long)blockIdx.x * BT + orow0 + i * GO::RSTEP;
-            if (ch < a.C && e0 < N) {
+            const long long ch = (long long)blockIdx.x * RCTA + orow0 + i * GO::RSTEP;
+            if (i < opass && ch < a.C && e0 < N) {
                 const unsigned char *src = s_out + (orow0 + i * GO::RSTEP) * POUT + ok * 16;
                 char *dst = (char *)a.y + (ch * a.out_pitch + e0) * OELEM;
                 if (a.vec_out && e0 + GO::EPC <= N) {
@@ -334,8 +341,8 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             }
             kout++;
         } else {
-            if constexpr (OUT_REAL) *(float *)(s_out + tid * POUT + jtile * 4) = r;
-            else                    *(float2 *)(s_out + tid * POUT + jtile * 8) = z;
+            if constexpr (OUT_REAL) *(float *)(s_out + myrow * POUT + jtile * 4) = r;
+            else                    *(float2 *)(s_out + myrow * POUT + jtile * 8) = z;
         }
     };
 
@@ -388,11 +395,13 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             if (t + NST - 1 < ntiles) { load_tile(t + NST - 1, sn); gen_taps(sn, false); }
             cp_async_commit();
         }
-        const unsigned char *row = s_in + stage * (BT * PIN) + tid * PIN;
+        const unsigned char *row = s_in + stage * (RCTA * PIN) + myrow * PIN;
         const float2 *tk = s_tap + (wid * NST + stage) * TS;
         int e = -1;
         if constexpr (HAS_RS) e = s_emit[wid * NST + stage];
-        if (t < nfast) {
+        if (!worker) {
+            // idle lane of a partially used warp: staging only
+        } else if (t < nfast) {
             if constexpr (IN_REAL) {
 #pragma unroll
                 for (int j = 0; j < TS; j += 4) {
@@ -589,8 +598,9 @@ size_t smem_bytes(unsigned m, const SeqArgs &a)
 {
     const bool in_real = m & F_INREAL, out_real = (m & (F_AM | F_FM | F_INREAL)) != 0;
     const int pin = TS * (in_real ? 4 : 8) + 16, pout = TS * (out_real ? 4 : 8) + 16;
-    size_t b = (size_t)NST * BT * pin;
-    if (!(m & F_RS)) b += (size_t)BT * pout;
+    const size_t rows = (size_t)(BT / 32) * a.cpw;
+    size_t b = (size_t)NST * rows * pin;
+    if (!(m & F_RS)) b += rows * pout;
     if (m & F_RS)  b += (BT / 32) * NST * TS * sizeof(float2) + 32 + (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15);
     if (m & F_NCO) b += 1024 * sizeof(float2);
     if (m & F_AGC) b += 128 * sizeof(double2);
@@ -607,10 +617,13 @@ cudaError_t seq_launch(unsigned mask, int nsos, const SeqArgs &a, cudaStream_t s
     const Entry *e = find(mask, nsos);
     if (!e) return cudaErrorInvalidValue;
     if (a.C <= 0 || a.n <= 0) return cudaSuccess;
+    if (a.cpw != 8 && a.cpw != 16 && a.cpw != 32) return cudaErrorInvalidValue;
+    if ((mask & F_AM) && a.cpw != 32) return cudaErrorInvalidValue;       // the in-kernel ampmodem rings are per thread
     const size_t smem = smem_bytes(mask, a);
     cudaError_t rc = cudaFuncSetAttribute((const void *)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
-    const unsigned grid = (unsigned)((a.C + BT - 1) / BT);
+    const int rows = (BT / 32) * a.cpw;
+    const unsigned grid = (unsigned)((a.C + rows - 1) / rows);
     e->fn<<<grid, BT, smem, stream>>>(a);
     return cudaGetLastError();
 }

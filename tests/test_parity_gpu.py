@@ -42,6 +42,24 @@ def test_iir_batched_ragged(cuda, n):
         assert np.array_equal(y[c].view(np.uint32), o(x[c]).view(np.uint32)), (c, n)
 
 
+@pytest.mark.parametrize("C", [28416 + 7, 56832 + 33])
+def test_iir_resampler_wide_batches(cuda, C):
+    """The channel-count regimes of the sequential kernel (8 / 16 / 32 channels per warp) give the same bits."""
+    rng = np.random.default_rng(21)
+    n = 1500
+    iir = L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=C); rs = L.ComplexResampler(0.024, Fc=0.024, channels=C)
+    chain = L.Chain(iir, rs)
+    assert chain.plan() == "seq[iir4+resamp]"
+    base = crandn(rng, 64, n)
+    x = np.tile(base, (C // 64 + 1, 1))[:C].copy()
+    ys = [chain(x), chain(x)]                               # two calls: carried state
+    for c in (0, 63, 64 * 100 + 5, C - 1):
+        oi, ors = O.ComplexIIRFilter(_sos=iir.sos()), O.ComplexResampler(0.024, Fc=0.024)
+        for k in range(2):
+            assert np.array_equal(ys[k][c].view(np.uint32), ors(oi(x[c])).view(np.uint32)), (C, c, k)
+    assert np.array_equal(ys[1][:64], ys[1][64:128])        # identical inputs -> identical outputs across CTAs
+
+
 def test_iir_streaming_invariance(cuda):
     rng = np.random.default_rng(3)
     x = crandn(rng, 3, 30011)
