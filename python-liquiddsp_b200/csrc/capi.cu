@@ -501,7 +501,10 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
     const bool in_real = (g.mask & F_INREAL) != 0, out_real = (g.mask & (F_AM | F_FM | F_INREAL)) != 0;
     a.x = x; a.y = y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.n = (long long)n;
     // enough warps to cover the recurrences' latency: aim for >= 12 warps per SM (148 SMs)
-    a.cpw = (g.mask & F_AM) ? 32 : (nch >= 148 * 12 * 32 ? 32 : (nch >= 148 * 12 * 16 ? 16 : 8));
+    // (only where the per-sample work is light: with the AGC / discriminator in the loop the kernel is issue-bound and
+    // idle lanes would only cost slots)
+    const bool light = (g.mask & (F_AGC | F_FM | F_AM)) == 0;
+    a.cpw = !light ? 32 : (nch >= 148 * 12 * 32 ? 32 : (nch >= 148 * 12 * 16 ? 16 : 8));
     a.out_tmajor = out_tmajor ? 1 : 0; a.out_pitch = out_tmajor ? (long long)nch : (long long)n_out;
     a.vec_in  = ((n * (in_real ? 4 : 8)) % 16 == 0) && (((size_t)x) % 16 == 0);
     a.vec_out = ((n_out * (out_real ? 4 : 8)) % 16 == 0) && (((size_t)y) % 16 == 0);

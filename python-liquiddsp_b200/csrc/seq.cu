@@ -43,7 +43,7 @@ template <int ELEM> struct Geo {
 };
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <unsigned M, int NSOS>
+template <unsigned M, int NSOS, bool FULL>
 __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __grid_constant__ SeqArgs a)
 {
     constexpr bool HAS_NCO = (M & F_NCO) != 0, HAS_IIR = (M & F_IIR) != 0, HAS_RS = (M & F_RS) != 0;
@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     // Channels per warp.  With few channels the kernel is bound by the latency of each channel's recurrence, not by
     // throughput, so the same channels are spread over more warps (8 or 16 working lanes each) and the schedulers
     // get 2-4x as many independent chains to interleave.  The idle lanes still help stage the tiles.
-    const int cpw = a.cpw, RCTA = (BT / 32) * cpw;                 // rows (channels) per CTA
+    // (FULL: 32 channels per warp known at compile time -- the many-channel instantiation carries no extra arithmetic)
+    const int cpw = FULL ? 32 : a.cpw, RCTA = (BT / 32) * cpw;     // rows (channels) per CTA
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char *s_in  = smem;                                   // NST stages of [RCTA][PIN]
     unsigned char *s_out = s_in + NST * RCTA * PIN;                // [RCTA][POUT] when the output is full rate
@@ -253,8 +254,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     };
 
     // ---- what happens to one sample on the decimated / demodulated side of the chain ----
-    auto tail = [&](float2 z, int jtile) {
-        float r = 0.f;
+    auto agc_apply = [&](float2 z) -> float2 {
         if constexpr (HAS_AGC) {
             // agc_crcf_execute (liquid agc.proto.c) then the wrapper's status poll, agc.hpp:115-125
             float yr = __fmul_rn(z.x, agc_g), yi = __fmul_rn(z.y, agc_g);
@@ -282,6 +282,10 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             if (agc_mode == 5 || agc_mode == 1) { yr = __fmul_rn(yr, 0.0f); yi = __fmul_rn(yi, 0.0f); }
             z = make_float2(yr, yi);
         }
+        return z;
+    };
+    auto post = [&](float2 z, int jtile) {
+        float r = 0.f;
         if constexpr (HAS_AM) {
             // ampmodem_demod_dsb_pll_carrier / _costas (liquid ampmodem.c)
             const float2 sc = __ldg(&a.am.sincos[nco_index(am_theta)]);
@@ -345,6 +349,8 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             else                    *(float2 *)(s_out + myrow * POUT + jtile * 8) = z;
         }
     };
+
+    auto tail = [&](float2 z, int jtile) { post(agc_apply(z), jtile); };
 
     // ---- one full-rate sample: oscillator and IIR; returns the (complex) value handed on ----
     auto head = [&](float2 xin) -> u64 {
@@ -500,9 +506,16 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                         }
                     }
                 }
+                // then one pass per remaining stage: the gain loop is a long serial chain per sample and runs rolled;
+                // the discriminator has no feedback, so its 16 samples are independent work for the scheduler
+                if constexpr (HAS_AGC) {
+                    float2 *rw = (float2 *)const_cast<unsigned char *>(row);
+#pragma unroll 1
+                    for (int j = 0; j < TS; j++) rw[j] = agc_apply(rw[j]);
+                }
                 if constexpr (HAS_AGC || HAS_FM) {
-#pragma unroll 2
-                    for (int j = 0; j < TS; j++) tail(*(const float2 *)(row + j * 8), j);
+#pragma unroll 4
+                    for (int j = 0; j < TS; j++) post(*(const float2 *)(row + j * 8), j);
                 }
             } else if constexpr (HAS_AGC || HAS_FM) {
 #pragma unroll 2
@@ -568,9 +581,9 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
 
 // ---- dispatch ----------------------------------------------------------------------------------
 typedef void (*SeqFn)(const SeqArgs);
-struct Entry { unsigned mask; int nsos; SeqFn fn; };
+struct Entry { unsigned mask; int nsos; SeqFn fn, fn_part; };       // full warps / 8-16 channels per warp
 
-#define LQB_E(M, S) { (M), (S), seq_kernel<(M), (S)> }
+#define LQB_E(M, S) { (M), (S), seq_kernel<(M), (S), true>, seq_kernel<(M), (S), false> }
 #define LQB_E_IIR(M) LQB_E(M, 1), LQB_E(M, 2), LQB_E(M, 3), LQB_E(M, 4)
 const Entry kTable[] = {
     // single stages
@@ -579,11 +592,9 @@ const Entry kTable[] = {
     // fused runs
     LQB_E(F_NCO | F_RS, 0),
     LQB_E_IIR(F_IIR | F_RS),
-    LQB_E_IIR(F_NCO | F_IIR | F_RS),
     LQB_E(F_AGC | F_FM, 0), LQB_E(F_FM | F_DE, 0), LQB_E(F_AGC | F_FM | F_DE, 0),
-    LQB_E_IIR(F_IIR | F_AGC),
     LQB_E_IIR(F_IIR | F_AGC | F_FM),
-    LQB_E_IIR(F_IIR | F_RS | F_AGC | F_AM | F_DE),
+    LQB_E(F_IIR | F_RS | F_AGC | F_AM | F_DE, 4),
 };
 #undef LQB_E
 #undef LQB_E_IIR
@@ -620,11 +631,12 @@ cudaError_t seq_launch(unsigned mask, int nsos, const SeqArgs &a, cudaStream_t s
     if (a.cpw != 8 && a.cpw != 16 && a.cpw != 32) return cudaErrorInvalidValue;
     if ((mask & F_AM) && a.cpw != 32) return cudaErrorInvalidValue;       // the in-kernel ampmodem rings are per thread
     const size_t smem = smem_bytes(mask, a);
-    cudaError_t rc = cudaFuncSetAttribute((const void *)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SeqFn fn = a.cpw == 32 ? e->fn : e->fn_part;
+    cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     const int rows = (BT / 32) * a.cpw;
     const unsigned grid = (unsigned)((a.C + rows - 1) / rows);
-    e->fn<<<grid, BT, smem, stream>>>(a);
+    fn<<<grid, BT, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
