@@ -141,6 +141,8 @@ def side_config(args, L, torch, dev, rank, world, barrier, max_over_ranks):
         C, n, kind, bps = 16384, 65536, 3, 12.0
         chain = L.Chain(L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=C), L.AGC(channels=C), L.FreqDem(0.1, channels=C))
         name, out_real = "config4: ComplexIIRFilter cheby2-8 + AGC + FreqDem, 16384 channels x 64K blocks", True
+    if args.block != BLOCK:
+        n = args.block                      # profiling runs use a shorter block
     x = torch.empty((C, n), dtype=torch.complex64, device=dev)
     cap = chain.out_len(n) + 2
     y = torch.empty((C, cap), dtype=torch.float32 if out_real else torch.complex64, device=dev)
