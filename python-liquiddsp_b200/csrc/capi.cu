@@ -23,6 +23,7 @@
 #include "fir.h"
 #include "am.h"
 #include "par.h"
+#include "scan.h"
 #include "synth.h"
 
 namespace lqb {
@@ -153,8 +154,36 @@ struct IirStage : lqb_stage_s {
         }
         return LQB_OK;
     }
+    // blocked-scan evaluation (mode 2): block responses in double, scratch for the per-block states
+    int scanB = 0; DevArr<double> scanH, scanM; DevArr<float2> vblk; DevArr<double2> sin;
     int materialize() override { return v.alloc((size_t)nsos * 2 * C); }
     int clear() override { return v.zero(); }
+    // H[k][j]: output at step k of a block started from unit state j with zero input; M[i][j]: state i after B steps
+    int prepare_scan(int B)
+    {
+        if (scanB == B) return LQB_OK;
+        const int S = 2 * nsos;
+        std::vector<double> H((size_t)B * S), M((size_t)S * S);
+        for (int j = 0; j < S; j++) {
+            std::vector<double> st(S, 0.0); st[j] = 1.0;
+            for (int k = 0; k < B; k++) {
+                double in = 0.0;
+                for (int q = 0; q < nsos; q++) {
+                    const double v1 = st[2 * q], v2 = st[2 * q + 1];
+                    const double v0 = in - (double)A[3 * q + 1] * v1 - (double)A[3 * q + 2] * v2;
+                    in = (double)B_(q, 0) * v0 + (double)B_(q, 1) * v1 + (double)B_(q, 2) * v2;
+                    st[2 * q + 1] = v1; st[2 * q] = v0;
+                }
+                H[(size_t)k * S + j] = in;
+            }
+            for (int i = 0; i < S; i++) M[(size_t)i * S + j] = st[i];
+        }
+        LQB_TRY(scanH.alloc(H.size())); LQB_TRY(scanH.upload(H.data(), H.size()));
+        LQB_TRY(scanM.alloc(M.size())); LQB_TRY(scanM.upload(M.data(), M.size()));
+        scanB = B;
+        return LQB_OK;
+    }
+    double B_(int q, int k) const { return this->B[3 * q + k]; }
     void fill(IirP &p, int s0, int ns) const
     {
         p.nsos = ns;
@@ -431,7 +460,7 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
                 IirStage *q = static_cast<IirStage *>(st[i]);
                 for (int s0 = 0; s0 < q->nsos; s0 += kMaxSos) {
                     Segment h; h.type = Segment::SEQ; h.mask = F_IIR; h.sos0 = s0; h.nsos = std::min(kMaxSos, q->nsos - s0);
-                    h.st = { st[i] }; h.name = "seq[iir" + std::to_string(h.nsos) + "]"; segs.push_back(h);
+                    h.st = { st[i] }; h.name = std::string(q->mode == 2 && q->nsos <= kMaxSos ? "scan" : "seq") + "[iir" + std::to_string(h.nsos) + "]"; segs.push_back(h);
                 }
                 i++; continue;
             }
@@ -496,6 +525,28 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         LQB_CUDA(nco_par_launch(q, (const float2 *)x, (float2 *)y, nch, ch0, (long long)n, stream));
         (*launches)++;
         return LQB_OK;
+    }
+    if (g.type == Segment::SEQ && g.mask == F_IIR && g.st.size() == 1 && static_cast<IirStage *>(g.st[0])->mode == 2) {
+        // time-parallel blocked scan when the call length allows equal blocks; otherwise the sequential kernel
+        IirStage *q = static_cast<IirStage *>(g.st[0]);
+        const int B = n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : (n % 64 == 0 ? 64 : 0));
+        if (B && n >= (size_t)(4 * B) && q->nsos <= kMaxSos && (((size_t)x) % 16 == 0) && (((size_t)y) % 16 == 0)) {
+            const long long K = (long long)n / B, rows = (long long)nch * K;
+            LQB_TRY(q->prepare_scan(B));
+            LQB_TRY(q->vblk.reserve((size_t)q->nsos * 2 * rows));
+            LQB_TRY(q->sin.reserve((size_t)rows * 2 * q->nsos));
+            LQB_CUDA(cudaMemsetAsync(q->vblk.p, 0, (size_t)q->nsos * 2 * rows * sizeof(float2), stream));
+            SeqArgs a{};
+            a.x = x; a.y = y; a.C = (int)rows; a.ch0 = 0; a.Ctot = (int)rows; a.n = B; a.out_pitch = B; a.vec_in = a.vec_out = 1; a.cpw = 32;
+            q->fill(a.iir, 0, q->nsos); a.iir.v = q->vblk.p;
+            LQB_CUDA(seq_launch(F_IIR, q->nsos, a, stream));
+            IirScanArgs sa{};
+            sa.y = (float2 *)y; sa.C = nch; sa.ch0 = ch0; sa.Ctot = q->C; sa.nsos = q->nsos; sa.B = B; sa.n = (long long)n;
+            sa.H = q->scanH.p; sa.M = q->scanM.p; sa.vblk = q->vblk.p; sa.v = q->v.p; sa.sin = q->sin.p;
+            LQB_CUDA(iir_scan_launch(sa, stream));
+            *launches += 2;
+            return LQB_OK;
+        }
     }
     SeqArgs a{};
     const bool in_real = (g.mask & F_INREAL) != 0, out_real = (g.mask & (F_AM | F_FM | F_INREAL)) != 0;
@@ -616,6 +667,7 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
     size_t chunk = std::max<size_t>(1, std::max<size_t>((size_t)64 << 20, in_total / 8) / std::max<size_t>(1, n * ib));
     if (chunk >= 64) chunk = chunk / 64 * 64;
     chunk = std::min<size_t>(chunk, (size_t)C);
+    for (auto *st : c->stages) if (st->kind == K_IIR && static_cast<IirStage *>(st)->mode == 2) chunk = (size_t)C;   // scan scratch is per stage
     for (int s = 0; s < lqb_chain_s::kStreams; s++) if (!c->streams[s]) LQB_CUDA(cudaStreamCreate(&c->streams[s]));
     const size_t nchunks = ((size_t)C + chunk - 1) / chunk;
     const size_t tmpb = max_intermediate_bytes(segs, n, chunk);
@@ -721,7 +773,7 @@ int lqb_iirfilt_crcf_set_mode(lqb_stage s, int mode)
 {
     LQB_GET(IirStage, q, s, K_IIR);
     if (mode < 0 || mode > 2) return fail(LQB_EINVAL, "iirfilt mode must be 0, 1 or 2");
-    if (mode == 2) return fail(LQB_ENOTIMPL, "time-parallel blocked-scan IIR is not built yet");
+    if (mode == 2 && q->nsos > kMaxSos) return fail(LQB_EINVAL, "blocked-scan IIR supports up to %d sections", kMaxSos);
     q->mode = mode; return LQB_OK;
 }
 

@@ -47,9 +47,10 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
     const int nh = a.ntaps - 1;
 
     for (int k = tid; k < ntaps_pad; k += NT) { const float h = k < a.ntaps ? a.taps[k] : 0.f; s_h[k] = make_float2(h, h); }
-    for (int i = tid; i < TN + halo; i += NT) {
+    // i advances by NT = 8 * 16 per pass, so its padded position advances by a constant 8 * 17
+    for (int i = tid, pi = phys(tid); i < TN + halo; i += NT, pi += (NT / 16) * 17) {
         const long long g = t0 - halo + i;                             // global sample index
-        float2 *dst = &s_x[phys(i)];
+        float2 *dst = &s_x[pi];
         if (g >= 0) { if (g < a.n) cp_async8(dst, xrow + g); else *dst = make_float2(0.f, 0.f); }
         else if (g + nh >= 0) cp_async8(dst, hrow + (g + nh));
         else *dst = make_float2(0.f, 0.f);
@@ -72,11 +73,12 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
     u64 acc[R];
 #pragma unroll
     for (int r = 0; r < R; r++) acc[r] = 0ull;
+    // halo + 1 = ntaps_pad is a multiple of 16 and o = 16 * tid, so ibase = 16 * m with m = tid + ntaps_pad/16 - 1 - kb/16:
+    // the padded position of ibase + q is 17 * m + q + (q >> 4) -- a per-chunk base plus compile-time offsets
     u64 W[2 * R - 1];
-    const int o = tid * R;
-    int ibase = o + halo - (R - 1);
+    const float2 *wb = s_x + 17 * (tid + ntaps_pad / R - 1);
 #pragma unroll
-    for (int q = 0; q < 2 * R - 1; q++) W[q] = pk(s_x[phys(ibase + q)]);
+    for (int q = 0; q < 2 * R - 1; q++) W[q] = pk(wb[q + (q >> 4)]);
     for (int kb = 0; kb < ntaps_pad; kb += R) {
 #pragma unroll
         for (int kk = 0; kk < R; kk++) {
@@ -85,25 +87,26 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
             for (int r = 0; r < R; r++) acc[r] = fma2(tap, W[r - kk + (R - 1)], acc[r]);
         }
         if (kb + R < ntaps_pad) {
-            ibase -= R;
+            wb -= 17;
 #pragma unroll
             for (int q = 2 * R - 2; q >= R; q--) W[q] = W[q - R];
 #pragma unroll
-            for (int q = 0; q < R; q++) W[q] = pk(s_x[phys(ibase + q)]);
+            for (int q = 0; q < R; q++) W[q] = pk(wb[q]);
         }
     }
     __syncthreads();
     const u64 sc = pk(a.scale, a.scale);
 #pragma unroll
-    for (int r = 0; r < R; r++) s_x[phys(o + r)] = upk(mul2(acc[r], sc));
+    for (int r = 0; r < R; r++) s_x[17 * tid + r] = upk(mul2(acc[r], sc));          // phys(16 * tid + r)
     __syncthreads();
     float2 *yrow = a.y + ch * a.n;
     const bool vec = ((a.n & 1) == 0) && ((((size_t)a.y) & 15) == 0);
     if (vec) {
-        for (int i = tid; i < TN / 2; i += NT) {
+        // sample pair 2i, 2i+1 sits at padded position 2i + (i >> 3); i advances by NT = 128, the position by 272
+        for (int i = tid, pi = 2 * tid + (tid >> 3); i < TN / 2; i += NT, pi += 2 * NT + NT / 8) {
             const long long g = t0 + 2 * i;
             if (g < a.n) {
-                const float2 u = s_x[phys(2 * i)], v = s_x[phys(2 * i + 1)];
+                const float2 u = s_x[pi], v = s_x[pi + 1];
                 *(float4 *)(yrow + g) = make_float4(u.x, u.y, v.x, v.y);
             }
         }
