@@ -339,6 +339,21 @@ def main():
         dt = max_over_ranks(time.perf_counter() - t0) / reps
         e2e = {"value": world * Ce * n / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(xn.nbytes), "d2h_bytes_per_step": int(yh.nbytes),
                "channels_per_gpu": Ce, "ms_per_step": dt * 1e3, "api": "liquiddsp.Chain.__call__ -> lqb_chain_execute (host pointers)"}
+        # the same call fed the SDR wire format (interleaved int16 I/Q, bytes_to_iq fused into the first kernel)
+        ih = torch.empty((Ce, 2 * n), dtype=torch.int16).pin_memory()
+        ih.copy_((torch.view_as_real(xh).reshape(Ce, 2 * n) * 32767.0).clamp(-32767, 32767).to(torch.int16))
+        inp = ih.numpy()
+        for _ in range(2):
+            yi = ch_e(inp)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            yi = ch_e(inp)
+        L.synchronize()
+        dti = max_over_ranks(time.perf_counter() - t0) / reps
+        e2e["int16_iq"] = {"value": world * Ce * n / dti / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(inp.nbytes),
+                           "d2h_bytes_per_step": int(yi.nbytes), "ms_per_step": dti * 1e3,
+                           "api": "liquiddsp.Chain.__call__(int16 I/Q) -> lqb_chain_execute_i16"}
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

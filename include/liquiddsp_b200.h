@@ -175,6 +175,15 @@ int lqb_chain_out_len(lqb_chain c, size_t n, size_t *n_out);
 int lqb_chain_execute(lqb_chain c, const void *x, size_t n, void *y, size_t y_capacity, size_t *n_out);
 int lqb_chain_execute_dev(lqb_chain c, const void *x_dev, size_t n, void *y_dev, size_t y_capacity,
                           size_t *n_out, void *stream);
+/* ---------------- int16 I/Q ingest : bytes_to_iq, utility.hpp:61-69 (wrapper.cpp:13) ----------------------
+ * SDRs deliver interleaved little-endian int16 I/Q; the reference converts with (float)x / 32767.0f on the host
+ * and then filters.  Here the conversion is fused into the first kernel of the chain (4 bytes per sample over
+ * PCIe and HBM instead of 8); chains whose first kernel has no int16 variant convert in one extra pass.
+ * iq: [n_channels x n] pairs (re, im) of int16.  lqb_bytes_to_iq is the stand-alone conversion. */
+int lqb_chain_execute_i16(lqb_chain c, const int16_t *iq, size_t n, void *y, size_t y_capacity, size_t *n_out);
+int lqb_chain_execute_i16_dev(lqb_chain c, const int16_t *iq_dev, size_t n, void *y_dev, size_t y_capacity,
+                              size_t *n_out, void *stream);
+int lqb_bytes_to_iq(const int16_t *iq, size_t n, lqb_cf *out);
 /* human-readable launch plan ("seq[iir4+resamp] -> seq[agc+am+deemph]") and the number of kernel
  * launches the last execute issued */
 int lqb_chain_plan(lqb_chain c, char *buf, size_t buf_len);

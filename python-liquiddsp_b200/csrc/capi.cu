@@ -353,9 +353,9 @@ struct lqb_chain_s {
     // host-execute resources: per-stream input/output staging and ping-pong scratch
     static constexpr int kStreams = 3;
     cudaStream_t streams[kStreams] = { nullptr, nullptr, nullptr };
-    lqb::DevArr<char> h_in[kStreams], h_out[kStreams], h_tmp[kStreams][2];
+    lqb::DevArr<char> h_in[kStreams], h_out[kStreams], h_tmp[kStreams][2], h_cvt[kStreams];
     // device-execute scratch
-    lqb::DevArr<char> d_tmp[2];
+    lqb::DevArr<char> d_tmp[2], d_cvt;
     // optional per-segment timing of execute_dev: one event pair per segment per call, on the caller's stream
     bool timing = false;
     std::vector<std::vector<std::pair<cudaEvent_t, cudaEvent_t>>> timed_calls;
@@ -485,7 +485,7 @@ static size_t seg_out_len(const Segment &g, size_t n) { for (auto *s : g.st) n =
 
 // run one segment on channels [ch0, ch0 + nch) of the chain; x/y point at the first of those rows
 static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_t n_out, int ch0, int nch, cudaStream_t stream,
-                       bool in_tmajor, bool out_tmajor, int *launches)
+                       bool in_tmajor, bool out_tmajor, int *launches, unsigned extra_mask = 0)
 {
     (*launches)++;
     const lqb_stage_s *first = g.st.front();
@@ -549,7 +549,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         }
     }
     SeqArgs a{};
-    const bool in_real = (g.mask & F_INREAL) != 0, out_real = (g.mask & (F_AM | F_FM | F_INREAL)) != 0;
+    const bool in_real = ((g.mask | extra_mask) & (F_INREAL | F_INI16)) != 0, out_real = (g.mask & (F_AM | F_FM | F_INREAL)) != 0;
     a.x = x; a.y = y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.n = (long long)n;
     // enough warps to cover the recurrences' latency: aim for >= 12 warps per SM (148 SMs)
     // (only where the per-sample work is light: with the AGC / discriminator in the loop the kernel is issue-bound and
@@ -571,7 +571,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         default: return fail(LQB_EINVAL, "stage kind %d cannot run in the sequential kernel", (int)s->kind);
         }
     }
-    LQB_CUDA(seq_launch(g.mask, g.nsos, a, stream));
+    LQB_CUDA(seq_launch(g.mask | extra_mask, g.nsos, a, stream));
     return LQB_OK;
 }
 
@@ -590,9 +590,23 @@ static int chain_validate(lqb_chain_s *c)
 }
 
 // all segments over channel range [ch0, ch0+nch); tmp0/tmp1 hold intermediates
-static int run_all(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, void *y, size_t n, int ch0, int nch,
-                   char *tmp0, char *tmp1, cudaStream_t stream, int *launches, bool timed = false)
+// can the first segment take interleaved int16 I/Q directly?
+static bool first_takes_i16(const std::vector<Segment> &segs)
 {
+    return !segs.empty() && segs[0].type == Segment::SEQ && seq_supported(segs[0].mask | F_INI16, segs[0].nsos);
+}
+
+static int run_all(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, void *y, size_t n, int ch0, int nch,
+                   char *tmp0, char *tmp1, cudaStream_t stream, int *launches, bool timed = false, bool in_i16 = false, char *cvt = nullptr)
+{
+    unsigned first_extra = 0;
+    if (in_i16) {
+        if (first_takes_i16(segs)) first_extra = F_INI16;          // bytes_to_iq fused into the front kernel
+        else {                                                      // otherwise one conversion pass, then the usual plan
+            LQB_CUDA(i16_to_c64_launch(x, (float2 *)cvt, (long long)nch * (long long)n, stream));
+            (*launches)++; x = cvt;
+        }
+    }
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
     if (timed && c->timed_calls.size() < 1024) {
         evs.resize(segs.size());
@@ -607,7 +621,7 @@ static int run_all(lqb_chain_s *c, const std::vector<Segment> &segs, const void 
         // both sides then touch HBM with warp-contiguous accesses and neither needs a staging tile
         const bool out_tm = k + 1 < segs.size() && segs[k].type == Segment::SEQ && (segs[k].mask & F_RS) && segs[k + 1].type == Segment::AMTAIL;
         if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[k].first, stream));
-        if (on > 0 || cur_n > 0) LQB_TRY(run_segment(segs[k], cur, dst, cur_n, on, ch0, nch, stream, in_tm, out_tm, launches));
+        if (on > 0 || cur_n > 0) LQB_TRY(run_segment(segs[k], cur, dst, cur_n, on, ch0, nch, stream, in_tm, out_tm, launches, k == 0 ? first_extra : 0u));
         if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[k].second, stream));
         cur = dst; cur_n = on; flip ^= 1; in_tm = out_tm;
     }
@@ -629,9 +643,10 @@ static void advance_all(lqb_chain_s *c, size_t n) { for (auto *s : c->stages) { 
 
 static int chain_out_len(lqb_chain_s *c, size_t n, size_t *n_out) { for (auto *s : c->stages) n = s->out_len(n); *n_out = n; return LQB_OK; }
 
-static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, size_t cap, size_t *n_out, cudaStream_t stream)
+static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, size_t cap, size_t *n_out, cudaStream_t stream, bool in_i16 = false)
 {
     LQB_TRY(chain_validate(c));
+    if (in_i16 && c->stages.front()->in_real()) return fail(LQB_EINVAL, "int16 I/Q input needs a chain that starts with a complex-input stage");
     for (auto *s : c->stages) LQB_TRY(s->ensure());
     std::vector<Segment> segs; LQB_TRY(build_plan(c, segs));
     size_t on; chain_out_len(c, n, &on);
@@ -643,14 +658,16 @@ static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, s
     const size_t tmpb = max_intermediate_bytes(segs, n, (size_t)C);
     if (segs.size() > 1) LQB_TRY(c->d_tmp[0].reserve(tmpb));
     if (segs.size() > 2) LQB_TRY(c->d_tmp[1].reserve(tmpb));
-    LQB_TRY(run_all(c, segs, x, y, n, 0, C, c->d_tmp[0].p, c->d_tmp[1].p, stream, &c->last_launches, c->timing));
+    if (in_i16 && !first_takes_i16(segs)) LQB_TRY(c->d_cvt.reserve((size_t)C * n * 8));
+    LQB_TRY(run_all(c, segs, x, y, n, 0, C, c->d_tmp[0].p, c->d_tmp[1].p, stream, &c->last_launches, c->timing, in_i16, c->d_cvt.p));
     advance_all(c, n);
     return LQB_OK;
 }
 
-static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, size_t cap, size_t *n_out)
+static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, size_t cap, size_t *n_out, bool in_i16 = false)
 {
     LQB_TRY(chain_validate(c));
+    if (in_i16 && c->stages.front()->in_real()) return fail(LQB_EINVAL, "int16 I/Q input needs a chain that starts with a complex-input stage");
     for (auto *s : c->stages) LQB_TRY(s->ensure());
     std::vector<Segment> segs; LQB_TRY(build_plan(c, segs));
     size_t on; chain_out_len(c, n, &on);
@@ -659,7 +676,8 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
     c->last_launches = 0;
     if (n == 0) return LQB_OK;
     const int C = c->stages[0]->C;
-    const size_t ib = elem_bytes(c->stages.front()->in_real()), ob = elem_bytes(c->stages.back()->out_real());
+    const size_t ib = in_i16 ? 4 : elem_bytes(c->stages.front()->in_real()), ob = elem_bytes(c->stages.back()->out_real());
+    const bool need_cvt = in_i16 && !first_takes_i16(segs);
     // Channel chunks on three streams: the H2D of chunk i+1 overlaps the kernels of chunk i.  A sequential
     // kernel takes about as long for 64 channels as for 64K (it is bound by the per-channel recurrence), so
     // chunks are few and large: an eighth of the call, at least 64 MB of input.
@@ -678,6 +696,7 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
     if (deferred) LQB_TRY(c->h_out[0].reserve(std::max<size_t>(16, out_total)));
     for (size_t s = 0; s < std::min<size_t>(nchunks, lqb_chain_s::kStreams); s++) {
         LQB_TRY(c->h_in[s].reserve(chunk * n * ib));
+        if (need_cvt) LQB_TRY(c->h_cvt[s].reserve(chunk * n * 8));
         if (!deferred) LQB_TRY(c->h_out[s].reserve(std::max<size_t>(16, chunk * on * ob)));
         if (segs.size() > 1) LQB_TRY(c->h_tmp[s][0].reserve(tmpb));
         if (segs.size() > 2) LQB_TRY(c->h_tmp[s][1].reserve(tmpb));
@@ -687,7 +706,7 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
         const size_t c0 = k * chunk, nc = std::min(chunk, (size_t)C - c0);
         char *dst = deferred ? c->h_out[0].p + c0 * on * ob : c->h_out[s].p;
         LQB_CUDA(cudaMemcpyAsync(c->h_in[s].p, (const char *)x + c0 * n * ib, nc * n * ib, cudaMemcpyHostToDevice, c->streams[s]));
-        LQB_TRY(run_all(c, segs, c->h_in[s].p, dst, n, (int)c0, (int)nc, c->h_tmp[s][0].p, c->h_tmp[s][1].p, c->streams[s], &c->last_launches));
+        LQB_TRY(run_all(c, segs, c->h_in[s].p, dst, n, (int)c0, (int)nc, c->h_tmp[s][0].p, c->h_tmp[s][1].p, c->streams[s], &c->last_launches, false, in_i16, c->h_cvt[s].p));
         if (on && !deferred) LQB_CUDA(cudaMemcpyAsync((char *)y + c0 * on * ob, dst, nc * on * ob, cudaMemcpyDeviceToHost, c->streams[s]));
     }
     for (int s = 0; s < lqb_chain_s::kStreams; s++) LQB_CUDA(cudaStreamSynchronize(c->streams[s]));
@@ -1019,6 +1038,21 @@ int lqb_chain_out_len(lqb_chain c, size_t n, size_t *n_out) { if (!c || !n_out) 
 int lqb_chain_execute(lqb_chain c, const void *x, size_t n, void *y, size_t cap, size_t *n_out) { if (!c) return fail(LQB_EINVAL, "null chain"); return chain_execute_host(c, x, n, y, cap, n_out); }
 int lqb_chain_execute_dev(lqb_chain c, const void *x, size_t n, void *y, size_t cap, size_t *n_out, void *stream)
 { if (!c) return fail(LQB_EINVAL, "null chain"); return chain_execute_dev(c, x, n, y, cap, n_out, (cudaStream_t)stream); }
+int lqb_chain_execute_i16(lqb_chain c, const int16_t *iq, size_t n, void *y, size_t cap, size_t *n_out)
+{ if (!c) return fail(LQB_EINVAL, "null chain"); return chain_execute_host(c, iq, n, y, cap, n_out, true); }
+int lqb_chain_execute_i16_dev(lqb_chain c, const int16_t *iq_dev, size_t n, void *y_dev, size_t cap, size_t *n_out, void *stream)
+{ if (!c) return fail(LQB_EINVAL, "null chain"); return chain_execute_dev(c, iq_dev, n, y_dev, cap, n_out, (cudaStream_t)stream, true); }
+int lqb_bytes_to_iq(const int16_t *iq, size_t n, lqb_cf *out)
+{
+    if (!iq || !out) return fail(LQB_EINVAL, "null argument");
+    if (n == 0) return LQB_OK;
+    DevArr<char> in, o;
+    LQB_TRY(in.alloc(n * 4)); LQB_TRY(o.alloc(n * 8));
+    LQB_CUDA(cudaMemcpy(in.p, iq, n * 4, cudaMemcpyHostToDevice));
+    LQB_CUDA(i16_to_c64_launch(in.p, (float2 *)o.p, (long long)n, nullptr));
+    LQB_CUDA(cudaMemcpy(out, o.p, n * 8, cudaMemcpyDeviceToHost));
+    return LQB_OK;
+}
 int lqb_chain_plan(lqb_chain c, char *buf, size_t len)
 {
     if (!c || !buf || !len) return fail(LQB_EINVAL, "null argument");

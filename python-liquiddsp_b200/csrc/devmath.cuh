@@ -108,6 +108,17 @@ __device__ __forceinline__ float log_rn(float x, const double2 *__restrict__ tab
     return (float)fma(p, r, fma((double)e, 0.6931471805599453094, t.y));
 }
 
+// bytes_to_iq (reference utility.hpp:61-69): (float)s / 32767.0f for an int16 pair.  One Newton step on s * fl(1/32767)
+// gives the correctly rounded quotient for every one of the 65536 possible inputs (checked exhaustively in
+// tests/test_oracle_kat.py), without an IEEE division per sample.
+__device__ __forceinline__ float2 i16_to_iq(unsigned packed)
+{
+    const float r = (float)(1.0 / 32767.0);
+    const float a = (float)(short)(packed & 0xffffu), b = (float)(short)(packed >> 16);
+    const float qa = __fmul_rn(a, r), qb = __fmul_rn(b, r);
+    return make_float2(__fmaf_rn(__fmaf_rn(-qa, 32767.0f, a), r, qa), __fmaf_rn(__fmaf_rn(-qb, 32767.0f, b), r, qb));
+}
+
 __device__ __forceinline__ unsigned nco_index(uint32_t theta) { return ((theta + (1u << 21)) >> 22) & 0x3ffu; }
 
 }  // namespace lqb

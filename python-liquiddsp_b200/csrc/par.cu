@@ -131,7 +131,22 @@ __global__ void nco_par_kernel(const NcoP q, const float2 *__restrict__ x, float
     }
 }
 
+// bytes_to_iq over a whole block: interleaved int16 I/Q -> complex64 (reference utility.hpp:61-69)
+__global__ void i16_to_c64_kernel(const unsigned *__restrict__ x, float2 *__restrict__ y, long long total)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        y[i] = i16_to_iq(x[i]);
+}
+
 }  // namespace
+
+cudaError_t i16_to_c64_launch(const void *x, float2 *y, long long total, cudaStream_t stream)
+{
+    if (total <= 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+    i16_to_c64_kernel<<<blocks, 256, 0, stream>>>((const unsigned *)x, y, total);
+    return cudaGetLastError();
+}
 
 cudaError_t nco_par_launch(const NcoP &q, const float2 *x, float2 *y, int nch, int ch0, long long n, cudaStream_t stream)
 {

@@ -11,4 +11,6 @@ cudaError_t resamp_par_launch(const ResampP &p, const NcoP *nco, const float2 *x
 inline int resamp_par_launch_count(bool has_nco, long long n_out) { return (n_out > 0 ? 1 : 0) + 1 + (has_nco ? 1 : 0); }
 // oscillator mix alone, phase in closed form (theta_0 + k * d_theta mod 2^32)
 cudaError_t nco_par_launch(const NcoP &q, const float2 *x, float2 *y, int nch, int ch0, long long n, cudaStream_t stream);
+// interleaved int16 I/Q pairs -> complex64, (float)s / 32767.0f exactly
+cudaError_t i16_to_c64_launch(const void *x, float2 *y, long long total, cudaStream_t stream);
 }  // namespace lqb

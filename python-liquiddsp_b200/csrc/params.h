@@ -16,7 +16,8 @@ constexpr int kAmRing   = 64;    // power-of-two ring >= kAmTaps
 constexpr int kMaxResampSub = 64; // resampler sub-filter length limit for the fused path (2*m)
 
 enum : unsigned {
-    F_NCO = 1u, F_IIR = 2u, F_RS = 4u, F_AGC = 8u, F_AM = 16u, F_FM = 32u, F_DE = 64u, F_INREAL = 128u
+    F_NCO = 1u, F_IIR = 2u, F_RS = 4u, F_AGC = 8u, F_AM = 16u, F_FM = 32u, F_DE = 64u, F_INREAL = 128u,
+    F_INI16 = 256u                 // input rows are interleaved int16 I/Q (bytes_to_iq fused into the first stage)
 };
 
 struct NcoP {

@@ -48,9 +48,10 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
 {
     constexpr bool HAS_NCO = (M & F_NCO) != 0, HAS_IIR = (M & F_IIR) != 0, HAS_RS = (M & F_RS) != 0;
     constexpr bool HAS_AGC = (M & F_AGC) != 0, HAS_AM = (M & F_AM) != 0, HAS_FM = (M & F_FM) != 0;
-    constexpr bool HAS_DE = (M & F_DE) != 0, IN_REAL = (M & F_INREAL) != 0;
+    constexpr bool HAS_DE = (M & F_DE) != 0, IN_REAL = (M & F_INREAL) != 0, IN_I16 = (M & F_INI16) != 0;
     constexpr bool OUT_REAL = HAS_AM || HAS_FM || IN_REAL;
-    constexpr int  IELEM = IN_REAL ? 4 : 8, OELEM = OUT_REAL ? 4 : 8;
+    constexpr int  IELEM = (IN_REAL || IN_I16) ? 4 : 8, OELEM = OUT_REAL ? 4 : 8;
+    static_assert(!IN_I16 || HAS_RS, "int16 ingest is compiled for the decimating front kernels");
     using GI = Geo<IELEM>; using GO = Geo<OELEM>;
     constexpr int  PIN = GI::PITCH, POUT = GO::PITCH;
     constexpr int  NS = NSOS > 0 ? NSOS : 1;
@@ -377,6 +378,26 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
         }
         return x;
     };
+    // one staged sample / a whole staged row as complex floats (int16 I/Q pairs are converted on the way)
+    auto ld1 = [&](const unsigned char *rw, int j) -> float2 {
+        if constexpr (IN_I16) return i16_to_iq(*(const unsigned *)(rw + j * 4));
+        else return *(const float2 *)(rw + j * 8);
+    };
+    auto ld_row = [&](const unsigned char *rw, u64 (&xs)[TS]) {
+        if constexpr (IN_I16) {
+#pragma unroll
+            for (int j = 0; j < TS; j += 4) {
+                const uint4 v = *(const uint4 *)(rw + j * 4);
+                xs[j] = pk(i16_to_iq(v.x)); xs[j + 1] = pk(i16_to_iq(v.y)); xs[j + 2] = pk(i16_to_iq(v.z)); xs[j + 3] = pk(i16_to_iq(v.w));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < TS; j += 2) {
+                const float4 v = *(const float4 *)(rw + j * 8);
+                xs[j] = pk(v.x, v.y); xs[j + 1] = pk(v.z, v.w);
+            }
+        }
+    };
     // resampler step for one sample: acc = acc*keep + round(tap*x).  keep is 1 (0 right after an
     // output) and comes from shared memory, so the two roundings of liquid's complex-tap dot product
     // (product, then sum) survive as FMUL2 + FFMA2; ptxas contracts a plain mul.f32x2 + add.f32x2 pair
@@ -424,11 +445,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 // the per-sample capture of the finished dot product.
                 auto body = [&](auto with_emit) {
                     u64 xs[TS];
-#pragma unroll
-                    for (int j = 0; j < TS; j += 2) {
-                        const float4 v = *(const float4 *)(row + j * 8);
-                        xs[j] = pk(v.x, v.y); xs[j + 1] = pk(v.z, v.w);
-                    }
+                    ld_row(row, xs);
                     u64 yy[NS], outv = 0;
 #pragma unroll
                     for (int k = 0; k < TS + NS - 1; k++) {
@@ -454,20 +471,18 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 };
                 if (e < 0) body(std::false_type{}); else body(std::true_type{});
             } else if constexpr (HAS_RS && !BIG_TAIL) {
-                u64 outv = 0;
+                u64 outv = 0, xs[TS];
+                ld_row(row, xs);
 #pragma unroll
-                for (int j = 0; j < TS; j += 2) {
-                    const float4 v = *(const float4 *)(row + j * 8);
-                    rs_step(head(make_float2(v.x, v.y)), tk[j]);
+                for (int j = 0; j < TS; j++) {
+                    rs_step(head(upk(xs[j])), tk[j]);
                     if (j == e) outv = rs_acc;
-                    rs_step(head(make_float2(v.z, v.w)), tk[j + 1]);
-                    if (j + 1 == e) outv = rs_acc;
                 }
                 if (e >= 0) tail(upk(outv), e);
             } else if constexpr (HAS_RS) {
 #pragma unroll 1
                 for (int j = 0; j < TS; j++) {
-                    rs_step(head(*(const float2 *)(row + j * 8)), tk[j]);
+                    rs_step(head(ld1(row, j)), tk[j]);
                     if (j == e) tail(upk(rs_acc), j);
                 }
             } else if constexpr (BIG_TAIL) {
@@ -536,7 +551,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 if constexpr (IN_REAL) {
                     tail(make_float2(*(const float *)(row + j * 4), 0.f), j);
                 } else {
-                    const u64 x = head(*(const float2 *)(row + j * 8));
+                    const u64 x = head(ld1(row, j));
                     if constexpr (HAS_RS) {
                         rs_step(x, tk[j]);
                         if (n0 + j >= N - L && active) a.rs.ring[(int)((a.rs.count + n0 + j) % L) * CT + gch] = upk(x);
@@ -592,6 +607,7 @@ const Entry kTable[] = {
     // fused runs
     LQB_E(F_NCO | F_RS, 0),
     LQB_E_IIR(F_IIR | F_RS),
+    LQB_E(F_INI16 | F_NCO | F_RS, 0), LQB_E_IIR(F_INI16 | F_IIR | F_RS),      // int16 I/Q ingest fused into the front kernel
     LQB_E(F_AGC | F_FM, 0), LQB_E(F_FM | F_DE, 0), LQB_E(F_AGC | F_FM | F_DE, 0),
     LQB_E_IIR(F_IIR | F_AGC | F_FM),
     LQB_E(F_IIR | F_RS | F_AGC | F_AM | F_DE, 4),
@@ -607,7 +623,7 @@ const Entry *find(unsigned mask, int nsos)
 
 size_t smem_bytes(unsigned m, const SeqArgs &a)
 {
-    const bool in_real = m & F_INREAL, out_real = (m & (F_AM | F_FM | F_INREAL)) != 0;
+    const bool in_real = (m & (F_INREAL | F_INI16)) != 0, out_real = (m & (F_AM | F_FM | F_INREAL)) != 0;
     const int pin = TS * (in_real ? 4 : 8) + 16, pout = TS * (out_real ? 4 : 8) + 16;
     const size_t rows = (size_t)(BT / 32) * a.cpw;
     size_t b = (size_t)NST * rows * pin;

@@ -20,7 +20,7 @@ import ctypes as C
 import os
 import numpy as np
 
-__all__ = ["ComplexIIRFilter", "DeemphasisFilter", "FIRFilter", "ComplexResampler", "NCO", "AGC",
+__all__ = ["bytes_to_iq", "ComplexIIRFilter", "DeemphasisFilter", "FIRFilter", "ComplexResampler", "NCO", "AGC",
            "AmpModem", "FreqDem", "Chain", "synth_fill", "lib_path"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -79,6 +79,8 @@ _SIG = {
     "lqb_chain_out_len": [_P, _SZ, C.POINTER(_SZ)],
     "lqb_chain_execute": [_P, _P, _SZ, _P, _SZ, C.POINTER(_SZ)],
     "lqb_chain_execute_dev": [_P, _P, _SZ, _P, _SZ, C.POINTER(_SZ), _P],
+    "lqb_chain_execute_i16": [_P, _P, _SZ, _P, _SZ, C.POINTER(_SZ)],
+    "lqb_chain_execute_i16_dev": [_P, _P, _SZ, _P, _SZ, C.POINTER(_SZ), _P], "lqb_bytes_to_iq": [_P, _SZ, _P],
     "lqb_chain_set_timing": [_P, _I], "lqb_chain_get_timing": [_P, _P, _I, C.POINTER(_I), C.POINTER(_I)],
     "lqb_chain_plan": [_P, C.c_char_p, _SZ], "lqb_chain_last_launches": [_P, C.POINTER(_I)], "lqb_chain_set_fusion": [_P, _I],
     "lqb_synth_fill": [_I, _P, _I, _I, _SZ, _U64, _U64, _P],
@@ -484,13 +486,46 @@ class Chain(_Stage):
             s._after()
 
     def __call__(self, x):
+        """x: complex64 [channels x samples] (or 1-D for one channel); or interleaved int16 I/Q, shape
+        [channels x 2*samples] / [2*samples] -- the SDR wire format, converted inside the first kernel."""
         self._sync()
+        if isinstance(x, np.ndarray) and x.dtype == np.int16:
+            return self._run_i16(x)
         return self._run(_lib.lqb_chain_execute, self._h, x)
+
+    def _run_i16(self, x):
+        x = np.ascontiguousarray(x)
+        flat = x.ndim == 1
+        x2 = x.reshape(1, -1) if flat else x
+        ch = self.channels
+        if x2.ndim != 2 or x2.shape[0] != ch or x2.shape[1] % 2:
+            raise ValueError("expected int16 I/Q of shape [%d x 2*samples], got %r" % (ch, x.shape))
+        n = x2.shape[1] // 2
+        n_out = _SZ(); _ck(_lib.lqb_chain_out_len(self._h, n, C.byref(n_out)))
+        y = np.empty((ch, n_out.value), dtype=self._out_dtype)
+        got = _SZ()
+        _ck(_lib.lqb_chain_execute_i16(self._h, _ptr(x2), n, _ptr(y), n_out.value, C.byref(got)))
+        self._after()
+        return y.reshape(-1) if flat else y
+
+    def execute_i16_dev(self, iq_ptr, n, y_ptr, y_capacity, stream=0):
+        got = _SZ()
+        _ck(_lib.lqb_chain_execute_i16_dev(self._h, C.c_void_p(iq_ptr), n, C.c_void_p(y_ptr), y_capacity, C.byref(got), C.c_void_p(stream)))
+        return got.value
 
     def execute_dev(self, x_ptr, n, y_ptr, y_capacity, stream=0):
         got = _SZ()
         _ck(_lib.lqb_chain_execute_dev(self._h, C.c_void_p(x_ptr), n, C.c_void_p(y_ptr), y_capacity, C.byref(got), C.c_void_p(stream)))
         return got.value
+
+
+def bytes_to_iq(b):
+    """wrapper.cpp:13 / utility.hpp:61-69: interleaved little-endian int16 I/Q bytes -> complex64, x / 32767."""
+    a = np.ascontiguousarray(np.frombuffer(b, dtype="<i2"))
+    n = a.size // 2
+    y = np.empty(n, np.complex64)
+    _ck(_lib.lqb_bytes_to_iq(_ptr(a), n, _ptr(y)))
+    return y
 
 
 def synth_fill(kind, x_ptr, n_channels, n, channel0=0, n0=0, seed=0xB200, stream=0):

@@ -209,6 +209,19 @@ def test_bytes_to_iq():
     assert np.allclose(O.bytes_to_iq(raw), [1 - 1j, 0 + 1j / 32767])
 
 
+def test_int16_conversion_without_division_is_exact():
+    """The device converts int16 -> float with s*r followed by one Newton step (r = fl(1/32767)) instead of an IEEE
+    division; for all 65536 inputs that is the correctly rounded (float)s / 32767.0f of utility.hpp:65-66."""
+    s16 = np.arange(-32768, 32768, dtype=np.int32)
+    ref = O.bytes_to_iq(np.stack([s16, s16[::-1]], axis=1).astype("<i2").tobytes())
+    r = np.float32(1.0 / 32767.0); sf = s16.astype(np.float32)
+    q0 = (sf * r).astype(np.float32)
+    res = (sf.astype(np.float64) - q0.astype(np.float64) * 32767.0).astype(np.float32)     # fma(-q0, 32767, s), exact in double
+    q = (q0.astype(np.float64) + res.astype(np.float64) * np.float64(r)).astype(np.float32)  # fma(res, r, q0)
+    assert np.array_equal(q, ref.real) and np.array_equal(q[::-1], ref.imag)
+    assert np.array_equal(ref.real, (sf / np.float32(32767.0)).astype(np.float32))
+
+
 def test_oracle_frozen_vectors():
     """Regression-freeze of the oracle itself (same image on the GPU box -> same libm -> same bits)."""
     x = VEC["x"]

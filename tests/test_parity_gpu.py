@@ -473,6 +473,41 @@ def test_config4_iir_agc_fm(cuda):
             assert np.linalg.norm(y[c] - yo) / np.sqrt(n) <= 5 * TOL_E2E, c
 
 
+def _to_i16(rng, C, n, amp=6000):
+    a = rng.integers(-amp, amp, size=(C, 2 * n)).astype(np.int16)
+    t = np.arange(n)
+    car = (8000 * (1 + 0.5 * np.sin(2 * np.pi * 1000 * t / 2e6)) * np.exp(2j * np.pi * 300 * t / 2e6))
+    a[:, 0::2] += car.real.astype(np.int16); a[:, 1::2] += car.imag.astype(np.int16)
+    return a
+
+
+def test_bytes_to_iq_all_values(cuda):
+    s16 = np.arange(-32768, 32768, dtype=np.int32)
+    raw = np.stack([s16, s16[::-1]], axis=1).astype("<i2").tobytes()
+    assert np.array_equal(L.bytes_to_iq(raw).view(np.uint32), O.bytes_to_iq(raw).view(np.uint32))
+
+
+@pytest.mark.parametrize("C,n", [(1, 65536), (70, 8192), (70, 8190), (60000, 2048)])
+def test_int16_ingest_fused_equals_convert_then_filter(cuda, C, n):
+    """Interleaved int16 I/Q fed straight to the chain == bytes_to_iq on the host followed by the same chain."""
+    rng = np.random.default_rng(31)
+    raw = _to_i16(rng, min(C, 64), n)
+    raw = np.tile(raw, (C // raw.shape[0] + 1, 1))[:C].copy()
+    a, b = _Radio(L, channels=C), _Radio(L, channels=C)
+    ca, cb = L.Chain(*a.stages()), L.Chain(*b.stages())
+    for blk in range(2):
+        x = np.stack([O.bytes_to_iq(raw[c].tobytes()) for c in range(min(C, 64))])
+        x = np.tile(x, (C // x.shape[0] + 1, 1))[:C].copy()
+        ya = ca(raw if C > 1 else raw[0])
+        yb = cb(x if C > 1 else x[0])
+        assert np.array_equal(np.asarray(ya).view(np.uint32), np.asarray(yb).view(np.uint32)), (C, n, blk)
+    if C == 70:
+        o = _oracle_radio_with_product_coeffs(a); ref = None
+        for blk in range(2):
+            ref = o(O.bytes_to_iq(raw[5].tobytes()))
+        assert rel_l2(np.asarray(ya)[5], ref) <= TOL_E2E
+
+
 def test_execute_dev_and_chunked_host_agree(cuda):
     """Device-pointer entry point == host entry point (which chunks channels over three streams)."""
     C, n = 300, 65536                                     # 157 MB of input -> 3 chunks
