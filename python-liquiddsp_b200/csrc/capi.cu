@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -108,6 +109,31 @@ static int log_table_dev(const double2 **out)
     }
     *out = it->second;
     return LQB_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (getenv("LQB_NO_TMA")) return (EncodeTiledFn) nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// rows of n complex64 samples as a 2-D float tensor [rows][2n]; box = one warp's tile: 32 rows x 16 samples (128 B), 128B swizzle
+static bool make_input_tmap(CUtensorMap *tm, const void *x, size_t n, size_t rows)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc || (((size_t)x) & 15) || (n & 1) || n * 2 > 0xffffffffull) return false;
+    const cuuint64_t gdim[2] = { (cuuint64_t)n * 2, (cuuint64_t)rows }, gstride[1] = { (cuuint64_t)n * 8 };
+    const cuuint32_t box[2] = { 32, 32 }, estr[2] = { 1, 1 };
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ------------------------------------------------------------------------------------ stages
@@ -571,6 +597,8 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         default: return fail(LQB_EINVAL, "stage kind %d cannot run in the sequential kernel", (int)s->kind);
         }
     }
+    // Blackwell data path for the many-channel front kernels: TMA tiled loads instead of per-lane cp.async
+    a.use_tma = (a.cpw == 32 && extra_mask == 0 && !in_real && seq_has_tma(g.mask, g.nsos) && make_input_tmap(&a.tmap, x, n, (size_t)nch)) ? 1 : 0;
     LQB_CUDA(seq_launch(g.mask | extra_mask, g.nsos, a, stream));
     return LQB_OK;
 }

@@ -41,6 +41,36 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ---------------------------------
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tLQB_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra LQB_WAIT;\n\t}" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+// bytes: multiple of 16; both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void *gsrc, unsigned bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// one [32 rows x 128 B] box of a 2-D tensor map into shared memory (SASS UTMALDG), completing on an mbarrier
+__device__ __forceinline__ void tma_load_2d(unsigned smem_dst, const void *tmap, int c0, int c1, void *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
 // radians -> uint32 phase, the oscillator's own arithmetic (see design.hpp nco_constrain): the
 // 1/(2 pi) product is taken in double and rounded to float, everything after is float; a
 // fractional part that rounds up to 1.0f wraps to phase 0.

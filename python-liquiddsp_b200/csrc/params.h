@@ -6,6 +6,7 @@
 // length; the host tracks the count, the kernels never move ring contents.
 #pragma once
 #include <stdint.h>
+#include <cuda.h>          // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace lqb {
 
@@ -69,7 +70,8 @@ struct AmP {
 struct FmP { float ref; float2 *rprime; };          // [Ctot]
 struct DeP { float b0, a1; float *v1; };            // [Ctot]
 
-struct SeqArgs {
+struct alignas(64) SeqArgs {
+    CUtensorMap tmap;              // TMA mode: the input as a 2-D tensor [C rows][2n floats], box 32 floats x 32 rows, 128B swizzle
     const void *x;                 // [C][n] input rows (complex64, or float32 when F_INREAL)
     void *y;                       // [C][out_pitch] output rows
     int C;                         // channels in this launch
@@ -77,6 +79,7 @@ struct SeqArgs {
     int Ctot;                      // channel stride of the state arrays
     int vec_in, vec_out;           // 1 when rows allow 16-byte vector access
     int cpw;                       // channels per warp: 32, or 16 / 8 to spread few channels over more warps
+    int use_tma;                   // tmap is valid: stage the input with TMA (full-warp kernels that have the variant)
     int out_tmajor;                // decimated output stored [sample][channel] (hand-off to the AM tail kernel)
     long long n, out_pitch;
     NcoP nco; IirP iir; ResampP rs; AgcP agc; AmP am; FmP fm; DeP de;

@@ -43,15 +43,23 @@ template <int ELEM> struct Geo {
 };
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <unsigned M, int NSOS, bool FULL>
+// MODE 0: 8 / 16 channels per warp (few channels), cp.async staging
+// MODE 1: 32 channels per warp, cp.async staging, padded row pitch
+// MODE 2: 32 channels per warp, TMA staging: one elected lane issues one cp.async.bulk.tensor.2d per tile for the
+//         warp's whole [32 rows x 128 B] box, 128-byte swizzle (row r's 16-byte chunk j sits at chunk j ^ (r & 7), so
+//         the 8 lanes of an LDS.128 phase hit 8 distinct bank groups without padding), completion on a per-warp
+//         mbarrier; rows past the last channel and samples past the end of the call are zero-filled by the hardware
+template <unsigned M, int NSOS, int MODE>
 __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __grid_constant__ SeqArgs a)
 {
+    constexpr bool FULL = MODE != 0, TMA = MODE == 2;
     constexpr bool HAS_NCO = (M & F_NCO) != 0, HAS_IIR = (M & F_IIR) != 0, HAS_RS = (M & F_RS) != 0;
     constexpr bool HAS_AGC = (M & F_AGC) != 0, HAS_AM = (M & F_AM) != 0, HAS_FM = (M & F_FM) != 0;
     constexpr bool HAS_DE = (M & F_DE) != 0, IN_REAL = (M & F_INREAL) != 0, IN_I16 = (M & F_INI16) != 0;
     constexpr bool OUT_REAL = HAS_AM || HAS_FM || IN_REAL;
     constexpr int  IELEM = (IN_REAL || IN_I16) ? 4 : 8, OELEM = OUT_REAL ? 4 : 8;
     static_assert(!IN_I16 || HAS_RS, "int16 ingest is compiled for the decimating front kernels");
+    static_assert(!TMA || (IELEM == 8 && HAS_RS), "TMA staging is compiled for complex64 input of the decimating front kernels");
     using GI = Geo<IELEM>; using GO = Geo<OELEM>;
     constexpr int  PIN = GI::PITCH, POUT = GO::PITCH;
     constexpr int  NS = NSOS > 0 ? NSOS : 1;
@@ -63,9 +71,12 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     // get 2-4x as many independent chains to interleave.  The idle lanes still help stage the tiles.
     // (FULL: 32 channels per warp known at compile time -- the many-channel instantiation carries no extra arithmetic)
     const int cpw = FULL ? 32 : a.cpw, RCTA = (BT / 32) * cpw;     // rows (channels) per CTA
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char *s_in  = smem;                                   // NST stages of [RCTA][PIN]
-    unsigned char *s_out = s_in + NST * RCTA * PIN;                // [RCTA][POUT] when the output is full rate
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // the swizzled TMA boxes need 1024-byte alignment
+    unsigned char *smem = TMA ? (unsigned char *)(((size_t)smem_raw + 1023) & ~(size_t)1023) : smem_raw;
+    constexpr int PINS = TMA ? TS * IELEM : PIN;                   // staged row pitch: dense under TMA, padded otherwise
+    unsigned char *s_in  = smem;                                   // NST stages of [RCTA][PINS]
+    unsigned char *s_out = s_in + NST * RCTA * PINS;               // [RCTA][POUT] when the output is full rate
     unsigned char *s_nxt = s_out + (HAS_RS ? 0 : RCTA * POUT);
     float2 *s_tap = (float2 *)s_nxt;                               // [warp][NST][TS] (tap, keep)
     s_nxt += HAS_RS ? (BT / 32) * NST * TS * sizeof(float2) : 0;
@@ -130,6 +141,10 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     }
     if constexpr (HAS_FM) fm_prev = a.fm.rprime[gch];
     if constexpr (HAS_DE) de_v1 = a.de.v1[gch];
+    __shared__ unsigned long long s_bar[(BT / 32) * NST];          // TMA mode: one mbarrier per warp and stage
+    if constexpr (TMA) {
+        if (tid == 0) { for (int i = 0; i < (BT / 32) * NST; i++) mbar_init(&s_bar[i], 1); mbar_init_fence(); }
+    }
     __syncthreads();
 
     // resampler: the first output's window may start before this call; that part comes from the ring
@@ -203,7 +218,16 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             src += grow;
         }
     };
+    const unsigned s_in_sh = (unsigned)__cvta_generic_to_shared(s_in);
     auto load_tile = [&](long long t, int stage) {
+        if constexpr (TMA) {
+            if (lane == 0) {
+                unsigned long long *bar = &s_bar[wid * NST + stage];
+                mbar_arrive_expect_tx(bar, 32 * TS * IELEM);
+                tma_load_2d(s_in_sh + stage * (RCTA * PINS) + wid * (32 * PINS), &a.tmap, (int)(t * (TS * 2)), (int)(blockIdx.x * RCTA + wid * 32), bar);
+            }
+            return;
+        }
         if (fast_cta && t < nfull) { load_tile_fast(t, stage); return; }
         const long long e0 = t * TS + (long long)lk * GI::EPC;    // first element of this thread's chunks
         const char *src = gsrc + t * (TS * IELEM);
@@ -379,8 +403,10 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
         return x;
     };
     // one staged sample / a whole staged row as complex floats (int16 I/Q pairs are converted on the way)
+    const unsigned swz = TMA ? (unsigned)(lane & 7) : 0u;        // this lane's chunk permutation under the 128-byte swizzle
     auto ld1 = [&](const unsigned char *rw, int j) -> float2 {
         if constexpr (IN_I16) return i16_to_iq(*(const unsigned *)(rw + j * 4));
+        else if constexpr (TMA) return *(const float2 *)(rw + ((((unsigned)j >> 1) ^ swz) << 4) + (j & 1) * 8);
         else return *(const float2 *)(rw + j * 8);
     };
     auto ld_row = [&](const unsigned char *rw, u64 (&xs)[TS]) {
@@ -389,6 +415,12 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             for (int j = 0; j < TS; j += 4) {
                 const uint4 v = *(const uint4 *)(rw + j * 4);
                 xs[j] = pk(i16_to_iq(v.x)); xs[j + 1] = pk(i16_to_iq(v.y)); xs[j + 2] = pk(i16_to_iq(v.z)); xs[j + 3] = pk(i16_to_iq(v.w));
+            }
+        } else if constexpr (TMA) {
+#pragma unroll
+            for (int j = 0; j < TS; j += 2) {
+                const float4 v = *(const float4 *)(rw + ((((unsigned)j >> 1) ^ swz) << 4));
+                xs[j] = pk(v.x, v.y); xs[j + 1] = pk(v.z, v.w);
             }
         } else {
 #pragma unroll
@@ -413,16 +445,22 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
         cp_async_commit();
     }
     int stage = 0;
+    unsigned phases = 0;                       // TMA mode: parity of each stage's mbarrier
 #pragma unroll 1
     for (long long t = 0; t < ntiles; t++) {
-        cp_async_wait<NST - 2>();
+        if constexpr (TMA) {
+            mbar_wait(&s_bar[wid * NST + stage], (phases >> stage) & 1u);
+            phases ^= 1u << stage;
+        } else {
+            cp_async_wait<NST - 2>();
+        }
         __syncwarp();                          // this warp's rows of tile t are in shared memory; its lanes are done with tile t-1
         {
             const int sn = stage == 0 ? NST - 1 : stage - 1;        // the stage tile t-1 occupied
             if (t + NST - 1 < ntiles) { load_tile(t + NST - 1, sn); gen_taps(sn, false); }
             cp_async_commit();
         }
-        const unsigned char *row = s_in + stage * (RCTA * PIN) + myrow * PIN;
+        const unsigned char *row = s_in + stage * (RCTA * PINS) + myrow * PINS;
         const float2 *tk = s_tap + (wid * NST + stage) * TS;
         int e = -1;
         if constexpr (HAS_RS) e = s_emit[wid * NST + stage];
@@ -596,23 +634,25 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
 
 // ---- dispatch ----------------------------------------------------------------------------------
 typedef void (*SeqFn)(const SeqArgs);
-struct Entry { unsigned mask; int nsos; SeqFn fn, fn_part; };       // full warps / 8-16 channels per warp
+struct Entry { unsigned mask; int nsos; SeqFn fn, fn_part, fn_tma; };       // full warps / 8-16 channels per warp / TMA staging
 
-#define LQB_E(M, S) { (M), (S), seq_kernel<(M), (S), true>, seq_kernel<(M), (S), false> }
+#define LQB_E(M, S) { (M), (S), seq_kernel<(M), (S), 1>, seq_kernel<(M), (S), 0>, nullptr }
+#define LQB_T(M, S) { (M), (S), seq_kernel<(M), (S), 1>, seq_kernel<(M), (S), 0>, seq_kernel<(M), (S), 2> }
 #define LQB_E_IIR(M) LQB_E(M, 1), LQB_E(M, 2), LQB_E(M, 3), LQB_E(M, 4)
 const Entry kTable[] = {
     // single stages
     LQB_E(F_NCO, 0), LQB_E(F_RS, 0), LQB_E(F_AGC, 0), LQB_E(F_FM, 0), LQB_E(F_DE | F_INREAL, 0),
     LQB_E_IIR(F_IIR), LQB_E(F_IIR, 5), LQB_E(F_IIR, 6), LQB_E(F_IIR, 7), LQB_E(F_IIR, 8),
     // fused runs
-    LQB_E(F_NCO | F_RS, 0),
-    LQB_E_IIR(F_IIR | F_RS),
+    LQB_T(F_NCO | F_RS, 0),
+    LQB_T(F_IIR | F_RS, 1), LQB_T(F_IIR | F_RS, 2), LQB_T(F_IIR | F_RS, 3), LQB_T(F_IIR | F_RS, 4),
     LQB_E(F_INI16 | F_NCO | F_RS, 0), LQB_E_IIR(F_INI16 | F_IIR | F_RS),      // int16 I/Q ingest fused into the front kernel
     LQB_E(F_AGC | F_FM, 0), LQB_E(F_FM | F_DE, 0), LQB_E(F_AGC | F_FM | F_DE, 0),
     LQB_E_IIR(F_IIR | F_AGC | F_FM),
     LQB_E(F_IIR | F_RS | F_AGC | F_AM | F_DE, 4),
 };
 #undef LQB_E
+#undef LQB_T
 #undef LQB_E_IIR
 
 const Entry *find(unsigned mask, int nsos)
@@ -621,12 +661,12 @@ const Entry *find(unsigned mask, int nsos)
     return nullptr;
 }
 
-size_t smem_bytes(unsigned m, const SeqArgs &a)
+size_t smem_bytes(unsigned m, const SeqArgs &a, bool tma)
 {
     const bool in_real = (m & (F_INREAL | F_INI16)) != 0, out_real = (m & (F_AM | F_FM | F_INREAL)) != 0;
     const int pin = TS * (in_real ? 4 : 8) + 16, pout = TS * (out_real ? 4 : 8) + 16;
     const size_t rows = (size_t)(BT / 32) * a.cpw;
-    size_t b = (size_t)NST * rows * pin;
+    size_t b = tma ? (size_t)NST * rows * (pin - 16) + 1024 : (size_t)NST * rows * pin;
     if (!(m & F_RS)) b += rows * pout;
     if (m & F_RS)  b += (BT / 32) * NST * TS * sizeof(float2) + 32 + (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15);
     if (m & F_NCO) b += 1024 * sizeof(float2);
@@ -638,6 +678,7 @@ size_t smem_bytes(unsigned m, const SeqArgs &a)
 }  // namespace
 
 bool seq_supported(unsigned mask, int nsos) { return find(mask, nsos) != nullptr; }
+bool seq_has_tma(unsigned mask, int nsos) { const Entry *e = find(mask, nsos); return e && e->fn_tma; }
 
 cudaError_t seq_launch(unsigned mask, int nsos, const SeqArgs &a, cudaStream_t stream)
 {
@@ -646,8 +687,9 @@ cudaError_t seq_launch(unsigned mask, int nsos, const SeqArgs &a, cudaStream_t s
     if (a.C <= 0 || a.n <= 0) return cudaSuccess;
     if (a.cpw != 8 && a.cpw != 16 && a.cpw != 32) return cudaErrorInvalidValue;
     if ((mask & F_AM) && a.cpw != 32) return cudaErrorInvalidValue;       // the in-kernel ampmodem rings are per thread
-    const size_t smem = smem_bytes(mask, a);
-    SeqFn fn = a.cpw == 32 ? e->fn : e->fn_part;
+    const bool tma = a.use_tma && a.cpw == 32 && e->fn_tma;
+    const size_t smem = smem_bytes(mask, a, tma);
+    SeqFn fn = tma ? e->fn_tma : (a.cpw == 32 ? e->fn : e->fn_part);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     const int rows = (BT / 32) * a.cpw;

@@ -10,6 +10,8 @@ constexpr int kSeqTS  = 16;   // samples per staged tile row (128 B of complex64
 
 // true when a kernel for this stage mask / section count was compiled
 bool seq_supported(unsigned mask, int nsos);
+// true when the kernel also exists with TMA (cp.async.bulk.tensor) input staging
+bool seq_has_tma(unsigned mask, int nsos);
 cudaError_t seq_launch(unsigned mask, int nsos, const SeqArgs &a, cudaStream_t stream);
 
 }  // namespace lqb
