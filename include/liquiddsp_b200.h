@@ -85,6 +85,13 @@ int lqb_iirfilt_crcf_freqresponse(lqb_stage s, float fc, lqb_cf *H);
 /* 0 = auto, 1 = channel-parallel sequential (bit-matches the oracle), 2 = time-parallel blocked scan */
 int lqb_iirfilt_crcf_set_mode(lqb_stage s, int mode);
 
+/* ---------------- iirfilt_rrrf (SOS) : RealIIRFilter iirfilter.hpp:301-356, RLowpassIIR.. :171-241 ------
+ * replaces iirfilt_rrrf_create_prototype (:180,198,216,234,332) and iirfilt_rrrf_execute_block.  real -> real.
+ * The C*IIR classes (:61-131) are lqb_iirfilt_crcf_create_prototype with the band type fixed. */
+int lqb_iirfilt_rrrf_create_prototype(int ftype, int btype, int order, float fc, float f0,
+                                      float ap, float as, int n_channels, lqb_stage *out);
+int lqb_iirfilt_rrrf_create_sos(const float *B, const float *A, int nsos, int n_channels, lqb_stage *out);
+
 /* ---------------- iirfilt_rrrf one-pole : DeemphasisFilter, iirfilter.hpp:358-392 ----------
  * replaces iirfilt_rrrf_create(b,1,a,2) (:371) and the per-sample iirfilt_rrrf_execute loop
  * (:388-389); coefficient formula of :366-370.  real in -> real out. */
@@ -97,6 +104,11 @@ int lqb_deemph_freqresponse(lqb_stage s, float fc, lqb_cf *H);
  * _freqresponse :27); the crcf form is what demod.hpp:105,135-136 uses.  complex -> complex. */
 int lqb_firfilt_crcf_create(const float *h, int h_len, int n_channels, lqb_stage *out);
 int lqb_firfilt_crcf_create_kaiser(int h_len, float fc, float as, float mu, int n_channels, lqb_stage *out);
+/* firfilt_rrrf : RealFIRFilter firfilter.hpp:5-36, RealDCBlocker :39-50 (create_dc_blocker), RealKaiserBessel
+ * :52-67 (create_kaiser, then set_scale(1/|H(0)|)).  real -> real; set_scale / get_taps / freqresponse below apply. */
+int lqb_firfilt_rrrf_create(const float *h, int h_len, int n_channels, lqb_stage *out);
+int lqb_firfilt_rrrf_create_kaiser(int h_len, float fc, float as, float mu, int n_channels, lqb_stage *out);
+int lqb_firfilt_rrrf_create_dc_blocker(int m, float as, int n_channels, lqb_stage *out);
 int lqb_firfilt_crcf_set_scale(lqb_stage s, float scale);
 int lqb_firfilt_crcf_get_taps(lqb_stage s, float *h, int *h_len);
 int lqb_firfilt_crcf_freqresponse(lqb_stage s, float fc, lqb_cf *H);

@@ -209,6 +209,35 @@ class ComplexIIRFilter:
         return y
 
 
+class RealIIRFilter(ComplexIIRFilter):
+    """wrapper.cpp:154-172, iirfilter.hpp:301-356.  iirfilt_rrrf runs the same section arithmetic on float samples;
+    with real coefficients the real lane of the crcf restatement IS that arithmetic, so it is run on x + 0j."""
+
+    def __call__(self, x):
+        return np.ascontiguousarray(ComplexIIRFilter.__call__(self, _f32(x).astype(_cf)).real)
+
+
+def _band_class(base, band, has_f0, name):
+    # iirfilter.hpp:61-131 (C*) and :171-241 (R*): band fixed, f0 = 0.1f for low/highpass, Ap = 0.5, As = 20 defaults
+    if has_f0:
+        def __init__(self, filter_type="butter", order=2, Fc=0.2, F0=0.3, Ap=0.5, As=20.0):
+            base.__init__(self, filter_type, band, order, Fc, F0, Ap, As)
+    else:
+        def __init__(self, filter_type="butter", order=2, Fc=0.2, Ap=0.5, As=20.0):
+            base.__init__(self, filter_type, band, order, Fc, 0.1, Ap, As)
+    return type(name, (base,), {"__init__": __init__})
+
+
+CLowpassIIR = _band_class(ComplexIIRFilter, "lowpass", False, "CLowpassIIR")
+CHighpassIIR = _band_class(ComplexIIRFilter, "highpass", False, "CHighpassIIR")
+CBandpassIIR = _band_class(ComplexIIRFilter, "bandpass", True, "CBandpassIIR")
+CBandstopIIR = _band_class(ComplexIIRFilter, "bandstop", True, "CBandstopIIR")
+RLowpassIIR = _band_class(RealIIRFilter, "lowpass", False, "RLowpassIIR")
+RHighpassIIR = _band_class(RealIIRFilter, "highpass", False, "RHighpassIIR")
+RBandpassIIR = _band_class(RealIIRFilter, "bandpass", True, "RBandpassIIR")
+RBandstopIIR = _band_class(RealIIRFilter, "bandstop", True, "RBandstopIIR")
+
+
 def iir_f64_truth(B, A, x):
     """Same recurrence in double with the same float32 coefficients."""
     B = np.ascontiguousarray(B, _f).ravel(); A = np.ascontiguousarray(A, _f).ravel()
@@ -246,6 +275,30 @@ class RealFIRFilter(FIRFilter):
         x = _f32(x); y = np.empty(x.shape[0], _f)
         lib.orc_firfilt_rrrf_execute_block(self._q, _p(x), x.shape[0], _p(y))
         return y
+
+
+class RealDCBlocker(RealFIRFilter):
+    """wrapper.cpp:249-252, firfilter.hpp:39-50."""
+
+    def __init__(self, slen=25, As=20.0):
+        self._q = lib.orc_firfilt_create_dc_blocker(slen, As)
+        if not self._q:
+            raise ValueError("firdes_notch failed")
+
+
+class RealKaiserBessel(RealFIRFilter):
+    """wrapper.cpp:254-257, firfilter.hpp:52-67: scale = 1.0 / abs(H(0)) (double division, narrowed to float)."""
+
+    def __init__(self, flen=25, Fc=0.25, As=20.0, offset=0.0):
+        self._q = lib.orc_firfilt_create_kaiser(flen, Fc, As, offset)
+        if not self._q:
+            raise ValueError("firdes_kaiser failed")
+        H0 = self.freqresponse(0.0)
+        mag = _f(np.hypot(_f(H0.real), _f(H0.imag)))
+        lib.orc_firfilt_set_scale(self._q, float(_f(1.0 / float(mag))))
+
+    def taps(self):
+        h = np.zeros(4096, _f); n = lib.orc_firfilt_get_taps(self._q, _p(h)); return h[:n].copy()
 
 
 class ComplexResampler:

@@ -169,6 +169,9 @@ namespace lqb {
 
 struct IirStage : lqb_stage_s {
     std::vector<float> B, A; int nsos = 0, mode = 0;
+    bool real_io = false;                               // iirfilt_rrrf: real samples (RealIIRFilter and the R* classes)
+    bool in_real() const override { return real_io; }
+    bool out_real() const override { return real_io; }
     DevArr<float2> v;                                   // [nsos][2][C]
     IirStage(int c) : lqb_stage_s(K_IIR, c) {}
     int init(const std::vector<float> &b, const std::vector<float> &a)
@@ -230,6 +233,9 @@ struct DeemphStage : lqb_stage_s {
 
 struct FirStage : lqb_stage_s {
     std::vector<float> h; float scale = 1.f; DevArr<float> taps; DevArr<float2> hist[2]; int cur = 0;
+    bool real_io = false;                               // firfilt_rrrf
+    bool in_real() const override { return real_io; }
+    bool out_real() const override { return real_io; }
     FirStage(int c) : lqb_stage_s(K_FIR, c) {}
     int materialize() override
     {
@@ -485,7 +491,7 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
             if (st[i]->kind == K_IIR) {              // long cascades: kMaxSos sections per launch
                 IirStage *q = static_cast<IirStage *>(st[i]);
                 for (int s0 = 0; s0 < q->nsos; s0 += kMaxSos) {
-                    Segment h; h.type = Segment::SEQ; h.mask = F_IIR; h.sos0 = s0; h.nsos = std::min(kMaxSos, q->nsos - s0);
+                    Segment h; h.type = Segment::SEQ; h.mask = F_IIR | (q->real_io ? F_INREAL : 0u); h.sos0 = s0; h.nsos = std::min(kMaxSos, q->nsos - s0);
                     h.st = { st[i] }; h.name = std::string(q->mode == 2 && q->nsos <= kMaxSos ? "scan" : "seq") + "[iir" + std::to_string(h.nsos) + "]"; segs.push_back(h);
                 }
                 i++; continue;
@@ -533,6 +539,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         const FirStage *f = static_cast<const FirStage *>(first);
         FirArgs a{};
         a.x = (const float2 *)x; a.y = (float2 *)y; a.C = nch; a.ch0 = ch0; a.Ctot = f->C; a.ntaps = (int)f->h.size();
+        a.real_io = f->real_io ? 1 : 0;
         a.n = (long long)n; a.scale = f->scale; a.taps = f->taps.p; a.hist_in = f->hist[f->cur].p; a.hist_out = f->hist[f->cur ^ 1].p;
         LQB_CUDA(fir_launch(a, stream));
         return LQB_OK;
@@ -552,7 +559,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         (*launches)++;
         return LQB_OK;
     }
-    if (g.type == Segment::SEQ && g.mask == F_IIR && g.st.size() == 1 && static_cast<IirStage *>(g.st[0])->mode == 2) {
+    if (g.type == Segment::SEQ && g.mask == F_IIR && g.st.size() == 1 && static_cast<IirStage *>(g.st[0])->mode == 2) {   // (complex data only)
         // time-parallel blocked scan when the call length allows equal blocks; otherwise the sequential kernel
         IirStage *q = static_cast<IirStage *>(g.st[0]);
         const int B = n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : (n % 64 == 0 ? 64 : 0));
@@ -802,6 +809,18 @@ int lqb_iirfilt_crcf_create_prototype(int ftype, int btype, int order, float fc,
     if (rc != 0) return fail(LQB_EINVAL, "iirdes: invalid design parameters (order %d, fc %g, f0 %g, ap %g, as %g)", order, fc, f0, ap, as);
     return lqb_iirfilt_crcf_create_sos(B.data(), A.data(), (int)B.size() / 3, C, out);
 }
+int lqb_iirfilt_rrrf_create_sos(const float *B, const float *A, int nsos, int C, lqb_stage *out)
+{
+    LQB_TRY(lqb_iirfilt_crcf_create_sos(B, A, nsos, C, out));
+    static_cast<IirStage *>(*out)->real_io = true;
+    return LQB_OK;
+}
+int lqb_iirfilt_rrrf_create_prototype(int ftype, int btype, int order, float fc, float f0, float ap, float as, int C, lqb_stage *out)
+{
+    LQB_TRY(lqb_iirfilt_crcf_create_prototype(ftype, btype, order, fc, f0, ap, as, C, out));
+    static_cast<IirStage *>(*out)->real_io = true;
+    return LQB_OK;
+}
 int lqb_iirfilt_crcf_get_sos(lqb_stage s, float *B, float *A, int *nsos)
 {
     LQB_GET(IirStage, q, s, K_IIR);
@@ -821,6 +840,7 @@ int lqb_iirfilt_crcf_set_mode(lqb_stage s, int mode)
     LQB_GET(IirStage, q, s, K_IIR);
     if (mode < 0 || mode > 2) return fail(LQB_EINVAL, "iirfilt mode must be 0, 1 or 2");
     if (mode == 2 && q->nsos > kMaxSos) return fail(LQB_EINVAL, "blocked-scan IIR supports up to %d sections", kMaxSos);
+    if (mode == 2 && q->real_io) return fail(LQB_ENOTIMPL, "blocked-scan IIR is built for complex samples only");
     q->mode = mode; return LQB_OK;
 }
 
@@ -850,6 +870,24 @@ int lqb_firfilt_crcf_create(const float *h, int n, int C, lqb_stage *out)
     FirStage *q = new FirStage(C);
     q->h.assign(h, h + n);
     *out = q; return LQB_OK;
+}
+int lqb_firfilt_rrrf_create(const float *h, int n, int C, lqb_stage *out)
+{
+    LQB_TRY(lqb_firfilt_crcf_create(h, n, C, out));
+    static_cast<FirStage *>(*out)->real_io = true;
+    return LQB_OK;
+}
+int lqb_firfilt_rrrf_create_kaiser(int n, float fc, float as, float mu, int C, lqb_stage *out)
+{
+    std::vector<float> h;
+    if (n < 1 || !design::firdes_kaiser((unsigned)n, fc, as, mu, h)) return fail(LQB_EINVAL, "firdes_kaiser: invalid parameters");
+    return lqb_firfilt_rrrf_create(h.data(), n, C, out);
+}
+int lqb_firfilt_rrrf_create_dc_blocker(int m, float as, int C, lqb_stage *out)
+{
+    std::vector<float> h;
+    if (m < 1 || !design::firdes_notch((unsigned)m, 0.0f, as, h)) return fail(LQB_EINVAL, "firdes_notch: invalid parameters");
+    return lqb_firfilt_rrrf_create(h.data(), (int)h.size(), C, out);
 }
 int lqb_firfilt_crcf_create_kaiser(int n, float fc, float as, float mu, int C, lqb_stage *out)
 {

@@ -30,6 +30,8 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
 }
 
+// REAL: firfilt_rrrf -- float samples in and out; they ride in the real lane of the same arithmetic
+template <bool REAL>
 __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntiles, const int ntaps_pad)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -43,6 +45,7 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
     const long long t0 = tile * TN;                                    // first output of this CTA
     const long long gch = a.ch0 + ch;
     const float2 *xrow = a.x + ch * a.n;
+    const float *xrow_r = (const float *)a.x + ch * a.n;
     const float2 *hrow = a.hist_in + gch * (long long)(a.ntaps - 1);
     const int nh = a.ntaps - 1;
 
@@ -51,7 +54,11 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
     for (int i = tid, pi = phys(tid); i < TN + halo; i += NT, pi += (NT / 16) * 17) {
         const long long g = t0 - halo + i;                             // global sample index
         float2 *dst = &s_x[pi];
-        if (g >= 0) { if (g < a.n) cp_async8(dst, xrow + g); else *dst = make_float2(0.f, 0.f); }
+        if (g >= 0) {
+            if (g >= a.n) *dst = make_float2(0.f, 0.f);
+            else if (REAL) *dst = make_float2(xrow_r[g], 0.f);
+            else cp_async8(dst, xrow + g);
+        }
         else if (g + nh >= 0) cp_async8(dst, hrow + (g + nh));
         else *dst = make_float2(0.f, 0.f);
     }
@@ -62,7 +69,7 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
         float2 *ho = a.hist_out + gch * (long long)nh;
         for (int j = tid; j < nh; j += NT) {
             const long long g = a.n - nh + j;
-            ho[j] = g >= 0 ? xrow[g] : hrow[g + nh];
+            ho[j] = g >= 0 ? (REAL ? make_float2(xrow_r[g], 0.f) : xrow[g]) : hrow[g + nh];
         }
     }
     cp_async_wait<0>();
@@ -100,6 +107,11 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
     for (int r = 0; r < R; r++) s_x[17 * tid + r] = upk(mul2(acc[r], sc));          // phys(16 * tid + r)
     __syncthreads();
     float2 *yrow = a.y + ch * a.n;
+    if (REAL) {
+        float *yr = (float *)a.y + ch * a.n;
+        for (int i = tid; i < TN; i += NT) { const long long g = t0 + i; if (g < a.n) yr[g] = s_x[phys(i)].x; }
+        return;
+    }
     const bool vec = ((a.n & 1) == 0) && ((((size_t)a.y) & 15) == 0);
     if (vec) {
         // sample pair 2i, 2i+1 sits at padded position 2i + (i >> 3); i advances by NT = 128, the position by 272
@@ -125,9 +137,10 @@ cudaError_t fir_launch(const FirArgs &a, cudaStream_t stream)
     const long long ntiles = (a.n + TN - 1) / TN;
     const size_t smem = (size_t)(TN + halo + ((TN + halo) >> 4) + 2 + ntaps_pad) * sizeof(float2);
     if (smem > 200 * 1024 || ntiles * (long long)a.C > 0x7fffffffLL) return cudaErrorInvalidValue;
-    cudaError_t rc = cudaFuncSetAttribute((const void *)fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto fn = a.real_io ? fir_kernel<true> : fir_kernel<false>;
+    cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
-    fir_kernel<<<(unsigned)(ntiles * a.C), NT, smem, stream>>>(a, (int)ntiles, ntaps_pad);
+    fn<<<(unsigned)(ntiles * a.C), NT, smem, stream>>>(a, (int)ntiles, ntaps_pad);
     return cudaGetLastError();
 }
 

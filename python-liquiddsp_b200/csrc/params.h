@@ -96,6 +96,7 @@ struct AmTailArgs {
 struct FirArgs {
     const float2 *x; float2 *y;    // [C][n]
     int C, ch0, Ctot, ntaps;
+    int real_io;                   // firfilt_rrrf: x and y are float rows
     long long n;
     float scale;
     const float *taps;             // device [ntaps] in design order h[0..ntaps-1]

@@ -470,9 +470,11 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             if constexpr (IN_REAL) {
 #pragma unroll
                 for (int j = 0; j < TS; j += 4) {
+                    // real samples ride in the real lane (the filters are real-coefficient, so that lane is exactly
+                    // the rrrf arithmetic; the imaginary lane carries zeros)
                     const float4 v = *(const float4 *)(row + j * 4);
-                    tail(make_float2(v.x, 0.f), j);     tail(make_float2(v.y, 0.f), j + 1);
-                    tail(make_float2(v.z, 0.f), j + 2); tail(make_float2(v.w, 0.f), j + 3);
+                    tail(upk(head(make_float2(v.x, 0.f))), j);     tail(upk(head(make_float2(v.y, 0.f))), j + 1);
+                    tail(upk(head(make_float2(v.z, 0.f))), j + 2); tail(upk(head(make_float2(v.w, 0.f))), j + 3);
                 }
             } else if constexpr (HAS_RS && !BIG_TAIL && HAS_IIR && !HAS_NCO) {
                 // Biquad cascade, skewed: at step k section s works on sample k-s, so the NS section updates of
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
 #pragma unroll 1
             for (int j = 0; j < nv; j++) {
                 if constexpr (IN_REAL) {
-                    tail(make_float2(*(const float *)(row + j * 4), 0.f), j);
+                    tail(upk(head(make_float2(*(const float *)(row + j * 4), 0.f))), j);
                 } else {
                     const u64 x = head(ld1(row, j));
                     if constexpr (HAS_RS) {
@@ -643,6 +645,7 @@ const Entry kTable[] = {
     // single stages
     LQB_E(F_NCO, 0), LQB_E(F_RS, 0), LQB_E(F_AGC, 0), LQB_E(F_FM, 0), LQB_E(F_DE | F_INREAL, 0),
     LQB_E_IIR(F_IIR), LQB_E(F_IIR, 5), LQB_E(F_IIR, 6), LQB_E(F_IIR, 7), LQB_E(F_IIR, 8),
+    LQB_E_IIR(F_IIR | F_INREAL), LQB_E(F_IIR | F_INREAL, 5), LQB_E(F_IIR | F_INREAL, 6), LQB_E(F_IIR | F_INREAL, 7), LQB_E(F_IIR | F_INREAL, 8),
     // fused runs
     LQB_T(F_NCO | F_RS, 0),
     LQB_T(F_IIR | F_RS, 1), LQB_T(F_IIR | F_RS, 2), LQB_T(F_IIR | F_RS, 3), LQB_T(F_IIR | F_RS, 4),

@@ -48,6 +48,10 @@ _SIG = {
     "lqb_stage_execute_dev": [_P, _P, _SZ, _P, _SZ, C.POINTER(_SZ), _P],
     "lqb_iirfilt_crcf_create_prototype": [_I, _I, _I, _F, _F, _F, _F, _I, _PP],
     "lqb_iirfilt_crcf_create_sos": [_P, _P, _I, _I, _PP],
+    "lqb_iirfilt_rrrf_create_prototype": [_I, _I, _I, _F, _F, _F, _F, _I, _PP],
+    "lqb_iirfilt_rrrf_create_sos": [_P, _P, _I, _I, _PP],
+    "lqb_firfilt_rrrf_create": [_P, _I, _I, _PP], "lqb_firfilt_rrrf_create_kaiser": [_I, _F, _F, _F, _I, _PP],
+    "lqb_firfilt_rrrf_create_dc_blocker": [_I, _F, _I, _PP],
     "lqb_iirfilt_crcf_get_sos": [_P, _P, _P, C.POINTER(_I)],
     "lqb_iirfilt_crcf_freqresponse": [_P, _F, C.POINTER(_cf)], "lqb_iirfilt_crcf_set_mode": [_P, _I],
     "lqb_deemph_create": [_F, _I, _PP], "lqb_deemph_get_coeffs": [_P, C.POINTER(_F), C.POINTER(_F)],
@@ -170,6 +174,8 @@ class _Stage:
 
 class ComplexIIRFilter(_Stage):
     """wrapper.cpp:134-152 / iirfilter.hpp:244-299."""
+    _create_prototype = "lqb_iirfilt_crcf_create_prototype"
+    _create_sos = "lqb_iirfilt_crcf_create_sos"
 
     def __init__(self, filter_type="butter", band_type="lowpass", order=2, Fc=0.2, F0=0.3, Ap=0.7, As=60.0,
                  channels=1, sos=None):
@@ -179,10 +185,10 @@ class ComplexIIRFilter(_Stage):
         self.order, self.Fc, self.F0, self.Ap, self.As = int(order), float(Fc), float(F0), float(Ap), float(As)
         if sos is not None:
             B = np.ascontiguousarray(sos[0], np.float32).ravel(); A = np.ascontiguousarray(sos[1], np.float32).ravel()
-            _ck(_lib.lqb_iirfilt_crcf_create_sos(_ptr(B), _ptr(A), B.size // 3, channels, C.byref(self._h)))
+            _ck(getattr(_lib, self._create_sos)(_ptr(B), _ptr(A), B.size // 3, channels, C.byref(self._h)))
         else:
-            _ck(_lib.lqb_iirfilt_crcf_create_prototype(_FILTER_TYPES.get(filter_type, 0), _BAND_TYPES.get(band_type, 0),
-                                                       int(order), Fc, F0, Ap, As, channels, C.byref(self._h)))
+            _ck(getattr(_lib, self._create_prototype)(_FILTER_TYPES.get(filter_type, 0), _BAND_TYPES.get(band_type, 0),
+                                                      int(order), Fc, F0, Ap, As, channels, C.byref(self._h)))
 
     def sos(self):
         B = np.zeros(3 * 64, np.float32); A = np.zeros(3 * 64, np.float32); n = _I()
@@ -202,6 +208,35 @@ class ComplexIIRFilter(_Stage):
         print("iir filter [sos], %d sections:" % len(B))
         for b, a in zip(B, A):
             print("  b:", b, " a:", a)
+
+
+class RealIIRFilter(ComplexIIRFilter):
+    """wrapper.cpp:154-172 / iirfilter.hpp:301-356: the same designs on real samples (iirfilt_rrrf)."""
+    _in_dtype = np.float32
+    _out_dtype = np.float32
+    _create_prototype = "lqb_iirfilt_rrrf_create_prototype"
+    _create_sos = "lqb_iirfilt_rrrf_create_sos"
+
+
+def _band_class(base, band, has_f0, doc):
+    # the reference's C*/R* classes fix the band type; low/highpass hand liquid f0 = 0.1 (iirfilter.hpp:72,90,180,198)
+    if has_f0:
+        def __init__(self, filter_type="butter", order=2, Fc=0.2, F0=0.3, Ap=0.5, As=20.0, channels=1):
+            base.__init__(self, filter_type, band, order, Fc, F0, Ap, As, channels=channels)
+    else:
+        def __init__(self, filter_type="butter", order=2, Fc=0.2, Ap=0.5, As=20.0, channels=1):
+            base.__init__(self, filter_type, band, order, Fc, 0.1, Ap, As, channels=channels)
+    return type(doc.split(":")[0], (base,), {"__init__": __init__, "__doc__": doc})
+
+
+CLowpassIIR = _band_class(ComplexIIRFilter, "lowpass", False, "CLowpassIIR: wrapper.cpp:36-45 / iirfilter.hpp:61-76")
+CHighpassIIR = _band_class(ComplexIIRFilter, "highpass", False, "CHighpassIIR: wrapper.cpp:47-56 / iirfilter.hpp:79-94")
+CBandpassIIR = _band_class(ComplexIIRFilter, "bandpass", True, "CBandpassIIR: wrapper.cpp:58-68 / iirfilter.hpp:97-112")
+CBandstopIIR = _band_class(ComplexIIRFilter, "bandstop", True, "CBandstopIIR: wrapper.cpp:70-80 / iirfilter.hpp:115-131")
+RLowpassIIR = _band_class(RealIIRFilter, "lowpass", False, "RLowpassIIR: wrapper.cpp:88-97 / iirfilter.hpp:171-186")
+RHighpassIIR = _band_class(RealIIRFilter, "highpass", False, "RHighpassIIR: wrapper.cpp:99-108 / iirfilter.hpp:189-204")
+RBandpassIIR = _band_class(RealIIRFilter, "bandpass", True, "RBandpassIIR: wrapper.cpp:110-120 / iirfilter.hpp:207-222")
+RBandstopIIR = _band_class(RealIIRFilter, "bandstop", True, "RBandstopIIR: wrapper.cpp:122-132 / iirfilter.hpp:225-241")
 
 
 class DeemphasisFilter(_Stage):
@@ -236,6 +271,37 @@ class FIRFilter(_Stage):
 
     def freqresponse(self, f):
         H = _cf(); _ck(_lib.lqb_firfilt_crcf_freqresponse(self._h, f, C.byref(H))); return complex(H.re, H.im)
+
+
+class RealFIRFilter(FIRFilter):
+    """wrapper.cpp:244-247 / firfilter.hpp:5-36 (firfilt_rrrf): real samples, real taps."""
+    _in_dtype = np.float32
+    _out_dtype = np.float32
+
+    def __init__(self, h, channels=1):
+        _Stage.__init__(self)
+        h = np.ascontiguousarray(h, np.float32).ravel()
+        _ck(_lib.lqb_firfilt_rrrf_create(_ptr(h), h.size, channels, C.byref(self._h)))
+
+
+class RealDCBlocker(RealFIRFilter):
+    """wrapper.cpp:249-252 / firfilter.hpp:39-50: firfilt_rrrf_create_dc_blocker(slen, As), 2*slen+1 taps."""
+
+    def __init__(self, slen=25, As=20.0, channels=1):
+        _Stage.__init__(self)
+        _ck(_lib.lqb_firfilt_rrrf_create_dc_blocker(int(slen), As, channels, C.byref(self._h)))
+
+
+class RealKaiserBessel(RealFIRFilter):
+    """wrapper.cpp:254-257 / firfilter.hpp:52-67: Kaiser lowpass scaled to unit gain at DC."""
+
+    def __init__(self, flen=25, Fc=0.25, As=20.0, offset=0.0, channels=1):
+        _Stage.__init__(self)
+        _ck(_lib.lqb_firfilt_rrrf_create_kaiser(int(flen), Fc, As, offset, channels, C.byref(self._h)))
+        # firfilter.hpp:59-60: set_scale(1.0 / abs(H(0))) -- the division is done in double, then narrowed
+        H0 = self.freqresponse(0.0)
+        mag = np.float32(np.hypot(np.float32(H0.real), np.float32(H0.imag)))
+        self.set_scale(float(np.float32(1.0 / float(mag))))
 
 
 class ComplexResampler(_Stage):

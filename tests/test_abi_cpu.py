@@ -56,6 +56,32 @@ def test_reference_api_surface():
     assert f.filter_type == "" and f.band_type == ""
     assert np.allclose(f.sos()[0], L.ComplexIIRFilter("butter", "lowpass", order=2, Fc=0.2).sos()[0])
     assert L.NCO("anything").type == "vco"                 # nco.hpp:16-24
+    # the real-sample and fixed-band families (wrapper.cpp:36-132, 154-172, 244-257)
+    assert sig(L.RealIIRFilter) == sig(L.ComplexIIRFilter)
+    for cls in (L.CLowpassIIR, L.CHighpassIIR, L.RLowpassIIR, L.RHighpassIIR):
+        assert sig(cls) == dict(filter_type="butter", order=2, Fc=0.2, Ap=0.5, As=20.0)
+    for cls in (L.CBandpassIIR, L.CBandstopIIR, L.RBandpassIIR, L.RBandstopIIR):
+        assert sig(cls) == dict(filter_type="butter", order=2, Fc=0.2, F0=0.3, Ap=0.5, As=20.0)
+    assert sig(L.RealDCBlocker) == dict(slen=25, As=20.0)
+    assert sig(L.RealKaiserBessel) == dict(flen=25, Fc=0.25, As=20.0, offset=0.0)
+    assert L.CBandpassIIR.__name__ == "CBandpassIIR" and L.RLowpassIIR("cheby1", 4, 0.1).band_type == "lowpass"
+
+
+def test_fixed_band_and_real_designs_equal_oracle():
+    for name, args in (("CLowpassIIR", ("cheby2", 5, 0.1)), ("CHighpassIIR", ("butter", 3, 0.2)), ("CBandpassIIR", ("cheby1", 4, 0.05, 0.2)),
+                       ("CBandstopIIR", ("butter", 2, 0.05, 0.3)), ("RLowpassIIR", ("butter", 6, 0.05)), ("RHighpassIIR", ("cheby1", 3, 0.1)),
+                       ("RBandpassIIR", ("cheby2", 3, 0.05, 0.25)), ("RBandstopIIR", ("butter", 4, 0.1, 0.2))):
+        g, o = getattr(L, name)(*args), getattr(O, name)(*args)
+        (B, A), (Bo, Ao) = g.sos(), o.sos()
+        assert B.shape == Bo.shape and np.max(np.abs(B - Bo)) < 2e-6 and np.max(np.abs(A - Ao)) < 2e-6, name
+        assert abs(g.freqresponse(0.07) - o.freqresponse(0.07)) < 1e-4 * max(1.0, abs(o.freqresponse(0.07)))
+    g, o = L.RealDCBlocker(25, 20.0), O.RealDCBlocker(25, 20.0)
+    assert g.taps().size == 51 and abs(g.freqresponse(0.0)) < 1e-3 and abs(g.freqresponse(0.0) - o.freqresponse(0.0)) < 1e-6
+    g, o = L.RealKaiserBessel(31, 0.1, 40.0), O.RealKaiserBessel(31, 0.1, 40.0)
+    assert np.array_equal(g.taps(), o.taps()) and abs(abs(g.freqresponse(0.0)) - 1.0) < 1e-6
+    assert g.freqresponse(0.0) == o.freqresponse(0.0) and abs(g.freqresponse(0.3)) < 0.02
+    with pytest.raises(ValueError):
+        L.RealKaiserBessel(31, 0.7)                        # cut-off outside (0, 0.5)
 
 
 @pytest.mark.parametrize("ft", ["butter", "cheby1", "cheby2"])
@@ -103,6 +129,8 @@ def test_planner():
     h = np.ones(8, np.float32)
     assert L.Chain(L.FIRFilter(h), L.ComplexIIRFilter(order=2), L.FIRFilter(h)).plan() == "fir -> seq[iir1] -> fir"
     assert L.Chain(*_radio()).out_len(65536) == 1573
+    assert L.Chain(L.RealIIRFilter("butter", "bandpass", order=10, Fc=0.1, F0=0.2), L.DeemphasisFilter()).plan() == "seq[iir8] -> seq[iir2] -> seq[deemph]"
+    assert L.Chain(L.AmpModem(0.5, "dsb", True), L.RealDCBlocker(), L.RLowpassIIR("butter", 4, 0.1)).plan() == "am[ampmodem] -> fir -> seq[iir2]"
     with pytest.raises(ValueError):                        # real-input stage after a complex-output stage
         L.Chain(L.ComplexIIRFilter(order=2), L.DeemphasisFilter()).plan()
     with pytest.raises(ValueError):

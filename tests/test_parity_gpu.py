@@ -134,6 +134,78 @@ def test_fir_streaming_invariance_and_scale(cuda):
     assert rel_l2(a(x), 0.25 * whole) <= 1e-6
 
 
+# ------------------------------------------------------------------------- 8f row 1: rrrf families
+@pytest.mark.parametrize("name,args", [("RLowpassIIR", ("cheby2", 8, 0.05)), ("RHighpassIIR", ("butter", 3, 0.2)),
+                                       ("RBandpassIIR", ("cheby1", 4, 0.05, 0.2)), ("RBandstopIIR", ("butter", 10, 0.05, 0.3))])
+def test_real_iir_families_bit_exact(cuda, name, args):
+    rng = np.random.default_rng(31)
+    g = getattr(L, name)(*args)
+    o = O.RealIIRFilter(_sos=g.sos())
+    x = rng.standard_normal(9001).astype(np.float32)
+    y, yo = np.concatenate([g(x[:4000]), g(x[4000:])]), o(x)          # state carried across calls
+    assert y.dtype == np.float32 and np.array_equal(y.view(np.uint32), yo.view(np.uint32)), rel_l2(y, yo)
+    g.reset()
+    assert np.array_equal(g(x[:100]), yo[:100])
+
+
+def test_real_iir_batched_matches_complex_lanes(cuda):
+    """C real channels through RealIIRFilter = the real lane of ComplexIIRFilter on the same samples."""
+    rng = np.random.default_rng(32)
+    C, n = 200, 777
+    x = rng.standard_normal((C, n)).astype(np.float32)
+    r = L.RealIIRFilter("cheby2", "lowpass", 8, 0.05, channels=C)
+    c = L.ComplexIIRFilter("cheby2", "lowpass", 8, 0.05, channels=C)
+    yr, yc = r(x), c(x.astype(np.complex64))
+    assert np.array_equal(yr, yc.real) and not np.any(yc.imag)
+    o = O.RealIIRFilter(_sos=r.sos())
+    assert np.array_equal(yr[137], o(x[137]))
+
+
+@pytest.mark.parametrize("name,args", [("CLowpassIIR", ("cheby2", 5, 0.1)), ("CHighpassIIR", ("butter", 3, 0.2)),
+                                       ("CBandpassIIR", ("cheby1", 4, 0.05, 0.2)), ("CBandstopIIR", ("butter", 2, 0.05, 0.3))])
+def test_fixed_band_complex_iir_bit_exact(cuda, name, args):
+    rng = np.random.default_rng(33)
+    g = getattr(L, name)(*args)
+    o = O.ComplexIIRFilter(_sos=g.sos())
+    x = crandn(rng, 5000)
+    assert np.array_equal(g(x).view(np.uint32), o(x).view(np.uint32))
+    # and against the oracle's own design of the same class (coefficients agree to ~1e-6): tolerance, not bits
+    assert rel_l2(g(x), getattr(O, name)(*args)(x)) <= 5e-4
+
+
+@pytest.mark.parametrize("ntaps,C,n", [(64, 3, 5000), (51, 1, 2049), (1, 2, 100), (200, 1, 9000)])
+def test_fir_rrrf(cuda, ntaps, C, n):
+    rng = np.random.default_rng(34)
+    h = O.firdes_kaiser(ntaps, 0.1, 60.0) if ntaps > 1 else np.array([0.5], np.float32)
+    g = L.RealFIRFilter(h, channels=C)
+    x = rng.standard_normal((C, n)).astype(np.float32)
+    cut = n // 3
+    y = np.concatenate([g(x[:, :cut]), g(x[:, cut:])], axis=1) if C > 1 else np.concatenate([g(x[0, :cut]), g(x[0, cut:])]).reshape(1, -1)
+    assert y.dtype == np.float32
+    for c in range(C):
+        assert rel_l2(y[c], O.RealFIRFilter(h)(x[c])) <= TOL_STAGE
+
+
+def test_real_dc_blocker_and_kaiser_bessel(cuda):
+    rng = np.random.default_rng(35)
+    x = (rng.standard_normal(6000) + 3.0).astype(np.float32)
+    g, o = L.RealDCBlocker(25, 20.0), O.RealDCBlocker(25, 20.0)
+    y, yo = g(x), o(x)
+    assert rel_l2(y, yo) <= TOL_STAGE and abs(float(np.mean(y[200:]))) < 0.05          # the +3 offset is gone
+    g, o = L.RealKaiserBessel(31, 0.1, 40.0), O.RealKaiserBessel(31, 0.1, 40.0)
+    y, yo = g(x), o(x)
+    assert rel_l2(y, yo) <= TOL_STAGE and abs(float(np.mean(y[200:])) - 3.0) < 0.05     # unit gain at DC
+
+
+def test_real_chain_am_dcblock_lowpass(cuda):
+    """demod.hpp BroadcastAM-style tail built from the widened classes: ampmodem -> RealDCBlocker -> RLowpassIIR."""
+    x = am_iq(20000, fs=48000.0, f_off=20.0, noise=0.01, amp=1.0)
+    am, dc, lp = L.AmpModem(0.5, "dsb", True), L.RealDCBlocker(), L.RLowpassIIR("butter", 4, 0.1)
+    chain = L.Chain(am, dc, lp)
+    oam, odc, olp = O.AmpModem(0.5, "dsb", True), O.RealDCBlocker(), O.RealIIRFilter(_sos=lp.sos())
+    assert rel_l2(chain(x), olp(odc(oam(x)))) <= TOL_E2E
+
+
 # ------------------------------------------------------------------------------------------- a3
 def test_resampler_readme_rate_counts_and_values(cuda):
     rng = np.random.default_rng(6)
