@@ -92,6 +92,13 @@ int lqb_iirfilt_rrrf_create_prototype(int ftype, int btype, int order, float fc,
                                       float ap, float as, int n_channels, lqb_stage *out);
 int lqb_iirfilt_rrrf_create_sos(const float *B, const float *A, int nsos, int n_channels, lqb_stage *out);
 
+/* ---------------- iirfilt, transfer-function form : CIIRFilter iirfilter.hpp:23-58, RIIRFilter :133-168 ------
+ * replaces iirfilt_crcf_create(b, nb, a, na) (:33) / iirfilt_rrrf_create (:143), _execute_block (:55,:165),
+ * _freqresponse (:48,:158), _reset (:43,:153).  Up to 16 coefficients per polynomial; a[0] normalises. */
+int lqb_iirfilt_crcf_create(const float *b, int nb, const float *a, int na, int n_channels, lqb_stage *out);
+int lqb_iirfilt_rrrf_create(const float *b, int nb, const float *a, int na, int n_channels, lqb_stage *out);
+int lqb_iirfilt_tf_freqresponse(lqb_stage s, float fc, lqb_cf *H);
+
 /* ---------------- iirfilt_rrrf one-pole : DeemphasisFilter, iirfilter.hpp:358-392 ----------
  * replaces iirfilt_rrrf_create(b,1,a,2) (:371) and the per-sample iirfilt_rrrf_execute loop
  * (:388-389); coefficient formula of :366-370.  real in -> real out. */

@@ -13,6 +13,7 @@
  */
 #include "liquid_oracle.h"
 #include <math.h>
+#include <complex.h>
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
@@ -191,6 +192,100 @@ static void cheby2_azpkf(unsigned n, float es, cfx *za, cfx *pa)
     }
 }
 
+/* ---- elliptic prototype   liquid: src/filter/src/ellip.c (after Orfanidis, "Lecture notes on elliptic filter
+ * design"): Landen sequences, n = 7 iterations, everything in float ---- */
+#define ELLIP_NITER 7
+static void landenf(float k, unsigned n, float *v)
+{
+    for (unsigned i = 0; i < n; i++) { float kp = sqrtf(1 - k * k); k = (1 - kp) / (1 + kp); v[i] = k; }
+}
+static void ellipkf(float k, unsigned n, float *K, float *Kp)
+{
+    float kmin = 4e-4f, kmax = sqrtf(1 - kmin * kmin), kp = sqrtf(1 - k * k), v[16];
+    unsigned i;
+    if (k > kmax) { float L = -logf(0.25f * kp); *K = L + 0.25f * (L - 1) * kp * kp; }
+    else { landenf(k, n, v); *K = M_PI * 0.5f; for (i = 0; i < n; i++) *K *= (1 + v[i]); }
+    if (k < kmin) { float L = -logf(k * 0.25f); *Kp = L + 0.25f * (L - 1) * k * k; }
+    else { landenf(kp, n, v); *Kp = M_PI * 0.5f; for (i = 0; i < n; i++) *Kp *= (1 + v[i]); }
+}
+static float ellipdegf(float N, float k1, unsigned n)
+{
+    float K1, K1p;
+    ellipkf(k1, n, &K1, &K1p);
+    float q1 = expf(-M_PI * K1p / K1), q = powf(q1, 1.0f / N), b = 0.0f, a = 0.0f;
+    unsigned m;
+    for (m = 0; m < n; m++) b += powf(q, (float)(m * (m + 1)));
+    for (m = 1; m < n; m++) a += powf(q, (float)(m * m));
+    float g = b / (1.0f + 2.0f * a);
+    return 4.0f * sqrtf(q) * g * g;
+}
+static float complex ellip_up(float complex w, float k, unsigned n)     /* ascending Landen recursion of cd / sn */
+{
+    float v[16]; landenf(k, n, v);
+    for (unsigned i = n; i > 0; i--) w = (1 + v[i - 1]) * w / (1 + v[i - 1] * w * w);
+    return w;
+}
+static float complex ellip_cdf(float complex u, float k, unsigned n) { return ellip_up(ccosf(u * (float)(M_PI * 0.5)), k, n); }
+static float complex ellip_snf(float complex u, float k, unsigned n) { return ellip_up(csinf(u * (float)(M_PI * 0.5)), k, n); }
+static float complex ellip_acdf(float complex w, float k, unsigned n)
+{
+    float v[16]; landenf(k, n, v);
+    for (unsigned i = 0; i < n; i++) {
+        float v1 = (i == 0) ? k : v[i - 1];
+        w = w / (1 + csqrtf(1 - w * w * v1 * v1)) * 2.0f / (1 + v[i]);
+    }
+    return cacosf(w) * 2.0f / (float)M_PI;
+}
+static float complex ellip_asnf(float complex w, float k, unsigned n) { return 1.0f - ellip_acdf(w, k, n); }
+static cfx from_c99(float complex z) { return cmk(crealf(z), cimagf(z)); }
+
+static void ellip_azpkf(unsigned n_, float ep, float es, cfx *za, cfx *pa)
+{
+    const unsigned n = ELLIP_NITER;
+    float k1 = ep / es, N = (float)n_;
+    float k = ellipdegf(N, k1, n);
+    unsigned r = n_ % 2, L = (n_ - r) / 2, i, t = 0;
+    float complex v0 = -I * ellip_asnf(I / ep, k1, n) / N;
+    for (i = 0; i < L; i++) {
+        float u = (2.0f * (i + 1) - 1.0f) / N;
+        float complex zeta = ellip_cdf(u, k, n);
+        float complex z = I * 1.0f / (k * zeta);
+        float complex p = I * ellip_cdf(u - I * v0, k, n);
+        za[t] = from_c99(z); pa[t++] = from_c99(p);
+        za[t] = from_c99(conjf(z)); pa[t++] = from_c99(conjf(p));
+    }
+    if (r) pa[t++] = from_c99(I * ellip_snf(I * v0, k, n));
+}
+
+/* ---- Bessel prototype   liquid: src/filter/src/bessel.c.  Poles = roots of the reverse Bessel polynomial
+ * theta_n(s) = sum_k (2n-k)! / (2^(n-k) k! (n-k)!) s^k, divided by the approximate 3 dB frequency
+ * sqrt((2n-1) ln 2).  liquid finds the roots with Orchard's recursion in float; here they are found in double
+ * (Durand-Kerner) and narrowed -- the same numbers to float accuracy. ---- */
+static void bessel_azpkf(unsigned n, cfx *pa)
+{
+    double c[18];
+    unsigned k, i, it;
+    for (k = 0; k <= n; k++)
+        c[k] = exp(lgamma(2.0 * n - k + 1) - lgamma((double)k + 1) - lgamma((double)(n - k) + 1) - (double)(n - k) * log(2.0));
+    for (k = 0; k <= n; k++) c[k] /= c[n];                 /* monic (c[n] = 1 already; keeps the intent explicit) */
+    double complex z[17];
+    for (i = 0; i < n; i++) z[i] = cpow(0.4 + 0.9 * I, (double)i) * (double)n;
+    for (it = 0; it < 500; it++) {
+        double worst = 0;
+        for (i = 0; i < n; i++) {
+            double complex num = 1.0, den = 1.0;
+            for (k = n; k-- > 0;) num = num * z[i] + c[k];
+            for (k = 0; k < n; k++) if (k != i) den *= (z[i] - z[k]);
+            double complex d = num / den;
+            z[i] -= d;
+            if (cabs(d) > worst) worst = cabs(d);
+        }
+        if (worst < 1e-14 * n) break;
+    }
+    float w3dB = sqrtf((2 * n - 1) * logf(2.0f));
+    for (i = 0; i < n; i++) pa[i] = cmk((float)creal(z[i]) / w3dB, (float)cimag(z[i]) / w3dB);
+}
+
 static float iirdes_freqprewarp(int btype, float fc, float f0)
 {
     float m = 0.0f;
@@ -327,8 +422,17 @@ static int iirdes_dzpk(int ftype, int btype, unsigned n, float fc, float f0, flo
         nza = 2 * L;
         epsilon = powf(10.0f, -as / 20.0f);
         cheby2_azpkf(n, epsilon, za, pa); break;
+    case ORC_IIRDES_ELLIP: {
+        nza = 2 * L;
+        float Gp = powf(10.0f, -ap / 20.0f), Gs = powf(10.0f, -as / 20.0f);
+        float ep = sqrtf(1.0f / (Gp * Gp) - 1.0f), es = sqrtf(1.0f / (Gs * Gs) - 1.0f);
+        k0 = cmk(r ? 1.0f : 1.0f / sqrtf(1.0f + ep * ep), 0.0f);
+        ellip_azpkf(n, ep, es, za, pa); break;
+    }
+    case ORC_IIRDES_BESSEL:
+        nza = 0; bessel_azpkf(n, pa); break;
     default:
-        return -2;   /* ellip / bessel: not restated yet */
+        return -2;
     }
     float m = iirdes_freqprewarp(btype, fc, f0);
     bilinear_zpkf(za, nza, pa, npa, k0, m, zd, pd, kd);

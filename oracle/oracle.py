@@ -238,6 +238,48 @@ RBandpassIIR = _band_class(RealIIRFilter, "bandpass", True, "RBandpassIIR")
 RBandstopIIR = _band_class(RealIIRFilter, "bandstop", True, "RBandstopIIR")
 
 
+class RIIRFilter:
+    """wrapper.cpp:82-86, iirfilter.hpp:133-168: iirfilt_rrrf_create(b, nb, a, na), transfer-function form."""
+
+    def __init__(self, Bc, Ac):
+        b, a = _f32(Bc), _f32(Ac)
+        self._q = lib.orc_iirfilt_rrrf_create(_p(b), b.size, _p(a), a.size)
+        if not self._q:
+            raise ValueError("iirfilt_rrrf_create failed")
+
+    def __del__(self):
+        if getattr(self, "_q", None):
+            lib.orc_iirfilt_rrrf_destroy(self._q); self._q = None
+
+    def reset(self):
+        lib.orc_iirfilt_rrrf_reset(self._q)
+
+    def freqresponse(self, f):
+        H = np.zeros(1, _cf); lib.orc_iirfilt_rrrf_freqresponse(self._q, f, _p(H)); return complex(H[0])
+
+    def __call__(self, x):
+        x = _f32(x); y = np.empty(x.shape[0], _f)
+        lib.orc_wrap_deemph_execute(self._q, _p(x), x.shape[0], _p(y))      # the per-sample iirfilt_rrrf_execute loop
+        return y
+
+
+class CIIRFilter:
+    """wrapper.cpp:30-34, iirfilter.hpp:23-58.  Real coefficients on complex samples: each lane is the rrrf recurrence."""
+
+    def __init__(self, Bc, Ac):
+        self._re, self._im = RIIRFilter(Bc, Ac), RIIRFilter(Bc, Ac)
+
+    def reset(self):
+        self._re.reset(); self._im.reset()
+
+    def freqresponse(self, f):
+        return self._re.freqresponse(f)
+
+    def __call__(self, x):
+        x = _c64(x)
+        return (self._re(x.real) + 1j * self._im(x.imag)).astype(_cf)
+
+
 def iir_f64_truth(B, A, x):
     """Same recurrence in double with the same float32 coefficients."""
     B = np.ascontiguousarray(B, _f).ravel(); A = np.ascontiguousarray(A, _f).ravel()

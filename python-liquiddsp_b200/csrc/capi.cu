@@ -137,7 +137,7 @@ static bool make_input_tmap(CUtensorMap *tm, const void *x, size_t n, size_t row
 }
 
 // ------------------------------------------------------------------------------------ stages
-enum Kind { K_NCO = 0, K_IIR, K_RESAMP, K_AGC, K_AM, K_FM, K_DEEMPH, K_FIR };
+enum Kind { K_NCO = 0, K_IIR, K_RESAMP, K_AGC, K_AM, K_FM, K_DEEMPH, K_FIR, K_TF };
 
 }  // namespace lqb
 
@@ -229,6 +229,24 @@ struct DeemphStage : lqb_stage_s {
     bool in_real() const override { return true; }
     bool out_real() const override { return true; }
     void fill(DeP &p) const { p.b0 = b0; p.a1 = a1; p.v1 = v1.p; }
+};
+
+// iirfilt_{crcf,rrrf}_create(b, nb, a, na): transfer-function form, coefficients normalised by a[0] in float
+struct TfStage : lqb_stage_s {
+    std::vector<float> b, a; bool real_io = false; DevArr<float2> v;
+    TfStage(int c) : lqb_stage_s(K_TF, c) {}
+    bool in_real() const override { return real_io; }
+    bool out_real() const override { return real_io; }
+    int delay() const { return (int)std::max(b.size(), a.size()) - 1; }
+    // delay elements the kernel instantiation keeps in registers
+    int padded() const { const int d = std::max(1, delay()); return d <= 1 ? 1 : d <= 2 ? 2 : d <= 4 ? 4 : d <= 8 ? 8 : 15; }
+    int materialize() override { return v.alloc((size_t)(kMaxTf - 1) * C); }
+    int clear() override { return v.zero(); }
+    void fill(TfP &p) const
+    {
+        for (int i = 0; i < kMaxTf; i++) { p.b[i] = i < (int)b.size() ? b[i] : 0.f; p.na[i] = i < (int)a.size() ? -a[i] : 0.f; }
+        p.nb = (int)b.size(); p.nna = (int)a.size(); p.v = v.p;
+    }
 };
 
 struct FirStage : lqb_stage_s {
@@ -407,7 +425,7 @@ static const char *kind_name(Kind k)
 {
     switch (k) {
     case K_NCO: return "nco"; case K_IIR: return "iir"; case K_RESAMP: return "resamp"; case K_AGC: return "agc";
-    case K_AM: return "ampmodem"; case K_FM: return "freqdem"; case K_DEEMPH: return "deemph"; case K_FIR: return "fir";
+    case K_AM: return "ampmodem"; case K_FM: return "freqdem"; case K_DEEMPH: return "deemph"; case K_FIR: return "fir"; case K_TF: return "tf";
     }
     return "?";
 }
@@ -415,7 +433,7 @@ static unsigned kind_flag(Kind k)
 {
     switch (k) {
     case K_NCO: return F_NCO; case K_IIR: return F_IIR; case K_RESAMP: return F_RS; case K_AGC: return F_AGC;
-    case K_AM: return F_AM; case K_FM: return F_FM; case K_DEEMPH: return F_DE; default: return 0;
+    case K_AM: return F_AM; case K_FM: return F_FM; case K_DEEMPH: return F_DE; case K_TF: return F_TF; default: return 0;
     }
 }
 // position in the order the sequential kernel applies its stages
@@ -431,6 +449,7 @@ static unsigned run_mask(const std::vector<lqb_stage_s *> &st, size_t i0, size_t
     for (size_t i = i0; i < i0 + len; i++) {
         m |= kind_flag(st[i]->kind);
         if (st[i]->kind == K_IIR) *nsos = static_cast<IirStage *>(st[i])->nsos;
+        if (st[i]->kind == K_TF) *nsos = static_cast<TfStage *>(st[i])->padded();
     }
     if (st[i0]->in_real()) m |= F_INREAL;
     return m;
@@ -601,6 +620,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         case K_AM:     LQB_TRY(static_cast<AmStage *>(s)->fill(a.am)); break;
         case K_FM:     static_cast<FmStage *>(s)->fill(a.fm); break;
         case K_DEEMPH: static_cast<DeemphStage *>(s)->fill(a.de); break;
+        case K_TF:     static_cast<TfStage *>(s)->fill(a.tf); break;
         default: return fail(LQB_EINVAL, "stage kind %d cannot run in the sequential kernel", (int)s->kind);
         }
     }
@@ -859,6 +879,31 @@ int lqb_deemph_freqresponse(lqb_stage s, float fc, lqb_cf *H)
     LQB_GET(DeemphStage, q, s, K_DEEMPH);
     const design::cplx e1 = std::polar(1.0f, (float)(-2 * design::kPi * fc));
     const design::cplx h = design::cplx(q->b0, 0.f) / (design::cplx(1.f, 0.f) + q->a1 * e1);
+    H->re = h.real(); H->im = h.imag(); return LQB_OK;
+}
+
+// ---- iirfilt, transfer-function form
+static int tf_create(const float *b, int nb, const float *a, int na, int C, bool real_io, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!b || !a || !out || nb < 1 || na < 1 || nb > kMaxTf || na > kMaxTf)
+        return fail(LQB_EINVAL, "iirfilt: need 1..%d numerator and denominator coefficients", kMaxTf);
+    if (a[0] == 0.f) return fail(LQB_EINVAL, "iirfilt: a[0] must not be zero");
+    TfStage *q = new TfStage(C);
+    q->real_io = real_io;
+    for (int i = 0; i < nb; i++) q->b.push_back(b[i] / a[0]);
+    for (int i = 0; i < na; i++) q->a.push_back(a[i] / a[0]);
+    *out = q; return LQB_OK;
+}
+int lqb_iirfilt_crcf_create(const float *b, int nb, const float *a, int na, int C, lqb_stage *out) { return tf_create(b, nb, a, na, C, false, out); }
+int lqb_iirfilt_rrrf_create(const float *b, int nb, const float *a, int na, int C, lqb_stage *out) { return tf_create(b, nb, a, na, C, true, out); }
+int lqb_iirfilt_tf_freqresponse(lqb_stage s, float fc, lqb_cf *H)
+{
+    LQB_GET(TfStage, q, s, K_TF);
+    design::cplx hb(0.f, 0.f), ha(0.f, 0.f);
+    for (size_t i = 0; i < q->b.size(); i++) hb += q->b[i] * design::cplx(cosf((float)(2 * design::kPi * fc * i)), -sinf((float)(2 * design::kPi * fc * i)));
+    for (size_t i = 0; i < q->a.size(); i++) ha += q->a[i] * design::cplx(cosf((float)(2 * design::kPi * fc * i)), -sinf((float)(2 * design::kPi * fc * i)));
+    const design::cplx h = hb / ha;
     H->re = h.real(); H->im = h.imag(); return LQB_OK;
 }
 

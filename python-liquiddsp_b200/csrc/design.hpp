@@ -148,7 +148,75 @@ inline float ellipse_axes(float eps, unsigned n, float &a, float &b)
 
 inline float pole_angle(unsigned i, unsigned n) { return (float)((float)(2 * (i + 1) + n - 1) * kPi / (float)(2 * n)); }
 
-// analog prototype; returns false for families outside the built scope
+// ---- elliptic prototype (liquid ellip.c, after Orfanidis): Landen sequences of 7 terms, float throughout
+namespace ellip {
+constexpr unsigned kIter = 7;
+inline void landen(float k, float (&v)[kIter])
+{
+    for (unsigned i = 0; i < kIter; i++) { const float kp = std::sqrt(1 - k * k); k = (1 - kp) / (1 + kp); v[i] = k; }
+}
+inline float quarter_period(float k, float kc)      // K(k) given the complementary modulus kc; near k = 1 the series in kc
+{
+    const float kmin = 4e-4f, kmax = std::sqrt(1 - kmin * kmin);
+    if (k > kmax) { const float L = -std::log(0.25f * kc); return L + 0.25f * (L - 1) * kc * kc; }
+    float v[kIter]; landen(k, v);
+    float K = (float)(kPi * 0.5f);
+    for (float vi : v) K *= (1 + vi);
+    return K;
+}
+inline float degree(float N, float k1)              // modulus k solving the degree equation N K'/K = K1'/K1
+{
+    const float k1c = std::sqrt(1 - k1 * k1);
+    const float K1 = quarter_period(k1, k1c), K1p = quarter_period(k1c, k1);
+    const float q1 = std::exp((float)(-kPi * K1p / K1)), q = std::pow(q1, 1.0f / N);
+    float b = 0.f, a = 0.f;
+    for (unsigned m = 0; m < kIter; m++) b += std::pow(q, (float)(m * (m + 1)));
+    for (unsigned m = 1; m < kIter; m++) a += std::pow(q, (float)(m * m));
+    const float g = b / (1.0f + 2.0f * a);
+    return 4.0f * std::sqrt(q) * g * g;
+}
+inline cplx ascend(cplx w, float k)                 // Gauss transformation back up the Landen sequence
+{
+    float v[kIter]; landen(k, v);
+    for (unsigned i = kIter; i > 0; i--) w = (1 + v[i - 1]) * w / (cplx(1.f, 0.f) + v[i - 1] * w * w);
+    return w;
+}
+inline cplx cd(cplx u, float k) { return ascend(std::cos(u * (float)(kPi * 0.5)), k); }
+inline cplx sn(cplx u, float k) { return ascend(std::sin(u * (float)(kPi * 0.5)), k); }
+inline cplx asn(cplx w, float k)
+{
+    float v[kIter]; landen(k, v);
+    for (unsigned i = 0; i < kIter; i++) {
+        const float v1 = i == 0 ? k : v[i - 1];
+        w = w / (cplx(1.f, 0.f) + std::sqrt(cplx(1.f, 0.f) - w * w * v1 * v1)) * 2.0f / (1 + v[i]);
+    }
+    return cplx(1.f, 0.f) - std::acos(w) * 2.0f / (float)kPi;
+}
+}  // namespace ellip
+
+// reverse Bessel polynomial roots (the delay-normalised Bessel poles), Durand-Kerner in double
+inline std::vector<std::complex<double>> bessel_roots(unsigned n)
+{
+    std::vector<double> c(n + 1);
+    for (unsigned k = 0; k <= n; k++)
+        c[k] = std::exp(std::lgamma(2.0 * n - k + 1) - std::lgamma((double)k + 1) - std::lgamma((double)(n - k) + 1) - (double)(n - k) * std::log(2.0));
+    std::vector<std::complex<double>> z(n);
+    for (unsigned i = 0; i < n; i++) z[i] = std::pow(std::complex<double>(0.4, 0.9), (double)i) * (double)n;
+    for (int it = 0; it < 500; it++) {
+        double worst = 0;
+        for (unsigned i = 0; i < n; i++) {
+            std::complex<double> num = 1.0, den = 1.0;
+            for (unsigned k = n; k-- > 0;) num = num * z[i] + c[k];
+            for (unsigned k = 0; k < n; k++) if (k != i) den *= (z[i] - z[k]);
+            const std::complex<double> d = num / den;
+            z[i] -= d; worst = std::max(worst, std::abs(d));
+        }
+        if (worst < 1e-14 * n) break;
+    }
+    return z;
+}
+
+// analog prototype; returns false for an unknown family
 inline bool analog_prototype(int ftype, unsigned n, float ap, float as, Zpk &A, cplx &k0)
 {
     const unsigned r = n % 2, L = (n - r) / 2;
@@ -188,6 +256,29 @@ inline bool analog_prototype(int ftype, unsigned n, float ap, float as, Zpk &A, 
             A.z.push_back(cplx(-1.f, 0.f) / cplx(0.f, std::cos(th)));
             A.z.push_back(cplx( 1.f, 0.f) / cplx(0.f, std::cos(th)));
         }
+        return true;
+    }
+    if (ftype == ELLIP) {
+        const float Gp = std::pow(10.0f, -ap / 20.0f), Gs = std::pow(10.0f, -as / 20.0f);
+        const float ep = std::sqrt(1.0f / (Gp * Gp) - 1.0f), es = std::sqrt(1.0f / (Gs * Gs) - 1.0f);
+        k0 = cplx(r ? 1.0f : 1.0f / std::sqrt(1.0f + ep * ep), 0.f);
+        const float k1 = ep / es, N = (float)n, k = ellip::degree(N, k1);
+        const cplx j(0.f, 1.f);
+        const cplx v0 = -j * ellip::asn(j / ep, k1) / N;
+        for (unsigned i = 0; i < L; i++) {
+            const float u = (2.0f * (i + 1) - 1.0f) / N;
+            const cplx z = j * 1.0f / (k * ellip::cd(cplx(u, 0.f), k));
+            const cplx p = j * ellip::cd(cplx(u, 0.f) - j * v0, k);
+            A.z.push_back(z); A.z.push_back(std::conj(z));
+            A.p.push_back(p); A.p.push_back(std::conj(p));
+        }
+        if (r) A.p.push_back(j * ellip::sn(j * v0, k));
+        return true;
+    }
+    if (ftype == BESSEL) {
+        // poles of the delay-normalised prototype over the approximate 3 dB frequency sqrt((2n-1) ln 2)
+        const float w3dB = std::sqrt((2 * n - 1) * std::log(2.0f));
+        for (const auto &z : bessel_roots(n)) A.p.emplace_back((float)z.real() / w3dB, (float)z.imag() / w3dB);
         return true;
     }
     return false;

@@ -18,7 +18,9 @@ constexpr int kMaxResampSub = 64; // resampler sub-filter length limit for the f
 
 enum : unsigned {
     F_NCO = 1u, F_IIR = 2u, F_RS = 4u, F_AGC = 8u, F_AM = 16u, F_FM = 32u, F_DE = 64u, F_INREAL = 128u,
-    F_INI16 = 256u                 // input rows are interleaved int16 I/Q (bytes_to_iq fused into the first stage)
+    F_INI16 = 256u,                // input rows are interleaved int16 I/Q (bytes_to_iq fused into the first stage)
+    F_TF = 512u                    // IIR in transfer-function form (iirfilt_*_create(b, nb, a, na)); the kernel's section
+                                   // count parameter then carries the (padded) number of delay elements
 };
 
 struct NcoP {
@@ -69,6 +71,12 @@ struct AmP {
 
 struct FmP { float ref; float2 *rprime; };          // [Ctot]
 struct DeP { float b0, a1; float *v1; };            // [Ctot]
+constexpr int kMaxTf = 16;         // coefficients per polynomial in transfer-function form
+struct TfP {
+    float b[kMaxTf], na[kMaxTf];   // b[i] / a0 and -(a[i] / a0)
+    int nb, nna;                   // lengths of b and a
+    float2 *v;                     // [kMaxTf - 1][Ctot] delay line v[1..]
+};
 
 struct alignas(64) SeqArgs {
     CUtensorMap tmap;              // TMA mode: the input as a 2-D tensor [C rows][2n floats], box 32 floats x 32 rows, 128B swizzle
@@ -82,7 +90,7 @@ struct alignas(64) SeqArgs {
     int use_tma;                   // tmap is valid: stage the input with TMA (full-warp kernels that have the variant)
     int out_tmajor;                // decimated output stored [sample][channel] (hand-off to the AM tail kernel)
     long long n, out_pitch;
-    NcoP nco; IirP iir; ResampP rs; AgcP agc; AmP am; FmP fm; DeP de;
+    NcoP nco; IirP iir; ResampP rs; AgcP agc; AmP am; FmP fm; DeP de; TfP tf;
 };
 
 struct AmTailArgs {

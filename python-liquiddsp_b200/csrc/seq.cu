@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     constexpr bool HAS_NCO = (M & F_NCO) != 0, HAS_IIR = (M & F_IIR) != 0, HAS_RS = (M & F_RS) != 0;
     constexpr bool HAS_AGC = (M & F_AGC) != 0, HAS_AM = (M & F_AM) != 0, HAS_FM = (M & F_FM) != 0;
     constexpr bool HAS_DE = (M & F_DE) != 0, IN_REAL = (M & F_INREAL) != 0, IN_I16 = (M & F_INI16) != 0;
+    constexpr bool HAS_TF = (M & F_TF) != 0;        // transfer-function IIR: NSOS = delay elements kept in registers
     constexpr bool OUT_REAL = HAS_AM || HAS_FM || IN_REAL;
     constexpr int  IELEM = (IN_REAL || IN_I16) ? 4 : 8, OELEM = OUT_REAL ? 4 : 8;
     static_assert(!IN_I16 || HAS_RS, "int16 ingest is compiled for the decimating front kernels");
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     constexpr int  PIN = GI::PITCH, POUT = GO::PITCH;
     constexpr int  NS = NSOS > 0 ? NSOS : 1;
     constexpr bool BIG_TAIL = HAS_AM;               // keep one copy of the ampmodem body
-    static_assert(HAS_IIR == (NSOS > 0), "section count and mask disagree");
+    static_assert((HAS_IIR || HAS_TF) == (NSOS > 0) && !(HAS_IIR && HAS_TF), "section count and mask disagree");
+    static_assert(!HAS_TF || NSOS < kMaxTf, "delay line longer than the coefficient arrays");
 
     // Channels per warp.  With few channels the kernel is bound by the latency of each channel's recurrence, not by
     // throughput, so the same channels are spread over more warps (8 or 16 working lanes each) and the schedulers
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     uint32_t nco_theta = 0, nco_dtheta = 0;
     u64 iv1[NS], iv2[NS], ca1[NS], ca2[NS], cb0[NS], cb1[NS], cb2[NS];
     u64 rs_acc = 0;
+    u64 tv[NS];                                                    // transfer-function form: v[1..NS] of the delay line
     float agc_g = 1.f, agc_y2p = 1.f; int agc_mode = 7; unsigned agc_timer = 0, agc_rises = 0;
     uint32_t am_theta = 0, am_dtheta = 0, am_cnt = a.am.count;
     float2 fm_prev = make_float2(0.f, 0.f);
@@ -123,6 +126,10 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             cb2[s] = pk(a.iir.b[s][2], a.iir.b[s][2]);
             iv1[s] = pk(a.iir.v[(2 * s + 0) * CT + gch]); iv2[s] = pk(a.iir.v[(2 * s + 1) * CT + gch]);
         }
+    }
+    if constexpr (HAS_TF) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) tv[i] = pk(a.tf.v[i * CT + gch]);
     }
     if constexpr (HAS_RS) {
         const int nb = a.rs.npfb * a.rs.sublen;
@@ -400,6 +407,19 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 iv2[s] = iv1[s]; iv1[s] = v0; x = y;
             }
         }
+        if constexpr (HAS_TF) {
+            // iirfilt_execute_norm: v0 = x - sum a[i] v[i] (i ascending), y = sum b[i] v[i] (from zero, i ascending),
+            // every step one fused multiply-add; tv[i-1] is v[i] after liquid's shift
+            u64 v0 = x;
+#pragma unroll
+            for (int i = 1; i <= NS; i++) if (i < a.tf.nna) v0 = fma2(pk(a.tf.na[i], a.tf.na[i]), tv[i - 1], v0);
+            u64 y = fma2(pk(a.tf.b[0], a.tf.b[0]), v0, 0ull);
+#pragma unroll
+            for (int i = 1; i <= NS; i++) if (i < a.tf.nb) y = fma2(pk(a.tf.b[i], a.tf.b[i]), tv[i - 1], y);
+#pragma unroll
+            for (int i = NS - 1; i > 0; i--) tv[i] = tv[i - 1];
+            tv[0] = v0; x = y;
+        }
         return x;
     };
     // one staged sample / a whole staged row as complex floats (int16 I/Q pairs are converted on the way)
@@ -618,6 +638,10 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 a.iir.v[(2 * s + 0) * CT + gch] = upk(iv1[s]); a.iir.v[(2 * s + 1) * CT + gch] = upk(iv2[s]);
             }
         }
+        if constexpr (HAS_TF) {
+#pragma unroll
+            for (int i = 0; i < NS; i++) a.tf.v[i * CT + gch] = upk(tv[i]);
+        }
         if constexpr (HAS_AGC) {
             a.agc.g[gch] = agc_g; a.agc.y2p[gch] = agc_y2p; a.agc.mode[gch] = agc_mode; a.agc.timer[gch] = agc_timer;
             if (agc_rises) atomicAdd(a.agc.rise_count, agc_rises);
@@ -646,6 +670,9 @@ const Entry kTable[] = {
     LQB_E(F_NCO, 0), LQB_E(F_RS, 0), LQB_E(F_AGC, 0), LQB_E(F_FM, 0), LQB_E(F_DE | F_INREAL, 0),
     LQB_E_IIR(F_IIR), LQB_E(F_IIR, 5), LQB_E(F_IIR, 6), LQB_E(F_IIR, 7), LQB_E(F_IIR, 8),
     LQB_E_IIR(F_IIR | F_INREAL), LQB_E(F_IIR | F_INREAL, 5), LQB_E(F_IIR | F_INREAL, 6), LQB_E(F_IIR | F_INREAL, 7), LQB_E(F_IIR | F_INREAL, 8),
+    // transfer-function IIR (CIIRFilter / RIIRFilter), delay elements padded to 1, 2, 4, 8, 15
+    LQB_E(F_TF, 1), LQB_E(F_TF, 2), LQB_E(F_TF, 4), LQB_E(F_TF, 8), LQB_E(F_TF, 15),
+    LQB_E(F_TF | F_INREAL, 1), LQB_E(F_TF | F_INREAL, 2), LQB_E(F_TF | F_INREAL, 4), LQB_E(F_TF | F_INREAL, 8), LQB_E(F_TF | F_INREAL, 15),
     // fused runs
     LQB_T(F_NCO | F_RS, 0),
     LQB_T(F_IIR | F_RS, 1), LQB_T(F_IIR | F_RS, 2), LQB_T(F_IIR | F_RS, 3), LQB_T(F_IIR | F_RS, 4),

@@ -52,6 +52,8 @@ _SIG = {
     "lqb_iirfilt_rrrf_create_sos": [_P, _P, _I, _I, _PP],
     "lqb_firfilt_rrrf_create": [_P, _I, _I, _PP], "lqb_firfilt_rrrf_create_kaiser": [_I, _F, _F, _F, _I, _PP],
     "lqb_firfilt_rrrf_create_dc_blocker": [_I, _F, _I, _PP],
+    "lqb_iirfilt_crcf_create": [_P, _I, _P, _I, _I, _PP], "lqb_iirfilt_rrrf_create": [_P, _I, _P, _I, _I, _PP],
+    "lqb_iirfilt_tf_freqresponse": [_P, _F, C.POINTER(_cf)],
     "lqb_iirfilt_crcf_get_sos": [_P, _P, _P, C.POINTER(_I)],
     "lqb_iirfilt_crcf_freqresponse": [_P, _F, C.POINTER(_cf)], "lqb_iirfilt_crcf_set_mode": [_P, _I],
     "lqb_deemph_create": [_F, _I, _PP], "lqb_deemph_get_coeffs": [_P, C.POINTER(_F), C.POINTER(_F)],
@@ -237,6 +239,26 @@ RLowpassIIR = _band_class(RealIIRFilter, "lowpass", False, "RLowpassIIR: wrapper
 RHighpassIIR = _band_class(RealIIRFilter, "highpass", False, "RHighpassIIR: wrapper.cpp:99-108 / iirfilter.hpp:189-204")
 RBandpassIIR = _band_class(RealIIRFilter, "bandpass", True, "RBandpassIIR: wrapper.cpp:110-120 / iirfilter.hpp:207-222")
 RBandstopIIR = _band_class(RealIIRFilter, "bandstop", True, "RBandstopIIR: wrapper.cpp:122-132 / iirfilter.hpp:225-241")
+
+
+class CIIRFilter(_Stage):
+    """wrapper.cpp:30-34 / iirfilter.hpp:23-58: IIR from transfer-function coefficients (Bc, Ac), complex samples."""
+    _create = "lqb_iirfilt_crcf_create"
+
+    def __init__(self, Bc, Ac, channels=1):
+        super().__init__()
+        b = np.ascontiguousarray(Bc, np.float32).ravel(); a = np.ascontiguousarray(Ac, np.float32).ravel()
+        _ck(getattr(_lib, self._create)(_ptr(b), b.size, _ptr(a), a.size, channels, C.byref(self._h)))
+
+    def freqresponse(self, f):
+        H = _cf(); _ck(_lib.lqb_iirfilt_tf_freqresponse(self._h, f, C.byref(H))); return complex(H.re, H.im)
+
+
+class RIIRFilter(CIIRFilter):
+    """wrapper.cpp:82-86 / iirfilter.hpp:133-168: the same on real samples (iirfilt_rrrf)."""
+    _in_dtype = np.float32
+    _out_dtype = np.float32
+    _create = "lqb_iirfilt_rrrf_create"
 
 
 class DeemphasisFilter(_Stage):

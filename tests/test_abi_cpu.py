@@ -62,6 +62,7 @@ def test_reference_api_surface():
         assert sig(cls) == dict(filter_type="butter", order=2, Fc=0.2, Ap=0.5, As=20.0)
     for cls in (L.CBandpassIIR, L.CBandstopIIR, L.RBandpassIIR, L.RBandstopIIR):
         assert sig(cls) == dict(filter_type="butter", order=2, Fc=0.2, F0=0.3, Ap=0.5, As=20.0)
+    assert sig(L.CIIRFilter) == sig(L.RIIRFilter) == dict(Bc=inspect._empty, Ac=inspect._empty)
     assert sig(L.RealDCBlocker) == dict(slen=25, As=20.0)
     assert sig(L.RealKaiserBessel) == dict(flen=25, Fc=0.25, As=20.0, offset=0.0)
     assert L.CBandpassIIR.__name__ == "CBandpassIIR" and L.RLowpassIIR("cheby1", 4, 0.1).band_type == "lowpass"
@@ -82,9 +83,17 @@ def test_fixed_band_and_real_designs_equal_oracle():
     assert g.freqresponse(0.0) == o.freqresponse(0.0) and abs(g.freqresponse(0.3)) < 0.02
     with pytest.raises(ValueError):
         L.RealKaiserBessel(31, 0.7)                        # cut-off outside (0, 0.5)
+    b, a = [0.2, 0.3, -0.1], [2.0, -0.8, 0.3, 0.05]
+    for g, o in ((L.CIIRFilter(b, a), O.CIIRFilter(b, a)), (L.RIIRFilter(b, a), O.RIIRFilter(b, a))):
+        assert abs(g.freqresponse(0.13) - o.freqresponse(0.13)) < 1e-6
+    with pytest.raises(ValueError):
+        L.CIIRFilter(b, [0.0, 1.0])
+    with pytest.raises(ValueError):
+        L.RIIRFilter(np.ones(17), [1.0])
+    assert L.Chain(L.CIIRFilter(b, a), L.CIIRFilter(np.ones(9), [1.0])).plan() == "seq[tf] -> seq[tf]"
 
 
-@pytest.mark.parametrize("ft", ["butter", "cheby1", "cheby2"])
+@pytest.mark.parametrize("ft", ["butter", "cheby1", "cheby2", "ellip", "bessel"])
 @pytest.mark.parametrize("bt", ["lowpass", "highpass", "bandpass", "bandstop"])
 @pytest.mark.parametrize("order", [1, 2, 3, 5, 8])
 def test_product_design_equals_oracle_design(ft, bt, order):
@@ -142,8 +151,8 @@ def test_argument_checking():
         L.ComplexIIRFilter("butter", order=0)
     with pytest.raises(ValueError):
         L.ComplexIIRFilter("butter", order=2, Fc=0.7)
-    with pytest.raises(NotImplementedError):
-        L.ComplexIIRFilter("ellip", order=4, Fc=0.1)
+    with pytest.raises(ValueError):
+        L.ComplexIIRFilter("ellip", order=4, Fc=0.1, As=-3.0)
     with pytest.raises(NotImplementedError):
         L.AmpModem(0.5, "usb", True)
     with pytest.raises(ValueError):

@@ -42,6 +42,36 @@ def test_iirdes_zpk_against_scipy(key, ft, bt, order, fc, ap, As):
     assert abs(k.real / KAT[key + "_k"] - 1) < 2e-3 and abs(k.imag) < 1e-6
 
 
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5, 8, 11])
+@pytest.mark.parametrize("bt", ["lowpass", "highpass"])
+def test_ellip_design_against_scipy(order, bt):
+    """liquid's elliptic design (Landen / Orfanidis) against scipy.signal.ellip computed live: the float design
+    lands within 1e-4 of the double-precision poles and zeros; the gain follows k0 = 1 (odd) or the ripple floor (even)."""
+    import scipy.signal as ss
+    z, p, k = O.iirdes_dzpk("ellip", bt, order, 0.1, 0.3, 1.0, 40.0)
+    zs, ps, ks = ss.ellip(order, 1.0, 40.0, 0.2, btype=bt, output="zpk")
+    _match_roots(p, ps, 1e-4)
+    if len(zs) < len(z):
+        zs = np.concatenate([zs, np.full(len(z) - len(zs), -1.0 if bt == "lowpass" else 1.0)])
+    _match_roots(z, zs, 5e-4)                             # zeros = j / (k cd(u)): float k moves them by up to 1.6e-4
+    assert abs(k.real / ks - 1) < 2e-3 and abs(k.imag) < 1e-5
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 5, 8, 12, 16])
+def test_bessel_design_against_scipy(order):
+    """Poles = scipy's delay-normalised Bessel prototype over sqrt((2n-1) ln 2) (liquid's 3 dB approximation), through
+    liquid's bilinear map; the magnitude at the design cut-off is then near -3 dB."""
+    import scipy.signal as ss
+    _, pa, _ = ss.besselap(order, "delay")
+    pa = pa / np.sqrt((2 * order - 1) * np.log(2.0))
+    m = np.tan(np.pi * 0.1)
+    z, p, k = O.iirdes_dzpk("bessel", "lowpass", order, 0.1, 0.3, 1.0, 40.0)
+    _match_roots(p, (1 + pa * m) / (1 - pa * m), 1e-5)
+    assert np.allclose(z, -1.0)
+    f = O.ComplexIIRFilter("bessel", "lowpass", order, 0.1)
+    assert abs(abs(f.freqresponse(0.0)) - 1) < 1e-3 and 0.66 < abs(f.freqresponse(0.1)) < 0.78
+
+
 def test_cheby2_formulas_in_float64_match_scipy():
     n, As, fc = 8, 60.0, 0.0075
     es = 10 ** (-As / 20)

@@ -18,7 +18,8 @@ TOL_E2E = 1e-4
 
 # ------------------------------------------------------------------------------------------- a1
 @pytest.mark.parametrize("ft,bt,order", [("cheby2", "lowpass", 8), ("butter", "lowpass", 2), ("butter", "lowpass", 1),
-                                          ("cheby1", "highpass", 5), ("cheby2", "bandpass", 4), ("butter", "bandstop", 10)])
+                                          ("cheby1", "highpass", 5), ("cheby2", "bandpass", 4), ("butter", "bandstop", 10),
+                                          ("ellip", "lowpass", 7), ("ellip", "bandpass", 3), ("bessel", "highpass", 6)])
 def test_iir_single_channel_bit_exact(cuda, ft, bt, order):
     rng = np.random.default_rng(1)
     fc = 0.0075 if (ft, order) == ("cheby2", 8) else 0.1
@@ -172,6 +173,26 @@ def test_fixed_band_complex_iir_bit_exact(cuda, name, args):
     assert np.array_equal(y.view(np.uint32), o(x).view(np.uint32))
     # and against the oracle's own design of the same class (coefficients agree to ~1e-6): tolerance, not bits
     assert rel_l2(y, getattr(O, name)(*args)(x)) <= 5e-4
+
+
+@pytest.mark.parametrize("nb,na", [(1, 2), (3, 3), (2, 5), (9, 1), (7, 12), (16, 16), (1, 1)])
+def test_transfer_function_iir_bit_exact(cuda, nb, na):
+    """CIIRFilter / RIIRFilter: iirfilt_execute_norm, any mix of numerator / denominator lengths up to 16."""
+    import scipy.signal as ss
+    rng = np.random.default_rng(36)
+    # stable denominator: a Butterworth polynomial of the right length (scaled so a[0] != 1 exercises normalisation)
+    a = (1.7 * ss.butter(na - 1, 0.3)[1]).astype(np.float32) if na > 1 else np.array([1.7], np.float32)
+    b = (0.2 * rng.standard_normal(nb)).astype(np.float32)
+    x = crandn(rng, 4099)
+    gc, oc = L.CIIRFilter(b, a), O.CIIRFilter(b, a)
+    yc = np.concatenate([gc(x[:1000]), gc(x[1000:])])
+    assert np.array_equal(yc.view(np.uint32), oc(x).view(np.uint32)), rel_l2(yc, oc(x))
+    gr, orr = L.RIIRFilter(b, a, channels=3), O.RIIRFilter(b, a)
+    xr = np.stack([x.real, x.imag, x.real[::-1]]).copy()
+    yr = gr(xr)
+    assert yr.dtype == np.float32 and np.array_equal(yr[0], orr(xr[0])) and np.array_equal(yr[1], yc.imag)
+    gr.reset()
+    assert np.array_equal(gr(xr[:, :50])[2], O.RIIRFilter(b, a)(xr[2, :50]))
 
 
 @pytest.mark.parametrize("ntaps,C,n", [(64, 3, 5000), (51, 1, 2049), (1, 2, 100), (200, 1, 9000)])
