@@ -179,6 +179,14 @@ int lqb_ampmodem_create(float mod_index, int type, int suppressed_carrier, int n
 int lqb_ampmodem_get_taps(lqb_stage s, float *lowpass, int *n_lowpass, float *dcblock, int *n_dcblock);
 int lqb_ampmodem_get_nco_u32(lqb_stage s, uint32_t *theta, uint32_t *d_theta, int n);
 
+/* ---------------- BroadcastAM : demod.hpp:94-153, wrapper.cpp:259-262 -----------------------------------
+ * replaces the per-sample demod_one loop (:124-131): nco_crcf PLL (bw 0.001, arg() detector), firfilt_crcf
+ * kaiser(2*slen+1, 0.01, 40 dB), wdelaycf(slen), iirfilt_rrrf cheby2 order-3 high-pass.  complex -> real.
+ * get_design: lowpass taps (2*slen+1) and the two DC-block sections B[6], A[6]. */
+int lqb_broadcast_am_create(int slen, int n_channels, lqb_stage *out);
+int lqb_broadcast_am_get_design(lqb_stage s, float *lp, int *n_lp, float *B, float *A);
+int lqb_broadcast_am_get_nco_u32(lqb_stage s, uint32_t *theta, uint32_t *d_theta, int n);
+
 /* ---------------- freqdem : FreqDem, demod.hpp:189-219 --------------------------------------
  * replaces freqdem_create (:197), freqdem_demodulate_block (:216), freqdem_reset (:205). */
 int lqb_freqdem_create(float kf, int n_channels, lqb_stage *out);

@@ -1072,6 +1072,69 @@ orc_iirfilt_rrrf orc_wrap_deemph_create(float sr)
 void orc_wrap_deemph_execute(orc_iirfilt_rrrf q, const float *x, unsigned n, float *y)
 { for (unsigned i = 0; i < n; i++) orc_iirfilt_rrrf_execute(q, x[i], &y[i]); }
 
+/* ==========================================================================================
+ *  BroadcastAM, demod.hpp:94-153 (the reference author's own demodulator; all arithmetic is liquid's)
+ *  create :100-108, reset :117-122, demod_one :133-152.  arg() (std::arg -> atan2f) is taken correctly
+ *  rounded, for the same reason as the AGC's logf/expf: its last bit differs between math libraries.
+ *  The rrrf SOS high-pass is the real lane of the crcf section arithmetic.
+ * ======================================================================================== */
+struct orc_bam_s {
+    unsigned m; orc_nco mixer; orc_firfilt lowpass; orc_iirfilt_crcf dcblock;
+    orc_cf *d; unsigned dlen, dpos;          /* wdelaycf(m): m+1 slots */
+};
+orc_bam orc_wrap_bam_create(int m)
+{
+    if (m < 1) return NULL;
+    orc_bam q = calloc(1, sizeof *q);
+    q->m = (unsigned)m;
+    q->mixer = orc_nco_create(ORC_NCO);
+    orc_nco_pll_set_bandwidth(q->mixer, 0.001f);
+    q->lowpass = orc_firfilt_create_kaiser(2 * q->m + 1, 0.01f, 40.0f, 0.0f);
+    q->dcblock = orc_iirfilt_crcf_create_prototype(ORC_IIRDES_CHEBY2, ORC_IIRDES_HIGHPASS, 3, 20.0f / 48000.0f, 0.0f, 0.5f, 20.0f);
+    q->dlen = q->m + 1; q->d = calloc(q->dlen, sizeof(orc_cf));
+    return q;
+}
+void orc_wrap_bam_destroy(orc_bam q)
+{
+    if (!q) return;
+    orc_nco_destroy(q->mixer); orc_firfilt_destroy(q->lowpass); orc_iirfilt_crcf_destroy(q->dcblock); free(q->d); free(q);
+}
+void orc_wrap_bam_reset(orc_bam q)
+{
+    orc_nco_reset(q->mixer); orc_firfilt_reset(q->lowpass); orc_iirfilt_crcf_reset(q->dcblock);
+    memset(q->d, 0, q->dlen * sizeof(orc_cf)); q->dpos = 0;
+}
+void orc_wrap_bam_get_nco(orc_bam q, uint32_t *t, uint32_t *d) { *t = q->mixer->theta; *d = q->mixer->d_theta; }
+unsigned orc_wrap_bam_get_design(orc_bam q, float *lp, float *B, float *A)
+{
+    orc_iirfilt_crcf_get_sos(q->dcblock, B, A);
+    return orc_firfilt_get_taps(q->lowpass, lp);
+}
+/* test hook: run with externally supplied DC-block sections (parity tests hand over the product's design, so
+ * the comparison is of the arithmetic, not of two float evaluations of a pole 2.6e-3 away from z = 1) */
+void orc_wrap_bam_set_dcblock(orc_bam q, const float *B, const float *A, unsigned nsos)
+{
+    orc_iirfilt_crcf_destroy(q->dcblock);
+    q->dcblock = orc_iirfilt_crcf_create_sos(B, A, nsos);
+}
+void orc_wrap_bam_execute(orc_bam q, const orc_cf *x, unsigned n, float *y)
+{
+    for (unsigned i = 0; i < n; i++) {
+        orc_cf x0, x1, v0, v1, in, out;
+        orc_firfilt_crcf_push(q->lowpass, x[i]); orc_firfilt_crcf_execute(q->lowpass, &x0);
+        q->d[q->dpos] = x[i]; q->dpos = (q->dpos + 1) % q->dlen;        /* wdelaycf_push */
+        x1 = q->d[q->dpos];                                             /* wdelaycf_read: x[n-m] */
+        orc_nco_mix_down(q->mixer, x0, &v0);
+        orc_nco_mix_down(q->mixer, x1, &v1);
+        float phase_error = (float)atan2((double)v0.im, (double)v0.re);
+        orc_nco_pll_step(q->mixer, phase_error);
+        orc_nco_step(q->mixer);
+        in.re = v1.re; in.im = 0.0f;
+        orc_iirfilt_crcf_execute_block(q->dcblock, &in, 1, &out);
+        y[i] = out.re;
+    }
+}
+
 /* bytes_to_iq, utility.hpp:61-69 */
 void orc_wrap_bytes_to_iq(const int16_t *iq, unsigned n, orc_cf *y)
 { for (unsigned i = 0; i < n; i++) { y[i].re = (float)iq[2 * i] / 32767.0f; y[i].im = (float)iq[2 * i + 1] / 32767.0f; } }

@@ -195,6 +195,14 @@ void  orc_wrap_deemph_coeffs(float sample_rate, float *b0, float *a1);
 orc_iirfilt_rrrf orc_wrap_deemph_create(float sample_rate);
 void  orc_wrap_deemph_execute(orc_iirfilt_rrrf q, const float *x, unsigned n, float *y);
 /* bytes_to_iq (utility.hpp:61-69) */
+typedef struct orc_bam_s *orc_bam;      /* BroadcastAM, demod.hpp:94-153 */
+orc_bam orc_wrap_bam_create(int m);
+void  orc_wrap_bam_destroy(orc_bam q);
+void  orc_wrap_bam_reset(orc_bam q);
+void  orc_wrap_bam_get_nco(orc_bam q, uint32_t *theta, uint32_t *d_theta);
+unsigned orc_wrap_bam_get_design(orc_bam q, float *lp, float *B, float *A);
+void  orc_wrap_bam_set_dcblock(orc_bam q, const float *B, const float *A, unsigned nsos);
+void  orc_wrap_bam_execute(orc_bam q, const orc_cf *x, unsigned n, float *y);
 void  orc_wrap_bytes_to_iq(const int16_t *iq, unsigned n, orc_cf *y);
 
 /* ---- README AMRadio chain (README.md:41-58) as one object, for the CPU baseline ---- */

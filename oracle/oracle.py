@@ -96,6 +96,9 @@ def _load(name="liboracle.so"):
         "orc_wrap_deemph_coeffs": (None, [F, P, P]), "orc_wrap_deemph_create": (P, [F]),
         "orc_wrap_deemph_execute": (None, [P, P, U, P]),
         "orc_wrap_bytes_to_iq": (None, [P, U, P]),
+        "orc_wrap_bam_create": (P, [I]), "orc_wrap_bam_destroy": (None, [P]), "orc_wrap_bam_reset": (None, [P]),
+        "orc_wrap_bam_get_nco": (None, [P, P, P]), "orc_wrap_bam_get_design": (U, [P, P, P, P]),
+        "orc_wrap_bam_execute": (None, [P, P, U, P]), "orc_wrap_bam_set_dcblock": (None, [P, P, P, U]),
         "orc_amradio_create": (P, [F, F, F]), "orc_amradio_destroy": (None, [P]),
         "orc_amradio_execute": (U, [P, P, U, P]),
     }
@@ -550,6 +553,38 @@ class DeemphasisFilter:
     def __call__(self, x):
         x = _f32(x); y = np.empty(x.shape[0], _f)
         lib.orc_wrap_deemph_execute(self._q, _p(x), x.shape[0], _p(y)); return y
+
+
+class BroadcastAM:
+    """wrapper.cpp:259-262, demod.hpp:94-153."""
+
+    def __init__(self, slen=25, _dcblock=None):
+        self._q = lib.orc_wrap_bam_create(slen)
+        if not self._q:
+            raise ValueError("BroadcastAM: slen must be >= 1")
+        if _dcblock is not None:
+            B, A = (np.ascontiguousarray(a, _f).ravel() for a in _dcblock)
+            lib.orc_wrap_bam_set_dcblock(self._q, _p(B), _p(A), B.size // 3)
+
+    def __del__(self):
+        if getattr(self, "_q", None):
+            lib.orc_wrap_bam_destroy(self._q); self._q = None
+
+    def reset(self): lib.orc_wrap_bam_reset(self._q)
+
+    def design(self):
+        lp = np.zeros(4096, _f); B = np.zeros(48, _f); A = np.zeros(48, _f)
+        n = lib.orc_wrap_bam_get_design(self._q, _p(lp), _p(B), _p(A))
+        return lp[:n].copy(), B[:6].reshape(2, 3).copy(), A[:6].reshape(2, 3).copy()
+
+    def nco_u32(self):
+        t = np.zeros(1, np.uint32); d = np.zeros(1, np.uint32)
+        lib.orc_wrap_bam_get_nco(self._q, _p(t), _p(d)); return int(t[0]), int(d[0])
+
+    def __call__(self, x):
+        x = _c64(x); y = np.empty(x.shape[0], _f)
+        lib.orc_wrap_bam_execute(self._q, _p(x), x.shape[0], _p(y))
+        return y
 
 
 def bytes_to_iq(b):

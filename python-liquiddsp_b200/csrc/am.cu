@@ -19,6 +19,7 @@
 #include "params.h"
 #include "devmath.cuh"
 #include "am.h"
+#include "bam.h"
 
 namespace lqb {
 namespace {
@@ -284,6 +285,13 @@ __global__ void __launch_bounds__(128) agc_tmajor_kernel(const __grid_constant__
 typedef void (*AmFn)(const AmTailArgs);
 
 }  // namespace
+
+cudaError_t agc_tmajor_launch(const AmTailArgs &a, cudaStream_t stream)
+{
+    if (a.C <= 0 || a.n <= 0) return cudaSuccess;
+    agc_tmajor_kernel<<<(unsigned)((a.C + 127) / 128), 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}
 
 cudaError_t amtail_launch(bool has_agc, bool has_de, const AmTailArgs &a, cudaStream_t stream)
 {

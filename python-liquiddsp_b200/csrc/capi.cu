@@ -23,6 +23,7 @@
 #include "seq.h"
 #include "fir.h"
 #include "am.h"
+#include "bam.h"
 #include "par.h"
 #include "scan.h"
 #include "synth.h"
@@ -137,7 +138,7 @@ static bool make_input_tmap(CUtensorMap *tm, const void *x, size_t n, size_t row
 }
 
 // ------------------------------------------------------------------------------------ stages
-enum Kind { K_NCO = 0, K_IIR, K_RESAMP, K_AGC, K_AM, K_FM, K_DEEMPH, K_FIR, K_TF };
+enum Kind { K_NCO = 0, K_IIR, K_RESAMP, K_AGC, K_AM, K_FM, K_DEEMPH, K_FIR, K_TF, K_BAM };
 
 }  // namespace lqb
 
@@ -373,6 +374,31 @@ struct AmStage : lqb_stage_s {
     }
 };
 
+// BroadcastAM (demod.hpp:94-153)
+struct BamStage : lqb_stage_s {
+    int m = 25, ntaps_pad = 56; std::vector<float> lp, B, A;       // lowpass taps (design order), DC-block sections
+    DevArr<float> hrev, dcv; DevArr<float2> hist; DevArr<uint32_t> theta, dtheta;
+    BamStage(int c) : lqb_stage_s(K_BAM, c) {}
+    bool out_real() const override { return true; }
+    int materialize() override
+    {
+        std::vector<float> hr((size_t)ntaps_pad, 0.f);                // window order, zero taps on the oldest side
+        const int nt = (int)lp.size(), pad = ntaps_pad - nt;
+        for (int i = 0; i < nt; i++) hr[pad + i] = lp[nt - 1 - i];
+        LQB_TRY(hrev.alloc(hr.size())); LQB_TRY(hrev.upload(hr.data(), hr.size()));
+        LQB_TRY(hist.alloc((size_t)(ntaps_pad - 1) * C)); LQB_TRY(dcv.alloc((size_t)4 * C));
+        LQB_TRY(theta.alloc(C)); return dtheta.alloc(C);
+    }
+    int clear() override { LQB_TRY(hist.zero()); LQB_TRY(dcv.zero()); LQB_TRY(theta.zero()); return dtheta.zero(); }
+    int fill(BamP &p) const
+    {
+        p.m = m; p.ntaps_pad = ntaps_pad; p.hrev = hrev.p; p.pll_alpha = 0.001f; p.pll_beta = std::sqrt(0.001f);
+        for (int s = 0; s < 2; s++) for (int k = 0; k < 3; k++) { p.b[s][k] = B[3 * s + k]; p.a[s][k] = A[3 * s + k]; }
+        p.hist = hist.p; p.dcv = dcv.p; p.theta = theta.p; p.dtheta = dtheta.p;
+        return sincos_table(&p.sincos);
+    }
+};
+
 struct FmStage : lqb_stage_s {
     float kf = 0.1f, ref = 0.f; DevArr<float2> rprime;
     FmStage(int c) : lqb_stage_s(K_FM, c) {}
@@ -387,7 +413,7 @@ constexpr int kParChannels = 16384;
 
 // ------------------------------------------------------------------------------------ chain
 struct Segment {
-    enum Type { SEQ, FIR, RESAMP_PAR, AMTAIL, NCO_PAR } type = SEQ;
+    enum Type { SEQ, FIR, RESAMP_PAR, AMTAIL, NCO_PAR, BAM } type = SEQ;
     unsigned mask = 0; int nsos = 0, sos0 = 0;
     std::vector<lqb_stage_s *> st;
     std::string name;
@@ -425,7 +451,7 @@ static const char *kind_name(Kind k)
 {
     switch (k) {
     case K_NCO: return "nco"; case K_IIR: return "iir"; case K_RESAMP: return "resamp"; case K_AGC: return "agc";
-    case K_AM: return "ampmodem"; case K_FM: return "freqdem"; case K_DEEMPH: return "deemph"; case K_FIR: return "fir"; case K_TF: return "tf";
+    case K_AM: return "ampmodem"; case K_FM: return "freqdem"; case K_DEEMPH: return "deemph"; case K_FIR: return "fir"; case K_TF: return "tf"; case K_BAM: return "broadcast_am";
     }
     return "?";
 }
@@ -482,6 +508,18 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
     for (size_t i = 0; i < st.size();) {
         Segment g;
         if (st[i]->kind == K_FIR) { g.type = Segment::FIR; g.st = { st[i] }; g.name = "fir"; segs.push_back(g); i++; continue; }
+        // [AGC ->] BroadcastAM [-> de-emphasis] (bam.cu).  The gain loop joins only behind a decimating kernel: it then
+        // runs in place on the time-major hand-off buffer
+        {
+            size_t j = i; std::string nm; Segment b;
+            const bool after_rs = !segs.empty() && segs.back().type == Segment::SEQ && (segs.back().mask & F_RS);
+            if (c->fuse >= 1 && after_rs && st[j]->kind == K_AGC && j + 1 < st.size() && st[j + 1]->kind == K_BAM) { b.st.push_back(st[j++]); nm = "agc+"; }
+            if (st[j]->kind == K_BAM) {
+                b.type = Segment::BAM; b.st.push_back(st[j++]); nm += "broadcast_am";
+                if (c->fuse >= 1 && j < st.size() && st[j]->kind == K_DEEMPH) { b.st.push_back(st[j++]); nm += "+deemph"; }
+                b.name = "bam[" + nm + "]"; segs.push_back(b); i = j; continue;
+            }
+        }
         // [AGC ->] ampmodem [-> de-emphasis] : the decimated-rate tail kernel (am.cu)
         if (c->fuse < 2) {
             size_t j = i; std::string nm;
@@ -552,6 +590,25 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         }
         LQB_CUDA(amtail_launch(has_agc, has_de, a, stream));
         *launches += amtail_launch_count(has_agc, a) - 1;
+        return LQB_OK;
+    }
+    if (g.type == Segment::BAM) {
+        BamArgs a{};
+        a.x = (const float2 *)x; a.y = (float *)y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.in_tmajor = in_tmajor ? 1 : 0;
+        a.n = (long long)n; a.in_pitch = in_tmajor ? (long long)nch : (long long)n; a.out_pitch = (long long)n_out;
+        for (lqb_stage_s *s : g.st) {
+            if (s->kind == K_AGC) {
+                if (!in_tmajor) return fail(LQB_EINVAL, "internal: in-place gain control needs the time-major hand-off");
+                AmTailArgs ag{};
+                ag.x = a.x; ag.C = nch; ag.ch0 = ch0; ag.Ctot = first->C; ag.in_tmajor = 1; ag.n = a.n; ag.in_pitch = a.in_pitch;
+                LQB_TRY(static_cast<AgcStage *>(s)->fill(ag.agc));
+                LQB_CUDA(agc_tmajor_launch(ag, stream));
+                (*launches)++;
+            }
+            else if (s->kind == K_BAM) LQB_TRY(static_cast<BamStage *>(s)->fill(a.p));
+            else if (s->kind == K_DEEMPH) { static_cast<DeemphStage *>(s)->fill(a.de); a.has_de = 1; }
+        }
+        LQB_CUDA(bam_launch(a, stream));
         return LQB_OK;
     }
     if (g.type == Segment::FIR) {
@@ -674,7 +731,8 @@ static int run_all(lqb_chain_s *c, const std::vector<Segment> &segs, const void 
         // a segment of the same IIR stage split by section offset keeps the sample count
         // a decimating sequential kernel hands its output to the AM tail kernel time-major [sample][channel]:
         // both sides then touch HBM with warp-contiguous accesses and neither needs a staging tile
-        const bool out_tm = k + 1 < segs.size() && segs[k].type == Segment::SEQ && (segs[k].mask & F_RS) && segs[k + 1].type == Segment::AMTAIL;
+        const bool out_tm = k + 1 < segs.size() && segs[k].type == Segment::SEQ && (segs[k].mask & F_RS) &&
+                            (segs[k + 1].type == Segment::AMTAIL || segs[k + 1].type == Segment::BAM);
         if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[k].first, stream));
         if (on > 0 || cur_n > 0) LQB_TRY(run_segment(segs[k], cur, dst, cur_n, on, ch0, nch, stream, in_tm, out_tm, launches, k == 0 ? first_extra : 0u));
         if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[k].second, stream));
@@ -1110,6 +1168,39 @@ int lqb_ampmodem_create(float mod, int type, int suppressed, int C, lqb_stage *o
     design::firdes_kaiser(kAmTaps, 0.01f, 40.0f, 0.0f, q->lp);
     design::firdes_notch(kAmDelay, 0.0f, 20.0f, q->dc);
     *out = q; return LQB_OK;
+}
+// ---- BroadcastAM
+int lqb_broadcast_am_create(int m, int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!out || m < 1 || m > kBamMaxM) return fail(LQB_EINVAL, "BroadcastAM: slen must be in 1..%d", kBamMaxM);
+    BamStage *q = new BamStage(C);
+    q->m = m; q->ntaps_pad = (2 * m + 1 + 7) / 8 * 8;
+    // demod.hpp:101-106: PLL bandwidth 0.001, lowpass kaiser(2m+1, 0.01, 40 dB), cheby2 order-3 high-pass at 20 Hz / 48 kHz
+    design::firdes_kaiser((unsigned)(2 * m + 1), 0.01f, 40.0f, 0.0f, q->lp);
+    if (design::iirdes_sos(design::CHEBY2, design::HIGHPASS, 3, 20.0f / 48000.0f, 0.0f, 0.5f, 20.0f, q->B, q->A) != 0 || q->B.size() != 6) {
+        delete q; return fail(LQB_EINVAL, "BroadcastAM: DC-block design failed");
+    }
+    *out = q; return LQB_OK;
+}
+int lqb_broadcast_am_get_design(lqb_stage s, float *lp, int *nlp, float *B, float *A)
+{
+    LQB_GET(BamStage, q, s, K_BAM);
+    if (lp) std::copy(q->lp.begin(), q->lp.end(), lp);
+    if (nlp) *nlp = (int)q->lp.size();
+    if (B) std::copy(q->B.begin(), q->B.end(), B);
+    if (A) std::copy(q->A.begin(), q->A.end(), A);
+    return LQB_OK;
+}
+int lqb_broadcast_am_get_nco_u32(lqb_stage s, uint32_t *theta, uint32_t *d_theta, int n)
+{
+    LQB_GET(BamStage, q, s, K_BAM);
+    if (n < 0 || n > q->C) return fail(LQB_EINVAL, "bad channel count");
+    LQB_TRY(q->ensure());
+    LQB_CUDA(cudaDeviceSynchronize());
+    if (theta) LQB_TRY(q->theta.download(theta, n));
+    if (d_theta) LQB_TRY(q->dtheta.download(d_theta, n));
+    return LQB_OK;
 }
 int lqb_ampmodem_get_taps(lqb_stage s, float *lp, int *nlp, float *dc, int *ndc)
 {

@@ -101,6 +101,27 @@ struct AmTailArgs {
     AgcP agc; AmP am; DeP de;
 };
 
+// BroadcastAM (demod.hpp:94-153): carrier PLL with an arg() phase detector, Kaiser lowpass of 2m+1 taps on the PLL
+// branch, the signal branch delayed by m, real part high-passed by a two-section IIR
+constexpr int kBamMaxM = 64;
+struct BamP {
+    int m, ntaps_pad;              // lowpass taps padded (leading zeros) to a multiple of 8
+    const float *hrev;             // [ntaps_pad] taps in window order: hrev[i] multiplies the sample (ntaps_pad-1-i) steps old
+    float pll_alpha, pll_beta;
+    float b[2][3], a[2][3];        // DC-block sections (iirfilt_rrrf, SOS)
+    const float2 *sincos;
+    float2 *hist;                  // [ntaps_pad - 1][Ctot] newest inputs of the previous calls, oldest first
+    float *dcv;                    // [4][Ctot] v1, v2 of each section
+    uint32_t *theta, *dtheta;      // [Ctot]
+};
+struct BamArgs {
+    const float2 *x;               // row-major [C][in_pitch] or time-major [n][in_pitch]
+    float *y;                      // [C][out_pitch]
+    int C, ch0, Ctot, in_tmajor, has_de;
+    long long n, in_pitch, out_pitch;
+    BamP p; DeP de;
+};
+
 struct FirArgs {
     const float2 *x; float2 *y;    // [C][n]
     int C, ch0, Ctot, ntaps;

@@ -81,6 +81,8 @@ _SIG = {
     "lqb_ampmodem_create": [_F, _I, _I, _I, _PP], "lqb_ampmodem_get_taps": [_P, _P, C.POINTER(_I), _P, C.POINTER(_I)],
     "lqb_ampmodem_get_nco_u32": [_P, _P, _P, _I],
     "lqb_freqdem_create": [_F, _I, _PP],
+    "lqb_broadcast_am_create": [_I, _I, _PP], "lqb_broadcast_am_get_design": [_P, _P, C.POINTER(_I), _P, _P],
+    "lqb_broadcast_am_get_nco_u32": [_P, _P, _P, _I],
     "lqb_chain_create": [_PP], "lqb_chain_append": [_P, _P], "lqb_chain_destroy": [_P],
     "lqb_chain_out_len": [_P, _SZ, C.POINTER(_SZ)],
     "lqb_chain_execute": [_P, _P, _SZ, _P, _SZ, C.POINTER(_SZ)],
@@ -504,6 +506,25 @@ class FreqDem(_Stage):
 
     def print(self):
         print("freqdem [kf %g]" % self.kd)
+
+
+class BroadcastAM(_Stage):
+    """wrapper.cpp:259-262 / demod.hpp:94-153: carrier-PLL AM demodulator with an IIR DC block."""
+    _out_dtype = np.float32
+
+    def __init__(self, slen=25, channels=1):
+        super().__init__()
+        _ck(_lib.lqb_broadcast_am_create(int(slen), channels, C.byref(self._h)))
+
+    def design(self):
+        """(lowpass taps, B[2x3], A[2x3]) -- the Kaiser lowpass and the two DC-block sections."""
+        lp = np.zeros(4096, np.float32); B = np.zeros(6, np.float32); A = np.zeros(6, np.float32); n = _I()
+        _ck(_lib.lqb_broadcast_am_get_design(self._h, _ptr(lp), C.byref(n), _ptr(B), _ptr(A)))
+        return lp[:n.value].copy(), B.reshape(2, 3), A.reshape(2, 3)
+
+    def nco_u32(self):
+        n = self.channels; t = np.zeros(n, np.uint32); d = np.zeros(n, np.uint32)
+        _ck(_lib.lqb_broadcast_am_get_nco_u32(self._h, _ptr(t), _ptr(d), n)); return t, d
 
 
 class Chain(_Stage):

@@ -63,6 +63,7 @@ def test_reference_api_surface():
     for cls in (L.CBandpassIIR, L.CBandstopIIR, L.RBandpassIIR, L.RBandstopIIR):
         assert sig(cls) == dict(filter_type="butter", order=2, Fc=0.2, F0=0.3, Ap=0.5, As=20.0)
     assert sig(L.CIIRFilter) == sig(L.RIIRFilter) == dict(Bc=inspect._empty, Ac=inspect._empty)
+    assert sig(L.BroadcastAM) == dict(slen=25)
     assert sig(L.RealDCBlocker) == dict(slen=25, As=20.0)
     assert sig(L.RealKaiserBessel) == dict(flen=25, Fc=0.25, As=20.0, offset=0.0)
     assert L.CBandpassIIR.__name__ == "CBandpassIIR" and L.RLowpassIIR("cheby1", 4, 0.1).band_type == "lowpass"
@@ -118,6 +119,18 @@ def test_product_tables_equal_oracle_tables():
     assert abs(L.FIRFilter(h).freqresponse(0.05) - O.FIRFilter(h).freqresponse(0.05)) < 1e-5
 
 
+def test_broadcast_am_design_equals_oracle():
+    for m in (25, 7, 40):
+        (lp, B, A), (lpo, Bo, Ao) = L.BroadcastAM(m).design(), O.BroadcastAM(m).design()
+        assert lp.size == 2 * m + 1 and np.array_equal(lp, lpo)
+        assert np.max(np.abs(B - Bo)) < 2e-6 and np.max(np.abs(A - Ao)) < 2e-6
+    assert A[1, 2] == 0 and B[1, 2] == 0                   # order 3: one biquad + one first-order section
+    with pytest.raises(ValueError):
+        L.BroadcastAM(0)
+    with pytest.raises(ValueError):
+        L.BroadcastAM(65)
+
+
 def _radio(ch=1):
     return (L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=ch), L.ComplexResampler(0.024, Fc=0.024, channels=ch),
             L.AGC(channels=ch), L.AmpModem(0.5, "dsb", True, channels=ch), L.DeemphasisFilter(48000, channels=ch))
@@ -140,6 +153,10 @@ def test_planner():
     assert L.Chain(*_radio()).out_len(65536) == 1573
     assert L.Chain(L.RealIIRFilter("butter", "bandpass", order=10, Fc=0.1, F0=0.2), L.DeemphasisFilter()).plan() == "seq[iir8] -> seq[iir2] -> seq[deemph]"
     assert L.Chain(L.AmpModem(0.5, "dsb", True), L.RealDCBlocker(), L.RLowpassIIR("butter", 4, 0.1)).plan() == "am[ampmodem] -> fir -> seq[iir2]"
+    rs = lambda ch=1: (L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=ch), L.ComplexResampler(0.024, Fc=0.024, channels=ch))
+    assert L.Chain(*rs(), L.BroadcastAM()).plan() == "seq[iir4+resamp] -> bam[broadcast_am]"
+    assert L.Chain(*rs(), L.AGC(), L.BroadcastAM(), L.DeemphasisFilter()).plan() == "seq[iir4+resamp] -> bam[agc+broadcast_am+deemph]"
+    assert L.Chain(L.AGC(), L.BroadcastAM(30)).plan() == "seq[agc] -> bam[broadcast_am]"      # no hand-off buffer to run the AGC in
     with pytest.raises(ValueError):                        # real-input stage after a complex-output stage
         L.Chain(L.ComplexIIRFilter(order=2), L.DeemphasisFilter()).plan()
     with pytest.raises(ValueError):

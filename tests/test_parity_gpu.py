@@ -228,6 +228,63 @@ def test_real_chain_am_dcblock_lowpass(cuda):
     assert rel_l2(chain(x), olp(odc(oam(x)))) <= TOL_E2E
 
 
+# ------------------------------------------------------------------------- 8f row 3: BroadcastAM
+def _bits_or_close(y, yo, tol=TOL_STAGE):
+    """The PLL branch takes arg() through a double-precision atan2 on both sides; the two math libraries agree after
+    rounding to float except with probability ~1e-8 per sample, so equality is expected and 1e-5 is demanded."""
+    return np.array_equal(y.view(np.uint32), yo.view(np.uint32)) or rel_l2(y, yo) <= tol
+
+
+@pytest.mark.parametrize("m,n", [(25, 30000), (7, 5001), (40, 3000), (64, 777), (25, 5)])
+def test_broadcast_am_single_channel(cuda, m, n):
+    x = am_iq(n, fs=48000.0, f_off=35.0, noise=0.01, amp=1.0)
+    # the oracle runs the product's DC-block sections: that filter's poles sit 2.6e-3 from z = 1, and the one-ulp
+    # differences between two float evaluations of the same design move its output by percent (measured 3.8 %)
+    g = L.BroadcastAM(m); o = O.BroadcastAM(m, _dcblock=g.design()[1:])
+    y, yo = g(x), o(x)
+    assert y.dtype == np.float32 and y.shape == (n,)
+    assert _bits_or_close(y, yo), rel_l2(y, yo)
+    t, d = g.nco_u32(); to, do = o.nco_u32()
+    assert abs(int(d[0]) - do) <= 256 and abs(int(np.int32(np.uint32(int(t[0]) - to)))) <= 1 << 16
+
+
+def test_broadcast_am_streaming_batched_reset(cuda):
+    rng = np.random.default_rng(41)
+    C, n = 70, 9000
+    x = np.stack([am_iq(n, fs=48000.0, f_off=10.0 + c, phase=0.1 * c, seed=c, noise=0.02, amp=0.5 + 0.01 * c) for c in range(C)])
+    a, b = L.BroadcastAM(25, channels=C), L.BroadcastAM(25, channels=C)
+    whole = a(x)
+    parts = np.concatenate([b(x[:, s:e]) for s, e in split_points(n, 7, rng)], axis=1)
+    assert np.array_equal(whole.view(np.uint32), parts.view(np.uint32))           # carried state: bit-identical
+    for c in (0, 33, 69):
+        assert _bits_or_close(whole[c], O.BroadcastAM(25, _dcblock=a.design()[1:])(x[c])), c
+    a.reset()
+    assert np.array_equal(a(x[:, :100]), whole[:, :100])
+
+
+def test_broadcast_am_receiver_chain(cuda):
+    """The author's preferred receiver: bandpass -> resample -> [AGC ->] BroadcastAM -> de-emphasis, fused plan
+    (time-major hand-off, gain control in place) against the stage-by-stage oracle and the unfused plan."""
+    C, n = 67, 65536
+    x = np.stack([am_iq(n, f_off=100.0 + 3 * c, phase=0.05 * c, seed=100 + c) for c in range(C)])
+    mk = lambda: (L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=C), L.ComplexResampler(0.024, Fc=0.024, channels=C),
+                  L.AGC(channels=C), L.BroadcastAM(25, channels=C), L.DeemphasisFilter(48000, channels=C))
+    st = mk(); st[2].scale = 0.01
+    fused = L.Chain(*st)
+    assert fused.plan() == "seq[iir4+resamp] -> bam[agc+broadcast_am+deemph]"
+    st0 = mk(); st0[2].scale = 0.01
+    plain = L.Chain(*st0, fuse=0)
+    yf = np.concatenate([fused(x[:, :30000]), fused(x[:, 30000:])], axis=1)
+    yp = np.concatenate([plain(x[:, :30000]), plain(x[:, 30000:])], axis=1)
+    assert np.array_equal(yf.view(np.uint32), yp.view(np.uint32))
+    for c in (0, 66):
+        oi, ors, oa, ob, od = (O.ComplexIIRFilter(_sos=st[0].sos()), O.ComplexResampler(0.024, Fc=0.024), O.AGC(),
+                               O.BroadcastAM(25, _dcblock=st[3].design()[1:]), O.DeemphasisFilter(48000))
+        oa.scale = 0.01
+        yo = od(ob(oa(ors(oi(x[c])))))
+        assert yo.shape == yf[c].shape and (np.array_equal(yf[c], yo) or rel_l2(yf[c], yo) <= TOL_E2E), (c, rel_l2(yf[c], yo))
+
+
 # ------------------------------------------------------------------------------------------- a3
 def test_resampler_readme_rate_counts_and_values(cuda):
     rng = np.random.default_rng(6)
