@@ -1135,6 +1135,98 @@ void orc_wrap_bam_execute(orc_bam q, const orc_cf *x, unsigned n, float *y)
     }
 }
 
+/* ==========================================================================================
+ *  firhilbf    liquid: src/filter/src/firhilb.proto.c (>= 1.3.2: four windows, toggle, two-output c2r)
+ *  reached from: SSBDemod (demod.hpp:163 create(25, 60), :181/:184 c2r_execute), HilbertTransform
+ *  (utility.hpp:79-80 create, :93 interp_execute, :101 decim_execute)
+ *  Half-band Kaiser prototype of 4m+1 taps, modulated by sin(pi t / 2); the 2m odd-offset taps, reversed,
+ *  form the quadrature branch; the in-phase branch is a pure delay.
+ * ======================================================================================== */
+struct orc_firhilbf_s { unsigned m, L; float *hq; float *w[4]; unsigned wi[4]; unsigned toggle; };
+
+orc_firhilbf orc_firhilbf_create(unsigned m, float as)
+{
+    if (m < 2) return NULL;
+    orc_firhilbf q = calloc(1, sizeof *q);
+    unsigned h_len = 4 * m + 1, i, j = 0;
+    q->m = m; q->L = 2 * m;
+    float *h = malloc(h_len * sizeof(float));
+    orc_firdes_kaiser(h_len, 0.25f, fabsf(as), 0.0f, h);
+    for (i = 0; i < h_len; i++) {
+        float t = (float)i - (float)(h_len - 1) / 2.0f;
+        h[i] = h[i] * sinf((float)(0.5f * M_PI * t));          /* imag(h[i] * cexpf(j 0.5 pi t)) */
+    }
+    q->hq = malloc(q->L * sizeof(float));
+    for (i = 1; i < h_len; i += 2) q->hq[j++] = h[h_len - i - 1];
+    free(h);
+    for (i = 0; i < 4; i++) q->w[i] = calloc(2 * q->L, sizeof(float));
+    return q;
+}
+void orc_firhilbf_destroy(orc_firhilbf q) { if (!q) return; free(q->hq); for (int i = 0; i < 4; i++) free(q->w[i]); free(q); }
+void orc_firhilbf_reset(orc_firhilbf q)
+{
+    for (int i = 0; i < 4; i++) { memset(q->w[i], 0, 2 * q->L * sizeof(float)); q->wi[i] = 0; }
+    q->toggle = 0;
+}
+unsigned orc_firhilbf_get_hq(orc_firhilbf q, float *hq) { memcpy(hq, q->hq, q->L * sizeof(float)); return q->L; }
+static void hw_push(orc_firhilbf q, int k, float x) { q->w[k][q->wi[k]] = q->w[k][q->wi[k] + q->L] = x; q->wi[k] = (q->wi[k] + 1) % q->L; }
+static const float *hw_read(orc_firhilbf q, int k) { return q->w[k] + q->wi[k]; }     /* oldest first */
+static float hw_dot(orc_firhilbf q, const float *r) { float s = 0.0f; for (unsigned i = 0; i < q->L; i++) s = FMA(q->hq[i], r[i], s); return s; }
+
+void orc_firhilbf_r2c_execute(orc_firhilbf q, float x, orc_cf *y)
+{
+    float yi, yq;
+    if (q->toggle == 0) { hw_push(q, 0, x); yi = hw_read(q, 0)[q->m - 1]; yq = hw_dot(q, hw_read(q, 1)); }
+    else                { hw_push(q, 1, x); yi = hw_read(q, 1)[q->m - 1]; yq = hw_dot(q, hw_read(q, 0)); }
+    q->toggle = 1 - q->toggle;
+    y->re = yi; y->im = yq;
+}
+void orc_firhilbf_c2r_execute(orc_firhilbf q, orc_cf x, float *y_lsb, float *y_usb)
+{
+    float yi, yq;
+    if (q->toggle == 0) { hw_push(q, 0, x.re); hw_push(q, 1, x.im); yi = hw_read(q, 0)[q->m - 1]; yq = hw_dot(q, hw_read(q, 3)); }
+    else                { hw_push(q, 2, x.re); hw_push(q, 3, x.im); yi = hw_read(q, 2)[q->m - 1]; yq = hw_dot(q, hw_read(q, 1)); }
+    q->toggle = 1 - q->toggle;
+    *y_lsb = yi + yq; *y_usb = yi - yq;
+}
+void orc_firhilbf_decim_execute(orc_firhilbf q, const float *x, orc_cf *y)
+{
+    float yi, yq;
+    hw_push(q, 1, x[0]); yq = hw_dot(q, hw_read(q, 1));
+    hw_push(q, 0, x[1]); yi = hw_read(q, 0)[q->m - 1];
+    if (q->toggle) { y->re = -yi; y->im = -yq; } else { y->re = yi; y->im = yq; }
+    q->toggle = 1 - q->toggle;
+}
+void orc_firhilbf_interp_execute(orc_firhilbf q, orc_cf x, float *y)
+{
+    float vr = q->toggle ? -x.re : x.re, vi = q->toggle ? -x.im : x.im;
+    hw_push(q, 0, vi); y[0] = hw_read(q, 0)[q->m - 1];
+    hw_push(q, 1, vr); y[1] = hw_dot(q, hw_read(q, 1));
+    q->toggle = 1 - q->toggle;
+}
+
+/* SSBDemod::execute, demod.hpp:172-186 */
+void orc_wrap_ssb_execute(orc_firhilbf q, int usb, const orc_cf *x, unsigned n, float *y)
+{
+    float lsb_, usb_;
+    for (unsigned i = 0; i < n; i++) { orc_firhilbf_c2r_execute(q, x[i], &lsb_, &usb_); y[i] = usb ? usb_ : lsb_; }
+}
+/* HilbertTransform::call, complex64 branch, utility.hpp:88-95: interp_execute(z[n], &y[n]) writes y[n] and y[n+1];
+ * every y[n+1] is overwritten by the next iteration, so y[n] keeps the delay-branch output.  The reference's last
+ * iteration writes y[len] past the end of the array; that write is dropped here. */
+void orc_wrap_hilbert_c2r(orc_firhilbf q, const orc_cf *z, unsigned n, float *y)
+{
+    float out[2];
+    for (unsigned i = 0; i < n; i++) { orc_firhilbf_interp_execute(q, z[i], out); y[i] = out[0]; }
+}
+/* float32 branch, utility.hpp:96-103: decim_execute(&z[n], &y[n]) reads z[n] and z[n+1] (overlapping pairs); the last
+ * iteration reads z[len] past the end of the array -- undefined in the reference, taken as 0.0f here. */
+void orc_wrap_hilbert_r2c(orc_firhilbf q, const float *z, unsigned n, orc_cf *y)
+{
+    float pair[2];
+    for (unsigned i = 0; i < n; i++) { pair[0] = z[i]; pair[1] = i + 1 < n ? z[i + 1] : 0.0f; orc_firhilbf_decim_execute(q, pair, &y[i]); }
+}
+
 /* bytes_to_iq, utility.hpp:61-69 */
 void orc_wrap_bytes_to_iq(const int16_t *iq, unsigned n, orc_cf *y)
 { for (unsigned i = 0; i < n; i++) { y[i].re = (float)iq[2 * i] / 32767.0f; y[i].im = (float)iq[2 * i + 1] / 32767.0f; } }

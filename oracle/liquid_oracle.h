@@ -195,6 +195,18 @@ void  orc_wrap_deemph_coeffs(float sample_rate, float *b0, float *a1);
 orc_iirfilt_rrrf orc_wrap_deemph_create(float sample_rate);
 void  orc_wrap_deemph_execute(orc_iirfilt_rrrf q, const float *x, unsigned n, float *y);
 /* bytes_to_iq (utility.hpp:61-69) */
+typedef struct orc_firhilbf_s *orc_firhilbf;   /* firhilbf: SSBDemod demod.hpp:155-187, HilbertTransform utility.hpp:71-108 */
+orc_firhilbf orc_firhilbf_create(unsigned m, float as);
+void  orc_firhilbf_destroy(orc_firhilbf q);
+void  orc_firhilbf_reset(orc_firhilbf q);
+unsigned orc_firhilbf_get_hq(orc_firhilbf q, float *hq);
+void  orc_firhilbf_r2c_execute(orc_firhilbf q, float x, orc_cf *y);
+void  orc_firhilbf_c2r_execute(orc_firhilbf q, orc_cf x, float *y_lsb, float *y_usb);
+void  orc_firhilbf_decim_execute(orc_firhilbf q, const float *x, orc_cf *y);
+void  orc_firhilbf_interp_execute(orc_firhilbf q, orc_cf x, float *y);
+void  orc_wrap_ssb_execute(orc_firhilbf q, int usb, const orc_cf *x, unsigned n, float *y);
+void  orc_wrap_hilbert_c2r(orc_firhilbf q, const orc_cf *z, unsigned n, float *y);
+void  orc_wrap_hilbert_r2c(orc_firhilbf q, const float *z, unsigned n, orc_cf *y);
 typedef struct orc_bam_s *orc_bam;      /* BroadcastAM, demod.hpp:94-153 */
 orc_bam orc_wrap_bam_create(int m);
 void  orc_wrap_bam_destroy(orc_bam q);

@@ -96,6 +96,9 @@ def _load(name="liboracle.so"):
         "orc_wrap_deemph_coeffs": (None, [F, P, P]), "orc_wrap_deemph_create": (P, [F]),
         "orc_wrap_deemph_execute": (None, [P, P, U, P]),
         "orc_wrap_bytes_to_iq": (None, [P, U, P]),
+        "orc_firhilbf_create": (P, [U, F]), "orc_firhilbf_destroy": (None, [P]), "orc_firhilbf_reset": (None, [P]),
+        "orc_firhilbf_get_hq": (U, [P, P]), "orc_wrap_ssb_execute": (None, [P, I, P, U, P]),
+        "orc_wrap_hilbert_c2r": (None, [P, P, U, P]), "orc_wrap_hilbert_r2c": (None, [P, P, U, P]),
         "orc_wrap_bam_create": (P, [I]), "orc_wrap_bam_destroy": (None, [P]), "orc_wrap_bam_reset": (None, [P]),
         "orc_wrap_bam_get_nco": (None, [P, P, P]), "orc_wrap_bam_get_design": (U, [P, P, P, P]),
         "orc_wrap_bam_execute": (None, [P, P, U, P]), "orc_wrap_bam_set_dcblock": (None, [P, P, P, U]),
@@ -553,6 +556,53 @@ class DeemphasisFilter:
     def __call__(self, x):
         x = _f32(x); y = np.empty(x.shape[0], _f)
         lib.orc_wrap_deemph_execute(self._q, _p(x), x.shape[0], _p(y)); return y
+
+
+class SSBDemod:
+    """wrapper.cpp:269-272, demod.hpp:155-187: firhilbf(25, 60 dB), band == "usb" picks the upper side-band."""
+
+    def __init__(self, band, _m=25, _As=60.0):
+        self.usb = band == "usb"
+        self._q = lib.orc_firhilbf_create(_m, _As)
+
+    def __del__(self):
+        if getattr(self, "_q", None):
+            lib.orc_firhilbf_destroy(self._q); self._q = None
+
+    def reset(self): lib.orc_firhilbf_reset(self._q)
+
+    def hq(self):
+        h = np.zeros(4096, _f); n = lib.orc_firhilbf_get_hq(self._q, _p(h)); return h[:n].copy()
+
+    def __call__(self, x):
+        x = _c64(x); y = np.empty(x.shape[0], _f)
+        lib.orc_wrap_ssb_execute(self._q, int(self.usb), _p(x), x.shape[0], _p(y))
+        return y
+
+
+class HilbertTransform:
+    """wrapper.cpp:174-176, utility.hpp:71-108: complex64 in -> float32 out, float32 in -> complex64 out, else None."""
+
+    def __init__(self, m=5, As=60.0):
+        self._c2r, self._r2c = lib.orc_firhilbf_create(m, As), lib.orc_firhilbf_create(m, As)
+        if not self._c2r:
+            raise ValueError("firhilbf: m must be >= 2")
+
+    def __del__(self):
+        for q in (getattr(self, "_c2r", None), getattr(self, "_r2c", None)):
+            if q:
+                lib.orc_firhilbf_destroy(q)
+        self._c2r = self._r2c = None
+
+    def __call__(self, x):
+        x = np.asarray(x)
+        if x.dtype == np.complex64:
+            x = np.ascontiguousarray(x); y = np.empty(x.shape[0], _f)
+            lib.orc_wrap_hilbert_c2r(self._c2r, _p(x), x.shape[0], _p(y)); return y
+        if x.dtype == np.float32:
+            x = np.ascontiguousarray(x); y = np.empty(x.shape[0], _cf)
+            lib.orc_wrap_hilbert_r2c(self._r2c, _p(x), x.shape[0], _p(y)); return y
+        return None
 
 
 class BroadcastAM:

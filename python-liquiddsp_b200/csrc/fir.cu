@@ -30,8 +30,10 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
 }
 
-// REAL: firfilt_rrrf -- float samples in and out; they ride in the real lane of the same arithmetic
-template <bool REAL>
+// IN_REAL / OUT_REAL: float rows instead of complex64.  firfilt_rrrf is real in, real out: the samples ride in the
+// real lane of the same arithmetic.  The firhilbf users (SSBDemod, HilbertTransform) run the two lanes with different
+// taps -- a pure delay in one, the quadrature filter in the other -- and combine them when the tile is written.
+template <bool IN_REAL, bool OUT_REAL>
 __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntiles, const int ntaps_pad)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -49,14 +51,19 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
     const float2 *hrow = a.hist_in + gch * (long long)(a.ntaps - 1);
     const int nh = a.ntaps - 1;
 
-    for (int k = tid; k < ntaps_pad; k += NT) { const float h = k < a.ntaps ? a.taps[k] : 0.f; s_h[k] = make_float2(h, h); }
+    const bool dup = a.mode == FIR_R2C;                                // real input feeds both lanes
+    auto lift = [&](float v) { return make_float2(v, dup ? v : 0.f); };
+    for (int k = tid; k < ntaps_pad; k += NT) {
+        const float h = k < a.ntaps ? a.taps[k] : 0.f;
+        s_h[k] = make_float2(h, a.taps_q ? (k < a.ntaps ? a.taps_q[k] : 0.f) : h);
+    }
     // i advances by NT = 8 * 16 per pass, so its padded position advances by a constant 8 * 17
     for (int i = tid, pi = phys(tid); i < TN + halo; i += NT, pi += (NT / 16) * 17) {
         const long long g = t0 - halo + i;                             // global sample index
         float2 *dst = &s_x[pi];
         if (g >= 0) {
             if (g >= a.n) *dst = make_float2(0.f, 0.f);
-            else if (REAL) *dst = make_float2(xrow_r[g], 0.f);
+            else if (IN_REAL) *dst = lift(xrow_r[g]);
             else cp_async8(dst, xrow + g);
         }
         else if (g + nh >= 0) cp_async8(dst, hrow + (g + nh));
@@ -69,7 +76,7 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
         float2 *ho = a.hist_out + gch * (long long)nh;
         for (int j = tid; j < nh; j += NT) {
             const long long g = a.n - nh + j;
-            ho[j] = g >= 0 ? (REAL ? make_float2(xrow_r[g], 0.f) : xrow[g]) : hrow[g + nh];
+            ho[j] = g >= 0 ? (IN_REAL ? lift(xrow_r[g]) : xrow[g]) : hrow[g + nh];
         }
     }
     cp_async_wait<0>();
@@ -104,10 +111,24 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
     __syncthreads();
     const u64 sc = pk(a.scale, a.scale);
 #pragma unroll
-    for (int r = 0; r < R; r++) s_x[17 * tid + r] = upk(mul2(acc[r], sc));          // phys(16 * tid + r)
+    for (int r = 0; r < R; r++) {
+        float2 v = upk(mul2(acc[r], sc));
+        if (a.mode != FIR_PLAIN) {
+            const unsigned long long kabs = a.count + (unsigned long long)(t0 + R * tid + r);
+            const long long kloc = t0 + R * tid + r;
+            if (a.mode == FIR_SSB_LSB) v.x = __fadd_rn(v.x, v.y);
+            else if (a.mode == FIR_SSB_USB) v.x = __fsub_rn(v.x, v.y);
+            else if (a.mode == FIR_C2R) v.x = kabs < (unsigned long long)a.delay ? 0.f : (((kabs - a.delay) & 1ull) ? -v.y : v.y);
+            else {                                                      // FIR_R2C
+                if (kloc == a.zero_at[0] || kloc == a.zero_at[1] || kloc == a.zero_at[2] || kloc == a.zero_at[3]) v.x = 0.f;
+                if (kabs & 1ull) { v.x = -v.x; v.y = -v.y; }
+            }
+        }
+        s_x[17 * tid + r] = v;                                                       // phys(16 * tid + r)
+    }
     __syncthreads();
     float2 *yrow = a.y + ch * a.n;
-    if (REAL) {
+    if (OUT_REAL) {
         float *yr = (float *)a.y + ch * a.n;
         for (int i = tid; i < TN; i += NT) { const long long g = t0 + i; if (g < a.n) yr[g] = s_x[phys(i)].x; }
         return;
@@ -137,7 +158,9 @@ cudaError_t fir_launch(const FirArgs &a, cudaStream_t stream)
     const long long ntiles = (a.n + TN - 1) / TN;
     const size_t smem = (size_t)(TN + halo + ((TN + halo) >> 4) + 2 + ntaps_pad) * sizeof(float2);
     if (smem > 200 * 1024 || ntiles * (long long)a.C > 0x7fffffffLL) return cudaErrorInvalidValue;
-    auto fn = a.real_io ? fir_kernel<true> : fir_kernel<false>;
+    const bool in_real = a.real_io || a.in_real, out_real = a.real_io || a.out_real;
+    auto fn = in_real ? (out_real ? fir_kernel<true, true> : fir_kernel<true, false>)
+                      : (out_real ? fir_kernel<false, true> : fir_kernel<false, false>);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     fn<<<(unsigned)(ntiles * a.C), NT, smem, stream>>>(a, (int)ntiles, ntaps_pad);

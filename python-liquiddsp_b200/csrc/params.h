@@ -122,10 +122,18 @@ struct BamArgs {
     BamP p; DeP de;
 };
 
+enum { FIR_PLAIN = 0, FIR_SSB_LSB, FIR_SSB_USB, FIR_R2C, FIR_C2R };
 struct FirArgs {
     const float2 *x; float2 *y;    // [C][n]
     int C, ch0, Ctot, ntaps;
     int real_io;                   // firfilt_rrrf: x and y are float rows
+    // firhilbf built on the same kernel: separate taps for the two lanes and a combining epilogue
+    int in_real, out_real;         // element types when they differ (real_io sets both)
+    int mode;                      // FIR_PLAIN, FIR_SSB_LSB / FIR_SSB_USB (re + / - im), FIR_R2C, FIR_C2R
+    int delay;                     // firhilbf semi-length m (sign toggles and the r2c end-of-call rule)
+    unsigned long long count;      // absolute index of this call's first sample since reset
+    long long zero_at[4];          // FIR_R2C: local output indices whose in-phase part is forced to zero (-1 = none)
+    const float *taps_q;           // taps of the imaginary lane (nullptr: same as taps)
     long long n;
     float scale;
     const float *taps;             // device [ntaps] in design order h[0..ntaps-1]
