@@ -179,6 +179,19 @@ int lqb_ampmodem_create(float mod_index, int type, int suppressed_carrier, int n
 int lqb_ampmodem_get_taps(lqb_stage s, float *lowpass, int *n_lowpass, float *dcblock, int *n_dcblock);
 int lqb_ampmodem_get_nco_u32(lqb_stage s, uint32_t *theta, uint32_t *d_theta, int n);
 
+/* ---------------- firhilbf : SSBDemod demod.hpp:155-187, HilbertTransform utility.hpp:71-108 -------------
+ * replaces firhilbf_create(m, As) (demod.hpp:163, utility.hpp:79-80) and the per-sample loops over
+ * firhilbf_c2r_execute (demod.hpp:181,184), firhilbf_interp_execute (utility.hpp:93), firhilbf_decim_execute (:101).
+ * SSB_LSB / SSB_USB: complex -> real (SSBDemod, m = 25, As = 60).  C2R: complex -> real, R2C: real -> complex, as
+ * HilbertTransform's two branches produce them, including the overlapping-pair indexing of the reference loops;
+ * the reference's one-element read past the end of the input (R2C) is taken as 0. */
+#define LQB_FIRHILB_SSB_LSB 0
+#define LQB_FIRHILB_SSB_USB 1
+#define LQB_FIRHILB_C2R     2
+#define LQB_FIRHILB_R2C     3
+int lqb_firhilbf_create(int kind, int m, float as, int n_channels, lqb_stage *out);
+int lqb_firhilbf_get_hq(lqb_stage s, float *hq, int *n);
+
 /* ---------------- BroadcastAM : demod.hpp:94-153, wrapper.cpp:259-262 -----------------------------------
  * replaces the per-sample demod_one loop (:124-131): nco_crcf PLL (bw 0.001, arg() detector), firfilt_crcf
  * kaiser(2*slen+1, 0.01, 40 dB), wdelaycf(slen), iirfilt_rrrf cheby2 order-3 high-pass.  complex -> real.

@@ -253,17 +253,30 @@ struct TfStage : lqb_stage_s {
 struct FirStage : lqb_stage_s {
     std::vector<float> h; float scale = 1.f; DevArr<float> taps; DevArr<float2> hist[2]; int cur = 0;
     bool real_io = false;                               // firfilt_rrrf
-    bool in_real() const override { return real_io; }
-    bool out_real() const override { return real_io; }
+    // firhilbf users: the imaginary lane has its own taps and the epilogue combines the lanes (fir.cu)
+    std::vector<float> hlane_q, hq; DevArr<float> taps_q; int mode = FIR_PLAIN, delay = 0; bool in_r = false, out_r = false;
+    unsigned long long count = 0; std::vector<unsigned long long> ends;     // samples since reset; ends of recent calls (R2C)
+    bool in_real() const override { return real_io || in_r; }
+    bool out_real() const override { return real_io || out_r; }
     FirStage(int c) : lqb_stage_s(K_FIR, c) {}
+    void host_reset() override { count = 0; ends.clear(); if (mode == FIR_R2C) ends.push_back(0); }   // the empty window behaves like a call boundary at 0
     int materialize() override
     {
         LQB_TRY(taps.alloc(h.size())); LQB_TRY(taps.upload(h.data(), h.size()));
+        if (!hlane_q.empty()) { LQB_TRY(taps_q.alloc(hlane_q.size())); LQB_TRY(taps_q.upload(hlane_q.data(), hlane_q.size())); }
         for (int k = 0; k < 2; k++) LQB_TRY(hist[k].alloc((size_t)std::max<size_t>(1, h.size() - 1) * C));
         return LQB_OK;
     }
     int clear() override { LQB_TRY(hist[0].zero()); return hist[1].zero(); }
-    void advance(size_t n) override { if (n) cur ^= 1; }
+    void advance(size_t n) override
+    {
+        if (!n) return;
+        cur ^= 1; count += n;
+        if (mode == FIR_R2C) {              // the reference's pairwise read runs one sample past each call (taken as zero)
+            ends.push_back(count);
+            while (!ends.empty() && ends.front() + (unsigned long long)delay - 1 < count) ends.erase(ends.begin());
+        }
+    }
 };
 
 struct ResampStage : lqb_stage_s {
@@ -616,6 +629,18 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         FirArgs a{};
         a.x = (const float2 *)x; a.y = (float2 *)y; a.C = nch; a.ch0 = ch0; a.Ctot = f->C; a.ntaps = (int)f->h.size();
         a.real_io = f->real_io ? 1 : 0;
+        a.in_real = f->in_r ? 1 : 0; a.out_real = f->out_r ? 1 : 0; a.mode = f->mode; a.delay = f->delay; a.count = f->count;
+        a.taps_q = f->hlane_q.empty() ? nullptr : f->taps_q.p;
+        for (int k = 0; k < 4; k++) a.zero_at[k] = -1;
+        if (f->mode == FIR_R2C) {
+            int nz = 0;
+            for (unsigned long long e : f->ends) {
+                const unsigned long long kabs = e + (unsigned long long)f->delay - 1;
+                if (kabs < f->count || kabs >= f->count + n) continue;
+                if (nz == 4) return fail(LQB_ENOTIMPL, "HilbertTransform: more than 4 call boundaries within one filter delay");
+                a.zero_at[nz++] = (long long)(kabs - f->count);
+            }
+        }
         a.n = (long long)n; a.scale = f->scale; a.taps = f->taps.p; a.hist_in = f->hist[f->cur].p; a.hist_out = f->hist[f->cur ^ 1].p;
         LQB_CUDA(fir_launch(a, stream));
         return LQB_OK;
@@ -938,6 +963,44 @@ int lqb_deemph_freqresponse(lqb_stage s, float fc, lqb_cf *H)
     const design::cplx e1 = std::polar(1.0f, (float)(-2 * design::kPi * fc));
     const design::cplx h = design::cplx(q->b0, 0.f) / (design::cplx(1.f, 0.f) + q->a1 * e1);
     H->re = h.real(); H->im = h.imag(); return LQB_OK;
+}
+
+// ---- firhilbf users
+int lqb_firhilbf_create(int kind, int m, float as, int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    std::vector<float> hq;
+    if (!out || kind < LQB_FIRHILB_SSB_LSB || kind > LQB_FIRHILB_R2C) return fail(LQB_EINVAL, "firhilbf: unknown kind %d", kind);
+    if (m < 2 || 4 * m > kFirMaxTaps || !design::firhilb_hq((unsigned)m, as, hq)) return fail(LQB_EINVAL, "firhilbf: m must be in 2..%d", kFirMaxTaps / 4);
+    FirStage *q = new FirStage(C);
+    q->hq = hq; q->delay = m;
+    // tap index = delay in samples.  in-phase lane: a pure delay; quadrature lane: hq[i] meets the sample 2m-1-i pushes old
+    if (kind == LQB_FIRHILB_SSB_LSB || kind == LQB_FIRHILB_SSB_USB) {
+        // c2r_execute alternates between two window pairs: both lanes see every second sample
+        q->h.assign((size_t)4 * m, 0.f); q->hlane_q.assign((size_t)4 * m, 0.f);
+        q->h[(size_t)2 * m] = 1.f;
+        for (int i = 0; i < 2 * m; i++) q->hlane_q[(size_t)(4 * m - 1 - 2 * i)] = hq[(size_t)i];
+        q->mode = kind == LQB_FIRHILB_SSB_USB ? FIR_SSB_USB : FIR_SSB_LSB; q->out_r = true;
+    } else if (kind == LQB_FIRHILB_R2C) {
+        // decim_execute on overlapping pairs: quadrature filter on z[n], in-phase delay on z[n+1]
+        q->h.assign((size_t)2 * m, 0.f); q->hlane_q.assign((size_t)2 * m, 0.f);
+        q->h[(size_t)m - 1] = 1.f;
+        for (int i = 0; i < 2 * m; i++) q->hlane_q[(size_t)(2 * m - 1 - i)] = hq[(size_t)i];
+        q->mode = FIR_R2C; q->in_r = true; q->host_reset();
+    } else {
+        // interp_execute with overlapping writes: only the delayed imaginary part survives, sign alternating
+        q->h.assign((size_t)m + 1, 0.f); q->hlane_q.assign((size_t)m + 1, 0.f);
+        q->hlane_q[(size_t)m] = 1.f;
+        q->mode = FIR_C2R; q->out_r = true;
+    }
+    *out = q; return LQB_OK;
+}
+int lqb_firhilbf_get_hq(lqb_stage s, float *hq, int *n)
+{
+    LQB_GET(FirStage, q, s, K_FIR);
+    if (hq) std::copy(q->hq.begin(), q->hq.end(), hq);
+    if (n) *n = (int)q->hq.size();
+    return LQB_OK;
 }
 
 // ---- iirfilt, transfer-function form

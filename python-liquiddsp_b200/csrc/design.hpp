@@ -107,6 +107,23 @@ struct ResampDesign {
     std::vector<float> bank;   // [npfb][sublen], each sub-filter reversed (oldest sample first)
 };
 
+// firhilbf_create(m, As): quadrature-branch taps.  Half-band Kaiser prototype of 4m+1 taps times sin(pi t / 2); the
+// 2m taps at odd offsets, in reverse order (liquid firhilb.proto.c)
+inline bool firhilb_hq(unsigned m, float as, std::vector<float> &hq)
+{
+    if (m < 2) return false;
+    const unsigned h_len = 4 * m + 1;
+    std::vector<float> h;
+    if (!firdes_kaiser(h_len, 0.25f, std::fabs(as), 0.0f, h)) return false;
+    for (unsigned i = 0; i < h_len; i++) {
+        const float t = (float)i - (float)(h_len - 1) / 2.0f;
+        h[i] = h[i] * std::sin((float)(0.5f * kPi * t));
+    }
+    hq.clear();
+    for (unsigned i = 1; i < h_len; i += 2) hq.push_back(h[h_len - i - 1]);
+    return true;
+}
+
 inline unsigned nextpow2(unsigned x) { x--; unsigned n = 0; while (x > 0) { x >>= 1; n++; } return n; }
 
 inline uint32_t resamp_step(float rate) { return (uint32_t)std::round((float)(1 << 24) / rate); }

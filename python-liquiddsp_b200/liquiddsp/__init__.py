@@ -81,6 +81,7 @@ _SIG = {
     "lqb_ampmodem_create": [_F, _I, _I, _I, _PP], "lqb_ampmodem_get_taps": [_P, _P, C.POINTER(_I), _P, C.POINTER(_I)],
     "lqb_ampmodem_get_nco_u32": [_P, _P, _P, _I],
     "lqb_freqdem_create": [_F, _I, _PP],
+    "lqb_firhilbf_create": [_I, _I, _F, _I, _PP], "lqb_firhilbf_get_hq": [_P, _P, C.POINTER(_I)],
     "lqb_broadcast_am_create": [_I, _I, _PP], "lqb_broadcast_am_get_design": [_P, _P, C.POINTER(_I), _P, _P],
     "lqb_broadcast_am_get_nco_u32": [_P, _P, _P, _I],
     "lqb_chain_create": [_PP], "lqb_chain_append": [_P, _P], "lqb_chain_destroy": [_P],
@@ -506,6 +507,47 @@ class FreqDem(_Stage):
 
     def print(self):
         print("freqdem [kf %g]" % self.kd)
+
+
+class SSBDemod(_Stage):
+    """wrapper.cpp:269-272 / demod.hpp:155-187: firhilbf(25, 60 dB); band == "usb" keeps the upper side-band, anything
+    else the lower one."""
+    _out_dtype = np.float32
+
+    def __init__(self, band, channels=1):
+        super().__init__()
+        self.usb = band == "usb"
+        _ck(_lib.lqb_firhilbf_create(1 if self.usb else 0, 25, 60.0, channels, C.byref(self._h)))
+
+    def hq(self):
+        h = np.zeros(1024, np.float32); n = _I(); _ck(_lib.lqb_firhilbf_get_hq(self._h, _ptr(h), C.byref(n))); return h[:n.value].copy()
+
+
+class _HilbertBranch(_Stage):
+    def __init__(self, kind, m, As, channels):
+        super().__init__()
+        self._in_dtype, self._out_dtype = (np.complex64, np.float32) if kind == 2 else (np.float32, np.complex64)
+        _ck(_lib.lqb_firhilbf_create(kind, int(m), As, channels, C.byref(self._h)))
+
+
+class HilbertTransform:
+    """wrapper.cpp:174-176 / utility.hpp:71-108: two firhilbf objects; complex64 input -> float32 (interp branch),
+    float32 input -> complex64 (decim branch), any other dtype -> None.  The element-wise loops of the reference
+    (overlapping pairs) are reproduced; its one-element overrun of the input is read as zero."""
+
+    def __init__(self, m=5, As=60.0, channels=1):
+        self._c2r, self._r2c = _HilbertBranch(2, m, As, channels), _HilbertBranch(3, m, As, channels)
+
+    def reset(self):
+        self._c2r.reset(); self._r2c.reset()
+
+    def __call__(self, x):
+        x = np.asarray(x)
+        if x.dtype == np.complex64:
+            return self._c2r(x)
+        if x.dtype == np.float32:
+            return self._r2c(x)
+        return None
 
 
 class BroadcastAM(_Stage):

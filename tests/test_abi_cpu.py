@@ -63,7 +63,12 @@ def test_reference_api_surface():
     for cls in (L.CBandpassIIR, L.CBandstopIIR, L.RBandpassIIR, L.RBandstopIIR):
         assert sig(cls) == dict(filter_type="butter", order=2, Fc=0.2, F0=0.3, Ap=0.5, As=20.0)
     assert sig(L.CIIRFilter) == sig(L.RIIRFilter) == dict(Bc=inspect._empty, Ac=inspect._empty)
-    assert sig(L.BroadcastAM) == dict(slen=25)
+    assert sig(L.BroadcastAM) == dict(slen=25) and sig(L.SSBDemod) == dict(band=inspect._empty)
+    assert sig(L.HilbertTransform) == dict(m=5, As=60.0)
+    assert np.array_equal(L.SSBDemod("usb").hq(), O.SSBDemod("usb").hq()) and L.SSBDemod("anything").usb is False
+    assert L.HilbertTransform()(np.zeros(4, np.float64)) is None          # utility.hpp:104: other dtypes -> None
+    with pytest.raises(ValueError):
+        L.HilbertTransform(m=1)
     assert sig(L.RealDCBlocker) == dict(slen=25, As=20.0)
     assert sig(L.RealKaiserBessel) == dict(flen=25, Fc=0.25, As=20.0, offset=0.0)
     assert L.CBandpassIIR.__name__ == "CBandpassIIR" and L.RLowpassIIR("cheby1", 4, 0.1).band_type == "lowpass"

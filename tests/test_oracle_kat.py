@@ -293,3 +293,23 @@ def test_broadcast_am_recovers_the_modulation():
     tail = y[-24000:]
     ref = audio[-24000 - 25:-25]                           # signal branch is delayed by m = 25
     assert abs(np.mean(tail)) < 0.02 and rel_l2(tail, ref) < 0.08      # the 20 Hz high-pass leads by ~3 degrees at 1 kHz
+
+
+def test_firhilbf_sideband_selection_and_analytic_signal():
+    """SSBDemod (demod.hpp:155-187): a tone above the carrier comes out of "usb" at twice its amplitude and is
+    suppressed by > 70 dB in "lsb"; firhilbf_r2c turns a real tone into its analytic signal at half rate."""
+    fs, n = 48000.0, 8000
+    t = np.arange(n) / fs
+    up = np.exp(2j * np.pi * 1500 * t).astype(np.complex64)
+    rms = lambda v: float(np.sqrt(np.mean(np.asarray(v, np.float64) ** 2)))
+    for band, other in (("usb", "lsb"), ("lsb", "usb")):
+        tone = up if band == "usb" else up.conj()
+        assert abs(rms(O.SSBDemod(band)(tone)[500:]) - np.sqrt(2)) < 1e-3
+        assert rms(O.SSBDemod(other)(tone)[500:]) < 2 * 10 ** (-70 / 20)
+    hq = O.SSBDemod("usb").hq()
+    assert hq.size == 50 and np.allclose(hq, -hq[::-1], atol=1e-7)        # antisymmetric quadrature filter
+    # HilbertTransform's complex64 branch keeps only the delayed imaginary part with alternating sign (utility.hpp:93)
+    z = (np.arange(40) + 1j * (np.arange(40) + 100)).astype(np.complex64)
+    y = O.HilbertTransform(5, 60.0)(z)
+    k = np.arange(5, 40)
+    assert np.all(y[:5] == 0) and np.array_equal(y[5:], ((-1.0) ** (k - 5) * (k - 5 + 100)).astype(np.float32))

@@ -228,6 +228,39 @@ def test_real_chain_am_dcblock_lowpass(cuda):
     assert rel_l2(chain(x), olp(odc(oam(x)))) <= TOL_E2E
 
 
+# ------------------------------------------------------------------------- 8f row 3: SSBDemod, HilbertTransform
+@pytest.mark.parametrize("band", ["usb", "lsb"])
+def test_ssb_demod(cuda, band):
+    rng = np.random.default_rng(51)
+    C, n = 3, 10000
+    x = crandn(rng, C, n)
+    g = L.SSBDemod(band, channels=C)
+    y = np.concatenate([g(x[:, s:e]) for s, e in split_points(n, 5, rng)], axis=1)      # odd / even cut points: toggle carried
+    assert y.dtype == np.float32
+    for c in range(C):
+        assert rel_l2(y[c], O.SSBDemod(band)(x[c])) <= TOL_STAGE
+    g.reset()
+    assert rel_l2(g(x[:, :333])[1], O.SSBDemod(band)(x[1, :333])) <= TOL_STAGE
+    one = L.SSBDemod(band)
+    assert rel_l2(one(x[0]), O.SSBDemod(band)(x[0])) <= TOL_STAGE
+
+
+@pytest.mark.parametrize("m", [5, 2, 25])
+def test_hilbert_transform_both_branches(cuda, m):
+    rng = np.random.default_rng(52)
+    n = 4001
+    g, o = L.HilbertTransform(m, 60.0), O.HilbertTransform(m, 60.0)
+    z = crandn(rng, n)
+    cuts = [(0, 1), (1, 3), (3, 4), (4, 1200), (1200, 1201), (1201, n)]                 # calls shorter than the filter delay too
+    yc = np.concatenate([g(z[s:e]) for s, e in cuts]); yco = np.concatenate([o(z[s:e]) for s, e in cuts])
+    assert yc.dtype == np.float32 and np.array_equal(yc, yco)                           # delay and sign only: exact
+    r = rng.standard_normal(n).astype(np.float32)
+    yr = np.concatenate([g(r[s:e]) for s, e in cuts]); yro = np.concatenate([o(r[s:e]) for s, e in cuts])
+    assert yr.dtype == np.complex64 and rel_l2(yr, yro) <= TOL_STAGE
+    assert np.array_equal(yr.real, yro.real)                                            # in-phase branch: pure delay, sign, end-of-call zero
+    assert g(np.zeros(8)) is None
+
+
 # ------------------------------------------------------------------------- 8f row 3: BroadcastAM
 def _bits_or_close(y, yo, tol=TOL_STAGE):
     """The PLL branch takes arg() through a double-precision atan2 on both sides; the two math libraries agree after
