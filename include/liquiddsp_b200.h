@@ -125,6 +125,16 @@ int lqb_firfilt_crcf_freqresponse(lqb_stage s, float fc, lqb_cf *H);
  * resamp_cccf_execute loop (:164-166).  complex in -> complex out, *n_out samples per channel
  * (all channels share rate and phase, so the batched output is rectangular). */
 int lqb_resamp_create(float rate, int m, float fc, float as, int npfb, int n_channels, lqb_stage *out);
+/* resamp_crcf / resamp_rrrf : CResampler resampler.hpp:38-70, RResampler :4-36 (create_default + execute_block),
+ * RealResampler :72-125 (resamp_rrrf_create, per-sample execute loop :104-107).  Real taps: fused multiply-add chain.
+ * create_default: m = 7, fc = min(0.49, rate/2), As = 60 dB, npfb = 64.  set_rate / get_state / get_bank apply. */
+int lqb_resamp_crcf_create(float rate, int m, float fc, float as, int npfb, int n_channels, lqb_stage *out);
+int lqb_resamp_rrrf_create(float rate, int m, float fc, float as, int npfb, int n_channels, lqb_stage *out);
+int lqb_resamp_crcf_create_default(float rate, int n_channels, lqb_stage *out);
+int lqb_resamp_rrrf_create_default(float rate, int n_channels, lqb_stage *out);
+/* wdelayf / wdelaycf : Delay utility.hpp:5-59 (read, then push: y[k] = x[k - (delay + 1)]).  real_samples selects
+ * float rows (wdelayf) or complex64 rows (wdelaycf). */
+int lqb_wdelay_create(int delay, int real_samples, int n_channels, lqb_stage *out);
 int lqb_resamp_set_rate(lqb_stage s, float rate);
 int lqb_resamp_get_state(lqb_stage s, uint32_t *step, uint32_t *phase);     /* 8.24 fixed point */
 int lqb_resamp_get_bank(lqb_stage s, float *bank, int *npfb, int *sublen);  /* [npfb][sublen] as firpfb stores it */

@@ -699,6 +699,7 @@ struct orc_resamp_s {
     uint32_t step, phase;
     float *bank;            /* [npfb][sublen] reversed sub-filters (real part; imaginary part is 0) */
     float *wr, *wi; unsigned w;
+    int real_taps;          /* 0: resamp_cccf arithmetic, 1: resamp_crcf / resamp_rrrf */
 };
 
 static unsigned nextpow2(unsigned x) { x--; unsigned n = 0; while (x > 0) { x >>= 1; n++; } return n; }
@@ -757,10 +758,15 @@ void orc_resamp_execute(orc_resamp q, orc_cf x, orc_cf *y, unsigned *nw)
         const float *h = q->bank + idx * q->sublen, *r = q->wr + q->w, *im = q->wi + q->w;
         /* dotprod_cccf_run with taps (h + 0j): prod = (fma(hr,xr,-(0*xi)), fma(hr,xi,0*xr)); r += prod */
         float sr = 0.0f, si = 0.0f;
-        for (unsigned i = 0; i < q->sublen; i++) {
-            float pr = FMA(h[i], r[i], -(0.0f * im[i]));
-            float pi = FMA(h[i], im[i], 0.0f * r[i]);
-            sr = sr + pr; si = si + pi;
+        if (q->real_taps) {
+            /* resamp_crcf / resamp_rrrf: dotprod_crcf / dotprod_rrrf, a fused multiply-add chain per lane */
+            for (unsigned i = 0; i < q->sublen; i++) { sr = FMA(h[i], r[i], sr); si = FMA(h[i], im[i], si); }
+        } else {
+            for (unsigned i = 0; i < q->sublen; i++) {
+                float pr = FMA(h[i], r[i], -(0.0f * im[i]));
+                float pi = FMA(h[i], im[i], 0.0f * r[i]);
+                sr = sr + pr; si = si + pi;
+            }
         }
         y[n].re = sr; y[n].im = si; n++;
         q->phase += q->step;
@@ -769,6 +775,15 @@ void orc_resamp_execute(orc_resamp q, orc_cf x, orc_cf *y, unsigned *nw)
     *nw = n;
 }
 
+/* resamp_crcf / resamp_rrrf arithmetic (CResampler, RResampler, RealResampler: resampler.hpp:4-125); real samples
+ * run in the real lane.  create_default: m = 7, fc = min(0.49, rate/2), As = 60 dB, npfb = 64. */
+void orc_resamp_set_real_taps(orc_resamp q, int on) { q->real_taps = on; }
+orc_resamp orc_resamp_create_default(float rate)
+{
+    orc_resamp q = orc_resamp_create(rate, 7, 0.5f * rate > 0.49f ? 0.49f : 0.5f * rate, 60.0f, 64);
+    if (q) q->real_taps = 1;
+    return q;
+}
 unsigned orc_resamp_execute_block(orc_resamp q, const orc_cf *x, unsigned n, orc_cf *y)
 {
     unsigned nw = 0, nd = 0;

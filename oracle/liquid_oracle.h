@@ -114,6 +114,8 @@ unsigned orc_resamp_get_sublen(orc_resamp q);
 void  orc_resamp_get_bank(orc_resamp q, float *out);
 void  orc_resamp_execute(orc_resamp q, orc_cf x, orc_cf *y, unsigned *nw);
 /* reference wrapper loop: ComplexResampler::execute, resampler.hpp:160-172 */
+void  orc_resamp_set_real_taps(orc_resamp q, int on);   /* resamp_crcf / resamp_rrrf dot product */
+orc_resamp orc_resamp_create_default(float rate);       /* resamp_crcf_create_default / resamp_rrrf_create_default */
 unsigned orc_resamp_execute_block(orc_resamp q, const orc_cf *x, unsigned n, orc_cf *y);
 
 /* ---- nco_crcf ---- */

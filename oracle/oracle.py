@@ -99,6 +99,7 @@ def _load(name="liboracle.so"):
         "orc_firhilbf_create": (P, [U, F]), "orc_firhilbf_destroy": (None, [P]), "orc_firhilbf_reset": (None, [P]),
         "orc_firhilbf_get_hq": (U, [P, P]), "orc_wrap_ssb_execute": (None, [P, I, P, U, P]),
         "orc_wrap_hilbert_c2r": (None, [P, P, U, P]), "orc_wrap_hilbert_r2c": (None, [P, P, U, P]),
+        "orc_resamp_set_real_taps": (None, [P, I]), "orc_resamp_create_default": (P, [F]),
         "orc_wrap_bam_create": (P, [I]), "orc_wrap_bam_destroy": (None, [P]), "orc_wrap_bam_reset": (None, [P]),
         "orc_wrap_bam_get_nco": (None, [P, P, P]), "orc_wrap_bam_get_design": (U, [P, P, P, P]),
         "orc_wrap_bam_execute": (None, [P, P, U, P]), "orc_wrap_bam_set_dcblock": (None, [P, P, P, U]),
@@ -389,6 +390,62 @@ class ComplexResampler:
         nw = lib.orc_resamp_execute_block(self._q, _p(x), x.shape[0], _p(y))
         assert nw <= cap
         return y[:nw].copy()
+
+
+class CResampler(ComplexResampler):
+    """wrapper.cpp:20-23, resampler.hpp:38-70: resamp_crcf_create_default(rate) + execute_block."""
+
+    def __init__(self, rate):
+        self._rate = rate
+        self._q = lib.orc_resamp_create_default(rate)
+        if not self._q:
+            raise ValueError("resamp create failed")
+
+
+class RResampler(CResampler):
+    """wrapper.cpp:15-18, resampler.hpp:4-36: the same on float samples (resamp_rrrf)."""
+
+    def __call__(self, x):
+        return np.ascontiguousarray(ComplexResampler.__call__(self, _f32(x).astype(_cf)).real)
+
+
+class RealResampler(ComplexResampler):
+    """wrapper.cpp:214-219, resampler.hpp:72-125: resamp_rrrf_create(rate, len, Fc, As, nfilter), per-sample loop."""
+
+    def __init__(self, rate, len=20, Fc=None, As=60.0, nfilter=13):
+        ComplexResampler.__init__(self, rate, len, Fc, As, nfilter)
+        lib.orc_resamp_set_real_taps(self._q, 1)
+
+    def __call__(self, x):
+        return np.ascontiguousarray(ComplexResampler.__call__(self, _f32(x).astype(_cf)).real)
+
+
+class Delay:
+    """wrapper.cpp:25-28, utility.hpp:5-59: wdelay read-then-push, separate float and complex lines; the property
+    setter rebuilds (and so clears) both."""
+
+    def __init__(self, nd=1):
+        self.delay = nd
+
+    @property
+    def delay(self):
+        return self._nd
+
+    @delay.setter
+    def delay(self, nd):
+        self._nd = int(nd)
+        self._buf = {np.dtype(np.float32): np.zeros(self._nd + 1, _f), np.dtype(np.complex64): np.zeros(self._nd + 1, _cf)}
+        self._ri = {k: 0 for k in self._buf}
+
+    def __call__(self, x):
+        x = np.asarray(x)
+        if x.dtype not in self._buf:
+            return None
+        v, ri, y = self._buf[x.dtype], self._ri[x.dtype], np.empty_like(x)
+        for n in range(x.shape[0]):                     # wdelay_read, then wdelay_push (wdelay.proto.c)
+            y[n] = v[ri]; v[ri] = x[n]; ri = (ri + 1) % (self._nd + 1)
+        self._ri[x.dtype] = ri
+        return y
 
 
 class NCO:

@@ -138,7 +138,7 @@ static bool make_input_tmap(CUtensorMap *tm, const void *x, size_t n, size_t row
 }
 
 // ------------------------------------------------------------------------------------ stages
-enum Kind { K_NCO = 0, K_IIR, K_RESAMP, K_AGC, K_AM, K_FM, K_DEEMPH, K_FIR, K_TF, K_BAM };
+enum Kind { K_NCO = 0, K_IIR, K_RESAMP, K_AGC, K_AM, K_FM, K_DEEMPH, K_FIR, K_TF, K_BAM, K_DELAY };
 
 }  // namespace lqb
 
@@ -279,7 +279,21 @@ struct FirStage : lqb_stage_s {
     }
 };
 
+// wdelayf / wdelaycf as the reference's Delay uses them (read, then push): y[k] = x[k - (nd + 1)]
+struct DelayStage : lqb_stage_s {
+    long long D = 1; bool real_io = false; int cur = 0; DevArr<float2> hist[2];      // float2 slots also when real
+    DelayStage(int c) : lqb_stage_s(K_DELAY, c) {}
+    bool in_real() const override { return real_io; }
+    bool out_real() const override { return real_io; }
+    int materialize() override { for (int k = 0; k < 2; k++) LQB_TRY(hist[k].alloc((size_t)D * C)); return LQB_OK; }
+    int clear() override { LQB_TRY(hist[0].zero()); return hist[1].zero(); }
+    void advance(size_t n) override { if (n) cur ^= 1; }
+};
+
 struct ResampStage : lqb_stage_s {
+    int variant = 0;                                    // 0 cccf (ComplexResampler), 1 crcf (CResampler), 2 rrrf (RResampler, RealResampler)
+    bool in_real() const override { return variant == 2; }
+    bool out_real() const override { return variant == 2; }
     float rate = 1.f; design::ResampDesign d; uint32_t step = 0, phase = 0, count = 0;
     DevArr<float> bank; DevArr<float2> ring;            // ring [sublen][C]
     ResampStage(int c) : lqb_stage_s(K_RESAMP, c) {}
@@ -295,7 +309,7 @@ struct ResampStage : lqb_stage_s {
     bool decimating() const
     {
         const uint64_t lo = (uint64_t)std::max<unsigned>(d.sublen, kSeqTS) << 24;
-        return (uint64_t)step >= lo && (uint64_t)step < (1ull << 32) - (1ull << 28) && d.sublen <= (unsigned)kMaxResampSub;
+        return variant == 0 && (uint64_t)step >= lo && (uint64_t)step < (1ull << 32) - (1ull << 28) && d.sublen <= (unsigned)kMaxResampSub;
     }
     size_t out_len(size_t n) const override
     {
@@ -312,7 +326,7 @@ struct ResampStage : lqb_stage_s {
     void fill(ResampP &p) const
     {
         p.step = step; p.phase = phase; p.bits = (int)d.bits; p.sublen = (int)d.sublen; p.npfb = (int)d.npfb;
-        p.bank = bank.p; p.ring = ring.p; p.count = count;
+        p.bank = bank.p; p.ring = ring.p; p.count = count; p.variant = variant;
     }
 };
 
@@ -426,7 +440,7 @@ constexpr int kParChannels = 16384;
 
 // ------------------------------------------------------------------------------------ chain
 struct Segment {
-    enum Type { SEQ, FIR, RESAMP_PAR, AMTAIL, NCO_PAR, BAM } type = SEQ;
+    enum Type { SEQ, FIR, RESAMP_PAR, AMTAIL, NCO_PAR, BAM, DELAY } type = SEQ;
     unsigned mask = 0; int nsos = 0, sos0 = 0;
     std::vector<lqb_stage_s *> st;
     std::string name;
@@ -464,7 +478,7 @@ static const char *kind_name(Kind k)
 {
     switch (k) {
     case K_NCO: return "nco"; case K_IIR: return "iir"; case K_RESAMP: return "resamp"; case K_AGC: return "agc";
-    case K_AM: return "ampmodem"; case K_FM: return "freqdem"; case K_DEEMPH: return "deemph"; case K_FIR: return "fir"; case K_TF: return "tf"; case K_BAM: return "broadcast_am";
+    case K_AM: return "ampmodem"; case K_FM: return "freqdem"; case K_DEEMPH: return "deemph"; case K_FIR: return "fir"; case K_TF: return "tf"; case K_BAM: return "broadcast_am"; case K_DELAY: return "delay";
     }
     return "?";
 }
@@ -521,6 +535,10 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
     for (size_t i = 0; i < st.size();) {
         Segment g;
         if (st[i]->kind == K_FIR) { g.type = Segment::FIR; g.st = { st[i] }; g.name = "fir"; segs.push_back(g); i++; continue; }
+        if (st[i]->kind == K_DELAY) { g.type = Segment::DELAY; g.st = { st[i] }; g.name = "delay"; segs.push_back(g); i++; continue; }
+        if (st[i]->kind == K_RESAMP && static_cast<ResampStage *>(st[i])->variant != 0) {      // real-tap resamplers: time-parallel kernel
+            g.type = Segment::RESAMP_PAR; g.st = { st[i] }; g.name = "par[resamp]"; segs.push_back(g); i++; continue;
+        }
         // [AGC ->] BroadcastAM [-> de-emphasis] (bam.cu).  The gain loop joins only behind a decimating kernel: it then
         // runs in place on the time-major hand-off buffer
         {
@@ -605,6 +623,12 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         *launches += amtail_launch_count(has_agc, a) - 1;
         return LQB_OK;
     }
+    if (g.type == Segment::DELAY) {
+        const DelayStage *d = static_cast<const DelayStage *>(first);
+        // histories are float2-slotted arrays; a real delay line uses them as float rows of the same length
+        LQB_CUDA(delay_launch(d->real_io, x, y, d->hist[d->cur].p, d->hist[d->cur ^ 1].p, nch, ch0, (long long)n, d->D, stream));
+        return LQB_OK;
+    }
     if (g.type == Segment::BAM) {
         BamArgs a{};
         a.x = (const float2 *)x; a.y = (float *)y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.in_tmajor = in_tmajor ? 1 : 0;
@@ -650,7 +674,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         ResampP p{}; r->fill(p);
         NcoP q{}; const bool has_nco = g.st.size() == 2;
         if (has_nco) LQB_TRY(static_cast<NcoStage *>(g.st.front())->fill(q));
-        LQB_CUDA(resamp_par_launch(p, has_nco ? &q : nullptr, (const float2 *)x, (float2 *)y, nch, ch0, r->C, (long long)n, (long long)n_out, stream));
+        LQB_CUDA(resamp_par_launch(p, has_nco ? &q : nullptr, x, y, nch, ch0, r->C, (long long)n, (long long)n_out, stream));
         *launches += resamp_par_launch_count(has_nco, (long long)n_out) - 1;
         return LQB_OK;
     }
@@ -1085,6 +1109,31 @@ int lqb_resamp_create(float rate, int m, float fc, float as, int npfb, int C, lq
     ResampStage *q = new ResampStage(C);
     if (!design::resamp_design((unsigned)m, fc, as, (unsigned)npfb, q->d)) { delete q; return fail(LQB_EINVAL, "resamp: invalid prototype (fc %g, As %g)", fc, as); }
     q->rate = rate; q->step = design::resamp_step(rate);
+    *out = q; return LQB_OK;
+}
+static int resamp_variant(int variant, float rate, int m, float fc, float as, int npfb, int C, lqb_stage *out)
+{
+    LQB_TRY(lqb_resamp_create(rate, m, fc, as, npfb, C, out));
+    static_cast<ResampStage *>(*out)->variant = variant;
+    return LQB_OK;
+}
+int lqb_resamp_crcf_create(float rate, int m, float fc, float as, int npfb, int C, lqb_stage *out) { return resamp_variant(1, rate, m, fc, as, npfb, C, out); }
+int lqb_resamp_rrrf_create(float rate, int m, float fc, float as, int npfb, int C, lqb_stage *out) { return resamp_variant(2, rate, m, fc, as, npfb, C, out); }
+// resamp_*_create_default: m = 7, fc = min(0.49, rate / 2), As = 60 dB, 64 filters
+int lqb_resamp_crcf_create_default(float rate, int C, lqb_stage *out)
+{
+    return resamp_variant(1, rate, 7, 0.5f * rate > 0.49f ? 0.49f : 0.5f * rate, 60.0f, 64, C, out);
+}
+int lqb_resamp_rrrf_create_default(float rate, int C, lqb_stage *out)
+{
+    return resamp_variant(2, rate, 7, 0.5f * rate > 0.49f ? 0.49f : 0.5f * rate, 60.0f, 64, C, out);
+}
+int lqb_wdelay_create(int delay, int real_samples, int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!out || delay < 0 || delay > (1 << 24)) return fail(LQB_EINVAL, "wdelay: delay must be in 0..2^24");
+    DelayStage *q = new DelayStage(C);
+    q->D = (long long)delay + 1; q->real_io = real_samples != 0;
     *out = q; return LQB_OK;
 }
 int lqb_resamp_set_rate(lqb_stage s, float rate)

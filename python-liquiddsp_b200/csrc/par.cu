@@ -35,13 +35,25 @@ __device__ __forceinline__ float2 nco_at(const NcoP &q, const float2 *tab, uint3
     return sc;
 }
 
-template <bool HAS_NCO>
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(gsrc) : "memory");
+}
+
+// VAR 0: resamp_cccf (ComplexResampler) -- complex taps: each product rounded, then added
+// VAR 1: resamp_crcf (CResampler)       -- real taps on complex samples: fused multiply-add chain per lane
+// VAR 2: resamp_rrrf (RResampler, RealResampler) -- the same on real samples (float rows in and out)
+template <bool HAS_NCO, int VAR>
 __global__ void __launch_bounds__(NT)
-resamp_par_kernel(const ResampP p, const NcoP q, const float2 *__restrict__ x, float2 *__restrict__ y, int ch0, int Ctot,
+resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, void *__restrict__ yv, int ch0, int Ctot,
                   long long n, long long n_out, int KT, int ntiles, int span_max)
 {
+    constexpr bool REAL = VAR == 2;
+    static_assert(!(REAL && HAS_NCO), "the mixer runs on complex samples");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *s_x = (float2 *)smem_raw;                   // span_max samples
+    float2 *s_x = (float2 *)smem_raw;                   // span_max samples (float2 slots also when the samples are real)
+    float  *s_xr = (float *)smem_raw;
     float  *s_b = (float *)(s_x + span_max);            // bank [npfb][sublen]
     float2 *s_t = (float2 *)(s_b + ((p.npfb * p.sublen + 3) & ~3));   // oscillator table (HAS_NCO)
     const int tid = threadIdx.x, L = p.sublen;
@@ -52,15 +64,22 @@ resamp_par_kernel(const ResampP p, const NcoP q, const float2 *__restrict__ x, f
     const unsigned long long P1 = (unsigned long long)p.phase + (unsigned long long)(k0 + nk - 1) * p.step;
     const long long i_lo = (long long)(P0 >> 24) - (L - 1), i_hi = (long long)(P1 >> 24);
     const int span = (int)(i_hi - i_lo + 1);
-    const float2 *xrow = x + ch * n;
+    const float2 *xrow = (const float2 *)xv + ch * n;
+    const float *xrow_r = (const float *)xv + ch * n;
     const long long gch = ch0 + ch;
 
     for (int i = tid; i < p.npfb * L; i += NT) s_b[i] = p.bank[i];
     for (int i = tid; i < span; i += NT) {
         const long long g = i_lo + i;
-        if (g >= 0) cp_async8(&s_x[i], xrow + g);
-        else if (g >= -(long long)L) s_x[i] = p.ring[(long long)(((long long)p.count + g + 4LL * L) % L) * Ctot + gch];
-        else s_x[i] = make_float2(0.f, 0.f);
+        if (REAL) {
+            if (g >= 0) cp_async4(&s_xr[i], xrow_r + g);
+            else if (g >= -(long long)L) s_xr[i] = p.ring[(long long)(((long long)p.count + g + 4LL * L) % L) * Ctot + gch].x;
+            else s_xr[i] = 0.f;
+        } else {
+            if (g >= 0) cp_async8(&s_x[i], xrow + g);
+            else if (g >= -(long long)L) s_x[i] = p.ring[(long long)(((long long)p.count + g + 4LL * L) % L) * Ctot + gch];
+            else s_x[i] = make_float2(0.f, 0.f);
+        }
     }
     if (HAS_NCO) for (int i = tid; i < 1024; i += NT) s_t[i] = q.sincos[i];
     cp_async_commit(); cp_async_wait<0>();
@@ -84,23 +103,30 @@ resamp_par_kernel(const ResampP p, const NcoP q, const float2 *__restrict__ x, f
         // dotprod_cccf order and rounding: product rounded, then added, oldest sample first (scalar intrinsics:
         // ptxas contracts a packed mul.f32x2 + add.f32x2 pair into FFMA2 even with .rn)
         float ar = 0.f, ai = 0.f;
-        for (int i = 0; i < L; i++) {
-            const float2 w = s_x[off + i];
-            ar = __fadd_rn(ar, __fmul_rn(h[i], w.x)); ai = __fadd_rn(ai, __fmul_rn(h[i], w.y));
+        if (VAR == 0) {
+            for (int i = 0; i < L; i++) {
+                const float2 w = s_x[off + i];
+                ar = __fadd_rn(ar, __fmul_rn(h[i], w.x)); ai = __fadd_rn(ai, __fmul_rn(h[i], w.y));
+            }
+        } else if (VAR == 1) {
+            for (int i = 0; i < L; i++) { const float2 w = s_x[off + i]; ar = __fmaf_rn(h[i], w.x, ar); ai = __fmaf_rn(h[i], w.y, ai); }
+        } else {
+            for (int i = 0; i < L; i++) ar = __fmaf_rn(h[i], s_xr[off + i], ar);
         }
-        y[ch * n_out + k0 + tid] = make_float2(ar, ai);
+        if (REAL) ((float *)yv)[ch * n_out + k0 + tid] = ar;
+        else ((float2 *)yv)[ch * n_out + k0 + tid] = make_float2(ar, ai);
     }
 }
 
 // the newest min(n, sublen) inputs of the call go into the history ring
-template <bool HAS_NCO>
-__global__ void ring_update_kernel(const ResampP p, const NcoP q, const float2 *__restrict__ x, int nch, int ch0, int Ctot, long long n)
+template <bool HAS_NCO, bool REAL>
+__global__ void ring_update_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, int nch, int ch0, int Ctot, long long n)
 {
     const int L = p.sublen;
     const long long first = n > L ? n - L : 0, cnt = n - first;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cnt * nch; i += (long long)gridDim.x * blockDim.x) {
         const long long j = first + i / nch, ch = i % nch;
-        float2 v = x[ch * n + j];
+        float2 v = REAL ? make_float2(((const float *)xv)[ch * n + j], 0.f) : ((const float2 *)xv)[ch * n + j];
         if (HAS_NCO) {
             const float2 sc = nco_at(q, q.sincos, q.theta[ch0 + ch], q.dtheta[ch0 + ch], j);
             v = q.dir == 2 ? mix_down(v, sc) : mix_up(v, sc);
@@ -131,6 +157,26 @@ __global__ void nco_par_kernel(const NcoP q, const float2 *__restrict__ x, float
     }
 }
 
+// wdelay read-then-push over a block (Delay, utility.hpp:5-59): y[k] = x[k - D]; the D samples before the call come
+// from hist_in (oldest first) and the newest D go to hist_out (ping-pong, so no CTA reads what another writes)
+template <typename T>
+__global__ void delay_kernel(const T *__restrict__ x, T *__restrict__ y, const T *__restrict__ hist_in, T *__restrict__ hist_out,
+                             int nch, int ch0, long long n, long long D)
+{
+    const long long total = (long long)nch * (n + D);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long ch = i / (n + D), k = i % (n + D);
+        const T *h = hist_in + (ch0 + ch) * D;
+        if (k < n) {
+            const long long s = k - D;
+            y[ch * n + k] = s >= 0 ? x[ch * n + s] : h[D + s];
+        } else {
+            const long long t = n - D + (k - n);                 // time index of history slot k - n after this call
+            hist_out[(ch0 + ch) * D + (k - n)] = t >= 0 ? x[ch * n + t] : h[D + t];
+        }
+    }
+}
+
 // bytes_to_iq over a whole block: interleaved int16 I/Q -> complex64 (reference utility.hpp:61-69)
 __global__ void i16_to_c64_kernel(const unsigned *__restrict__ x, float2 *__restrict__ y, long long total)
 {
@@ -148,6 +194,17 @@ cudaError_t i16_to_c64_launch(const void *x, float2 *y, long long total, cudaStr
     return cudaGetLastError();
 }
 
+cudaError_t delay_launch(bool real, const void *x, void *y, const void *hist_in, void *hist_out, int nch, int ch0, long long n, long long D,
+                         cudaStream_t stream)
+{
+    if (nch <= 0 || n <= 0) return cudaSuccess;
+    const long long total = (long long)nch * (n + D);
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+    if (real) delay_kernel<float><<<blocks, 256, 0, stream>>>((const float *)x, (float *)y, (const float *)hist_in, (float *)hist_out, nch, ch0, n, D);
+    else      delay_kernel<float2><<<blocks, 256, 0, stream>>>((const float2 *)x, (float2 *)y, (const float2 *)hist_in, (float2 *)hist_out, nch, ch0, n, D);
+    return cudaGetLastError();
+}
+
 cudaError_t nco_par_launch(const NcoP &q, const float2 *x, float2 *y, int nch, int ch0, long long n, cudaStream_t stream)
 {
     if (nch <= 0 || n <= 0) return cudaSuccess;
@@ -160,10 +217,11 @@ cudaError_t nco_par_launch(const NcoP &q, const float2 *x, float2 *y, int nch, i
     return cudaGetLastError();
 }
 
-cudaError_t resamp_par_launch(const ResampP &p, const NcoP *nco, const float2 *x, float2 *y, int nch, int ch0, int Ctot,
+cudaError_t resamp_par_launch(const ResampP &p, const NcoP *nco, const void *x, void *y, int nch, int ch0, int Ctot,
                               long long n, long long n_out, cudaStream_t stream)
 {
     if (nch <= 0 || n <= 0) return cudaSuccess;
+    if (p.variant < 0 || p.variant > 2 || (p.variant == 2 && nco)) return cudaErrorInvalidValue;
     const NcoP q = nco ? *nco : NcoP{};
     if (n_out > 0) {
         // outputs per CTA: as many as keep the staged input span within ~48 KB
@@ -175,7 +233,9 @@ cudaError_t resamp_par_launch(const ResampP &p, const NcoP *nco, const float2 *x
         if (ntiles * (long long)nch > 0x7fffffffLL) return cudaErrorInvalidValue;
         const size_t smem = (size_t)span_max * sizeof(float2) + (size_t)((p.npfb * p.sublen + 3) & ~3) * sizeof(float) + (nco ? 1024 * sizeof(float2) : 0);
         if (smem > 200 * 1024) return cudaErrorInvalidValue;
-        auto fn = nco ? resamp_par_kernel<true> : resamp_par_kernel<false>;
+        auto fn = p.variant == 2 ? resamp_par_kernel<false, 2>
+                : p.variant == 1 ? (nco ? resamp_par_kernel<true, 1> : resamp_par_kernel<false, 1>)
+                                 : (nco ? resamp_par_kernel<true, 0> : resamp_par_kernel<false, 0>);
         cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (rc != cudaSuccess) return rc;
         fn<<<(unsigned)(ntiles * nch), NT, smem, stream>>>(p, q, x, y, ch0, Ctot, n, n_out, KT, (int)ntiles, span_max);
@@ -184,8 +244,9 @@ cudaError_t resamp_par_launch(const ResampP &p, const NcoP *nco, const float2 *x
     }
     const long long work = (n < p.sublen ? n : p.sublen) * (long long)nch;
     const unsigned blocks = (unsigned)((work + 255) / 256 < 1184 ? (work + 255) / 256 : 1184);
-    if (nco) ring_update_kernel<true><<<blocks, 256, 0, stream>>>(p, q, x, nch, ch0, Ctot, n);
-    else     ring_update_kernel<false><<<blocks, 256, 0, stream>>>(p, q, x, nch, ch0, Ctot, n);
+    if (nco)                 ring_update_kernel<true, false><<<blocks, 256, 0, stream>>>(p, q, x, nch, ch0, Ctot, n);
+    else if (p.variant == 2) ring_update_kernel<false, true><<<blocks, 256, 0, stream>>>(p, q, x, nch, ch0, Ctot, n);
+    else                     ring_update_kernel<false, false><<<blocks, 256, 0, stream>>>(p, q, x, nch, ch0, Ctot, n);
     cudaError_t rc = cudaGetLastError();
     if (rc != cudaSuccess || !nco) return rc;
     nco_advance_kernel<<<(nch + 255) / 256, 256, 0, stream>>>(q, nch, ch0, n);

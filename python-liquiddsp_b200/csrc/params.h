@@ -43,6 +43,7 @@ struct ResampP {
     const float *bank;             // device [npfb][sublen], sub-filters reversed
     float2 *ring;                  // [sublen][Ctot] last sublen inputs, slot = count % sublen
     uint32_t count;                // inputs consumed since reset, modulo sublen
+    int variant;                   // 0 resamp_cccf, 1 resamp_crcf, 2 resamp_rrrf (time-parallel kernel only)
 };
 
 struct AgcP {

@@ -61,7 +61,10 @@ _SIG = {
     "lqb_firfilt_crcf_create": [_P, _I, _I, _PP], "lqb_firfilt_crcf_create_kaiser": [_I, _F, _F, _F, _I, _PP],
     "lqb_firfilt_crcf_set_scale": [_P, _F], "lqb_firfilt_crcf_get_taps": [_P, _P, C.POINTER(_I)],
     "lqb_firfilt_crcf_freqresponse": [_P, _F, C.POINTER(_cf)],
-    "lqb_resamp_create": [_F, _I, _F, _F, _I, _I, _PP], "lqb_resamp_set_rate": [_P, _F],
+    "lqb_resamp_create": [_F, _I, _F, _F, _I, _I, _PP],
+    "lqb_resamp_crcf_create": [_F, _I, _F, _F, _I, _I, _PP], "lqb_resamp_rrrf_create": [_F, _I, _F, _F, _I, _I, _PP],
+    "lqb_resamp_crcf_create_default": [_F, _I, _PP], "lqb_resamp_rrrf_create_default": [_F, _I, _PP],
+    "lqb_wdelay_create": [_I, _I, _I, _PP], "lqb_resamp_set_rate": [_P, _F],
     "lqb_resamp_get_state": [_P, C.POINTER(_U32), C.POINTER(_U32)],
     "lqb_resamp_get_bank": [_P, _P, C.POINTER(_I), C.POINTER(_I)],
     "lqb_nco_create": [_I, _I, _PP], "lqb_nco_set_direction": [_P, _I],
@@ -360,6 +363,72 @@ class ComplexResampler(_Stage):
     def print(self):
         s, p = self.state()
         print("resampler [rate: %g, step 0x%08x, phase 0x%08x]" % (self._rate, s, p))
+
+
+class RealResampler(ComplexResampler):
+    """wrapper.cpp:214-219 / resampler.hpp:72-125: resamp_rrrf_create(rate, len, Fc, As, nfilter) on float samples."""
+    _in_dtype = np.float32
+    _out_dtype = np.float32
+
+    def __init__(self, rate, len=20, Fc=None, As=60.0, nfilter=13, channels=1):
+        _Stage.__init__(self)
+        if Fc is None:
+            raise TypeError("RealResampler() missing required argument: 'Fc'")
+        self._rate = float(rate)
+        _ck(_lib.lqb_resamp_rrrf_create(rate, int(len), Fc, As, int(nfilter), channels, C.byref(self._h)))
+
+
+class CResampler(ComplexResampler):
+    """wrapper.cpp:20-23 / resampler.hpp:38-70: resamp_crcf_create_default(rate); `rate` is fixed at construction."""
+
+    def __init__(self, rate, channels=1):
+        _Stage.__init__(self)
+        self._rate = float(rate)
+        _ck(_lib.lqb_resamp_crcf_create_default(rate, channels, C.byref(self._h)))
+
+
+class RResampler(ComplexResampler):
+    """wrapper.cpp:15-18 / resampler.hpp:4-36: resamp_rrrf_create_default(rate) on float samples."""
+    _in_dtype = np.float32
+    _out_dtype = np.float32
+
+    def __init__(self, rate, channels=1):
+        _Stage.__init__(self)
+        self._rate = float(rate)
+        _ck(_lib.lqb_resamp_rrrf_create_default(rate, channels, C.byref(self._h)))
+
+
+class _DelayLine(_Stage):
+    def __init__(self, nd, real, channels):
+        super().__init__()
+        self._in_dtype = self._out_dtype = np.float32 if real else np.complex64
+        _ck(_lib.lqb_wdelay_create(int(nd), 1 if real else 0, channels, C.byref(self._h)))
+
+
+class Delay:
+    """wrapper.cpp:25-28 / utility.hpp:5-59: one float and one complex delay line (read, then push -- nd + 1 samples);
+    complex64 input -> complex64, float32 -> float32, anything else -> None.  Setting `delay` rebuilds both lines."""
+
+    def __init__(self, nd=1, channels=1):
+        self._channels = channels
+        self.delay = nd
+
+    @property
+    def delay(self):
+        return self._nd
+
+    @delay.setter
+    def delay(self, nd):
+        self._nd = int(nd)
+        self._real, self._cplx = _DelayLine(nd, True, self._channels), _DelayLine(nd, False, self._channels)
+
+    def __call__(self, x):
+        x = np.asarray(x)
+        if x.dtype == np.complex64:
+            return self._cplx(x)
+        if x.dtype == np.float32:
+            return self._real(x)
+        return None
 
 
 class NCO(_Stage):

@@ -63,6 +63,16 @@ def test_reference_api_surface():
     for cls in (L.CBandpassIIR, L.CBandstopIIR, L.RBandpassIIR, L.RBandstopIIR):
         assert sig(cls) == dict(filter_type="butter", order=2, Fc=0.2, F0=0.3, Ap=0.5, As=20.0)
     assert sig(L.CIIRFilter) == sig(L.RIIRFilter) == dict(Bc=inspect._empty, Ac=inspect._empty)
+    assert sig(L.RealResampler) == sig(L.ComplexResampler)
+    assert sig(L.CResampler) == sig(L.RResampler) == dict(rate=inspect._empty) and sig(L.Delay) == dict(nd=1)
+    d = L.Delay(3); d.delay = 7
+    assert d.delay == 7 and d(np.zeros(4, np.int16)) is None
+    for rate in (0.08, 0.5, 1.0, 2.2):                   # create_default: fc = min(0.49, rate/2), 64 filters of 14 taps
+        g, o = L.CResampler(rate), O.CResampler(rate)
+        assert g.state()[0] == o.step and g.bank().shape == (64, 14) and np.array_equal(g.bank(), o.bank())
+        assert np.array_equal(L.RResampler(rate).bank(), o.bank())
+    assert np.array_equal(L.RealResampler(0.3, Fc=0.1).bank(), O.RealResampler(0.3, Fc=0.1).bank())
+    assert L.Chain(L.FreqDem(0.1), L.RResampler(0.08), L.DeemphasisFilter()).plan() == "seq[freqdem] -> par[resamp] -> seq[deemph]"
     assert sig(L.BroadcastAM) == dict(slen=25) and sig(L.SSBDemod) == dict(band=inspect._empty)
     assert sig(L.HilbertTransform) == dict(m=5, As=60.0)
     assert np.array_equal(L.SSBDemod("usb").hq(), O.SSBDemod("usb").hq()) and L.SSBDemod("anything").usb is False

@@ -228,6 +228,51 @@ def test_real_chain_am_dcblock_lowpass(cuda):
     assert rel_l2(chain(x), olp(odc(oam(x)))) <= TOL_E2E
 
 
+# ------------------------------------------------------------------------- 8f row 4: resampler variants, Delay
+@pytest.mark.parametrize("rate", [0.08, 0.5, 1.0, 2.2, 48000.0 / 600000.0])
+def test_default_resamplers_bit_exact(cuda, rate):
+    """CResampler / RResampler (resamp_*_create_default): output count, phase and values, streaming."""
+    rng = np.random.default_rng(61)
+    n = 6001
+    x = crandn(rng, n)
+    g, o = L.CResampler(rate), O.CResampler(rate)
+    cuts = split_points(n, 5, rng)
+    y = np.concatenate([g(x[s:e]) for s, e in cuts]); yo = np.concatenate([o(x[s:e]) for s, e in cuts])
+    assert y.shape == yo.shape and np.array_equal(y.view(np.uint32), yo.view(np.uint32)) and g.state()[1] == o.phase
+    gr, orr = L.RResampler(rate, channels=3), O.RResampler(rate)
+    xr = np.stack([x.real, x.imag, x.real[::-1]]).copy()
+    yr = np.concatenate([gr(xr[:, s:e]) for s, e in cuts], axis=1)
+    assert yr.dtype == np.float32 and np.array_equal(yr[0], y.real) and np.array_equal(yr[1], y.imag)
+    assert np.array_equal(yr[2], np.concatenate([orr(xr[2, s:e]) for s, e in cuts]))
+
+
+def test_real_resampler_rate_property_and_reset(cuda):
+    rng = np.random.default_rng(62)
+    x = rng.standard_normal(5000).astype(np.float32)
+    g, o = L.RealResampler(0.3, Fc=0.12), O.RealResampler(0.3, Fc=0.12)
+    assert np.array_equal(g(x[:2000]), o(x[:2000]))
+    g.rate = 0.41; o.rate = 0.41
+    assert g.rate == 0.41 and np.array_equal(g(x[2000:]), o(x[2000:]))
+    g.reset(); o.reset()
+    assert np.array_equal(g(x[:100]), o(x[:100]))
+
+
+@pytest.mark.parametrize("nd", [0, 1, 7, 300])
+def test_delay(cuda, nd):
+    rng = np.random.default_rng(63)
+    g, o = L.Delay(nd), O.Delay(nd)
+    z = crandn(rng, 1000); r = rng.standard_normal(1000).astype(np.float32)
+    for s, e in [(0, 1), (1, 5), (5, 400), (400, 1000)]:            # the two lines keep separate state
+        assert np.array_equal(g(z[s:e]), o(z[s:e])) and np.array_equal(g(r[s:e]), o(r[s:e]))
+    g.delay = nd; o.delay = nd                                       # the setter rebuilds and clears both lines
+    assert np.array_equal(g(z[:50]), o(z[:50])) and np.array_equal(g(r[:50]), o(r[:50]))
+    gb = L.Delay(nd, channels=5)
+    zb = crandn(rng, 5, 700)
+    yb = np.concatenate([gb(zb[:, :123]), gb(zb[:, 123:])], axis=1)
+    ref = np.concatenate([np.zeros((5, nd + 1), np.complex64), zb], axis=1)[:, :700]
+    assert np.array_equal(yb, ref)
+
+
 # ------------------------------------------------------------------------- 8f row 3: SSBDemod, HilbertTransform
 @pytest.mark.parametrize("band", ["usb", "lsb"])
 def test_ssb_demod(cuda, band):
