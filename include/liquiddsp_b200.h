@@ -202,6 +202,15 @@ int lqb_ampmodem_get_nco_u32(lqb_stage s, uint32_t *theta, uint32_t *d_theta, in
 int lqb_firhilbf_create(int kind, int m, float as, int n_channels, lqb_stage *out);
 int lqb_firhilbf_get_hq(lqb_stage s, float *hq, int *n);
 
+/* ---------------- FMStereo : demod.hpp:4-85, wrapper.cpp:264-267 ------------------------------------------
+ * replaces the per-sample demod_one loop (:43-48): freqdem(4.0), nco_crcf pilot mixer + PLL, two iirfilt_rrrf 75 us
+ * de-emphasis filters, two resamp_rrrf_create_default(pcm_rate / iq_rate).  complex -> interleaved (left, right)
+ * floats; lqb_stage_out_len counts floats (two per output pair).  lqb_stage_reset resets the resamplers only, as
+ * FMStereo::reset does (:35-38).  phase_error (uninitialised in the reference) starts at 0. */
+int lqb_fmstereo_create(float iq_rate, float pcm_rate, int n_channels, lqb_stage *out);
+int lqb_fmstereo_get_state(lqb_stage s, uint32_t *theta, uint32_t *d_theta, float *phase_error, int n);
+int lqb_fmstereo_get_deemph(lqb_stage s, float *b0, float *a1);
+
 /* ---------------- BroadcastAM : demod.hpp:94-153, wrapper.cpp:259-262 -----------------------------------
  * replaces the per-sample demod_one loop (:124-131): nco_crcf PLL (bw 0.001, arg() detector), firfilt_crcf
  * kaiser(2*slen+1, 0.01, 40 dB), wdelaycf(slen), iirfilt_rrrf cheby2 order-3 high-pass.  complex -> real.

@@ -1242,6 +1242,69 @@ void orc_wrap_hilbert_r2c(orc_firhilbf q, const float *z, unsigned n, orc_cf *y)
     for (unsigned i = 0; i < n; i++) { pair[0] = z[i]; pair[1] = i + 1 < n ? z[i + 1] : 0.0f; orc_firhilbf_decim_execute(q, pair, &y[i]); }
 }
 
+/* ==========================================================================================
+ *  FMStereo, demod.hpp:4-85.  create :16-33, reset :35-38 (the resamplers only), demod_one :56-84, execute :40-54.
+ *  As written in the reference: the mixer's frequency is never set (it starts at 0 and only the PLL moves it), the PLL
+ *  keeps nco_crcf_create's default bandwidth (0.1), and phase_error is an uninitialised member -- taken as 0 here.
+ *  arg() and the discriminator's cargf are taken correctly rounded (see BroadcastAM); the one-pole phase filter is
+ *  the double expression 0.999*pe + 0.001*arg with GCC's contraction, narrowed to float on assignment.
+ * ======================================================================================== */
+struct orc_fmstereo_s {
+    orc_nco mixer; float ref, rr, ri; orc_iirfilt_rrrf emphL, emphR; orc_resamp audioL, audioR; float phase_error;
+};
+orc_fmstereo orc_wrap_fmstereo_create(float iq_rate, float pcm_rate)
+{
+    orc_fmstereo q = calloc(1, sizeof *q);
+    float mB[1], mA[2];
+    mA[0] = 1.0;
+    mA[1] = -exp(-1.0 / (75.0E-6 * iq_rate));
+    mB[0] = 1.0 + mA[1];
+    q->mixer = orc_nco_create(ORC_NCO);
+    q->ref = 1.0f / (2 * M_PI * 4.0f);                       /* freqdem_create(4.0): ref = 1/(2 pi kf) */
+    q->emphL = orc_iirfilt_rrrf_create(mB, 1, mA, 2);
+    q->emphR = orc_iirfilt_rrrf_create(mB, 1, mA, 2);
+    q->audioL = orc_resamp_create_default(pcm_rate / iq_rate);
+    q->audioR = orc_resamp_create_default(pcm_rate / iq_rate);
+    if (!q->audioL || !q->audioR) { orc_wrap_fmstereo_destroy(q); return NULL; }
+    return q;
+}
+void orc_wrap_fmstereo_destroy(orc_fmstereo q)
+{
+    if (!q) return;
+    orc_nco_destroy(q->mixer); orc_iirfilt_rrrf_destroy(q->emphL); orc_iirfilt_rrrf_destroy(q->emphR);
+    orc_resamp_destroy(q->audioL); orc_resamp_destroy(q->audioR); free(q);
+}
+void orc_wrap_fmstereo_reset(orc_fmstereo q) { orc_resamp_reset(q->audioL); orc_resamp_reset(q->audioR); }
+void orc_wrap_fmstereo_get_state(orc_fmstereo q, uint32_t *theta, uint32_t *d_theta, float *pe)
+{ *theta = q->mixer->theta; *d_theta = q->mixer->d_theta; *pe = q->phase_error; }
+void orc_wrap_fmstereo_get_deemph(orc_fmstereo q, float *b0, float *a1) { *b0 = q->emphL->b[0]; *a1 = q->emphL->a[1]; }
+unsigned orc_wrap_fmstereo_execute(orc_fmstereo q, const orc_cf *x, unsigned n, float *y)
+{
+    unsigned nw = 0;
+    for (unsigned i = 0; i < n; i++) {
+        /* freqdem_demodulate: cargf(conjf(r') * r) * ref */
+        float a = q->rr, b = q->ri, c = x[i].re, d = x[i].im;
+        float re = FMA(a, c, b * d), im = FMA(a, d, -(b * c));
+        float s = (float)atan2((double)im, (double)re) * q->ref;
+        q->rr = c; q->ri = d;
+        orc_cf in = { s, 0.0f }, sc;
+        orc_nco_mix_down(q->mixer, in, &sc);                                  /* down by the pilot */
+        float arg = (float)atan2((double)sc.im, (double)sc.re);
+        q->phase_error = (float)fma(0.999, (double)q->phase_error, 0.001 * (double)arg);
+        orc_nco_mix_down(q->mixer, sc, &sc);                                  /* and once more */
+        orc_nco_pll_step(q->mixer, q->phase_error);
+        orc_nco_step(q->mixer);
+        float left, right; orc_cf ol[4], orr[4]; unsigned nl, nr;
+        orc_iirfilt_rrrf_execute(q->emphL, s + sc.re, &left);
+        orc_iirfilt_rrrf_execute(q->emphR, s - sc.re, &right);
+        orc_cf li = { left, 0.0f }, ri = { right, 0.0f };
+        orc_resamp_execute(q->audioL, li, ol, &nl);
+        orc_resamp_execute(q->audioR, ri, orr, &nr);
+        if (nl + nr == 2) { y[nw] = ol[0].re; y[nw + 1] = orr[0].re; nw += 2; }   /* execute(), :45-48 */
+    }
+    return nw;
+}
+
 /* bytes_to_iq, utility.hpp:61-69 */
 void orc_wrap_bytes_to_iq(const int16_t *iq, unsigned n, orc_cf *y)
 { for (unsigned i = 0; i < n; i++) { y[i].re = (float)iq[2 * i] / 32767.0f; y[i].im = (float)iq[2 * i + 1] / 32767.0f; } }

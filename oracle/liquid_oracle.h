@@ -209,6 +209,13 @@ void  orc_firhilbf_interp_execute(orc_firhilbf q, orc_cf x, float *y);
 void  orc_wrap_ssb_execute(orc_firhilbf q, int usb, const orc_cf *x, unsigned n, float *y);
 void  orc_wrap_hilbert_c2r(orc_firhilbf q, const orc_cf *z, unsigned n, float *y);
 void  orc_wrap_hilbert_r2c(orc_firhilbf q, const float *z, unsigned n, orc_cf *y);
+typedef struct orc_fmstereo_s *orc_fmstereo;   /* FMStereo, demod.hpp:4-85 */
+orc_fmstereo orc_wrap_fmstereo_create(float iq_rate, float pcm_rate);
+void  orc_wrap_fmstereo_destroy(orc_fmstereo q);
+void  orc_wrap_fmstereo_reset(orc_fmstereo q);
+void  orc_wrap_fmstereo_get_state(orc_fmstereo q, uint32_t *theta, uint32_t *d_theta, float *pe);
+void  orc_wrap_fmstereo_get_deemph(orc_fmstereo q, float *b0, float *a1);
+unsigned orc_wrap_fmstereo_execute(orc_fmstereo q, const orc_cf *x, unsigned n, float *y);   /* y: interleaved L, R */
 typedef struct orc_bam_s *orc_bam;      /* BroadcastAM, demod.hpp:94-153 */
 orc_bam orc_wrap_bam_create(int m);
 void  orc_wrap_bam_destroy(orc_bam q);

@@ -100,6 +100,9 @@ def _load(name="liboracle.so"):
         "orc_firhilbf_get_hq": (U, [P, P]), "orc_wrap_ssb_execute": (None, [P, I, P, U, P]),
         "orc_wrap_hilbert_c2r": (None, [P, P, U, P]), "orc_wrap_hilbert_r2c": (None, [P, P, U, P]),
         "orc_resamp_set_real_taps": (None, [P, I]), "orc_resamp_create_default": (P, [F]),
+        "orc_wrap_fmstereo_create": (P, [F, F]), "orc_wrap_fmstereo_destroy": (None, [P]), "orc_wrap_fmstereo_reset": (None, [P]),
+        "orc_wrap_fmstereo_get_state": (None, [P, P, P, P]), "orc_wrap_fmstereo_get_deemph": (None, [P, P, P]),
+        "orc_wrap_fmstereo_execute": (U, [P, P, U, P]),
         "orc_wrap_bam_create": (P, [I]), "orc_wrap_bam_destroy": (None, [P]), "orc_wrap_bam_reset": (None, [P]),
         "orc_wrap_bam_get_nco": (None, [P, P, P]), "orc_wrap_bam_get_design": (U, [P, P, P, P]),
         "orc_wrap_bam_execute": (None, [P, P, U, P]), "orc_wrap_bam_set_dcblock": (None, [P, P, P, U]),
@@ -660,6 +663,33 @@ class HilbertTransform:
             x = np.ascontiguousarray(x); y = np.empty(x.shape[0], _cf)
             lib.orc_wrap_hilbert_r2c(self._r2c, _p(x), x.shape[0], _p(y)); return y
         return None
+
+
+class FMStereo:
+    """wrapper.cpp:264-267, demod.hpp:4-85.  Output: interleaved [L0, R0, L1, R1, ...] float32."""
+
+    def __init__(self, iq_rate=600000.0, pcm_rate=48000.0):
+        self._q = lib.orc_wrap_fmstereo_create(iq_rate, pcm_rate)
+        if not self._q:
+            raise ValueError("FMStereo: bad rates")
+
+    def __del__(self):
+        if getattr(self, "_q", None):
+            lib.orc_wrap_fmstereo_destroy(self._q); self._q = None
+
+    def reset(self): lib.orc_wrap_fmstereo_reset(self._q)
+
+    def state(self):
+        t = np.zeros(1, np.uint32); d = np.zeros(1, np.uint32); pe = np.zeros(1, _f)
+        lib.orc_wrap_fmstereo_get_state(self._q, _p(t), _p(d), _p(pe)); return int(t[0]), int(d[0]), float(pe[0])
+
+    def deemph(self):
+        b = np.zeros(1, _f); a = np.zeros(1, _f); lib.orc_wrap_fmstereo_get_deemph(self._q, _p(b), _p(a)); return float(b[0]), float(a[0])
+
+    def __call__(self, x):
+        x = _c64(x); y = np.empty(2 * x.shape[0] + 8, _f)
+        nw = lib.orc_wrap_fmstereo_execute(self._q, _p(x), x.shape[0], _p(y))
+        return y[:nw].copy()
 
 
 class BroadcastAM:

@@ -24,6 +24,7 @@
 #include "fir.h"
 #include "am.h"
 #include "bam.h"
+#include "fmst.h"
 #include "par.h"
 #include "scan.h"
 #include "synth.h"
@@ -138,7 +139,7 @@ static bool make_input_tmap(CUtensorMap *tm, const void *x, size_t n, size_t row
 }
 
 // ------------------------------------------------------------------------------------ stages
-enum Kind { K_NCO = 0, K_IIR, K_RESAMP, K_AGC, K_AM, K_FM, K_DEEMPH, K_FIR, K_TF, K_BAM, K_DELAY };
+enum Kind { K_NCO = 0, K_IIR, K_RESAMP, K_AGC, K_AM, K_FM, K_DEEMPH, K_FIR, K_TF, K_BAM, K_DELAY, K_FMST };
 
 }  // namespace lqb
 
@@ -426,6 +427,44 @@ struct BamStage : lqb_stage_s {
     }
 };
 
+// FMStereo (demod.hpp:4-85): complex in, interleaved (left, right) float pairs out -- two floats per resampler output
+struct FmstStage : lqb_stage_s {
+    float b0 = 0, a1 = 0; design::ResampDesign d; uint32_t step = 0, phase = 0, count = 0;
+    DevArr<float> bank, pe, vL, vR, ringL, ringR; DevArr<float2> rprime; DevArr<uint32_t> theta, dtheta;
+    FmstStage(int c) : lqb_stage_s(K_FMST, c) {}
+    bool out_real() const override { return true; }
+    int materialize() override
+    {
+        LQB_TRY(bank.alloc(d.bank.size())); LQB_TRY(bank.upload(d.bank.data(), d.bank.size()));
+        LQB_TRY(pe.alloc(C)); LQB_TRY(vL.alloc(C)); LQB_TRY(vR.alloc(C)); LQB_TRY(rprime.alloc(C)); LQB_TRY(theta.alloc(C)); LQB_TRY(dtheta.alloc(C));
+        LQB_TRY(ringL.alloc((size_t)d.sublen * C)); return ringR.alloc((size_t)d.sublen * C);
+    }
+    // FMStereo::reset (demod.hpp:35-38) resets the two resamplers and nothing else
+    void host_reset() override { phase = 0; count = 0; }
+    int clear() override { LQB_TRY(ringL.zero()); return ringR.zero(); }
+    size_t pairs(size_t n) const
+    {
+        const uint64_t lim = ((uint64_t)n << 24);
+        if (n == 0 || (uint64_t)phase > lim - 1) return 0;
+        return (size_t)((lim - 1 - phase) / step + 1);
+    }
+    size_t out_len(size_t n) const override { return 2 * pairs(n); }
+    void advance(size_t n) override
+    {
+        const uint64_t k = pairs(n);
+        phase = (uint32_t)((uint64_t)phase + k * step - ((uint64_t)n << 24));
+        count = (uint32_t)((count + n) % d.sublen);
+    }
+    int fill(FmstP &p) const
+    {
+        p.ref = (float)(1.0f / (2 * design::kPi * 4.0f)); p.pll_alpha = 0.1f; p.pll_beta = std::sqrt(0.1f); p.b0 = b0; p.a1 = a1;
+        p.rs.step = step; p.rs.phase = phase; p.rs.bits = (int)d.bits; p.rs.sublen = (int)d.sublen; p.rs.npfb = (int)d.npfb;
+        p.rs.bank = bank.p; p.rs.ring = nullptr; p.rs.count = count; p.rs.variant = 2;
+        p.rprime = rprime.p; p.theta = theta.p; p.dtheta = dtheta.p; p.pe = pe.p; p.vL = vL.p; p.vR = vR.p; p.ringL = ringL.p; p.ringR = ringR.p;
+        return sincos_table(&p.sincos);
+    }
+};
+
 struct FmStage : lqb_stage_s {
     float kf = 0.1f, ref = 0.f; DevArr<float2> rprime;
     FmStage(int c) : lqb_stage_s(K_FM, c) {}
@@ -440,7 +479,7 @@ constexpr int kParChannels = 16384;
 
 // ------------------------------------------------------------------------------------ chain
 struct Segment {
-    enum Type { SEQ, FIR, RESAMP_PAR, AMTAIL, NCO_PAR, BAM, DELAY } type = SEQ;
+    enum Type { SEQ, FIR, RESAMP_PAR, AMTAIL, NCO_PAR, BAM, DELAY, FMST } type = SEQ;
     unsigned mask = 0; int nsos = 0, sos0 = 0;
     std::vector<lqb_stage_s *> st;
     std::string name;
@@ -478,7 +517,7 @@ static const char *kind_name(Kind k)
 {
     switch (k) {
     case K_NCO: return "nco"; case K_IIR: return "iir"; case K_RESAMP: return "resamp"; case K_AGC: return "agc";
-    case K_AM: return "ampmodem"; case K_FM: return "freqdem"; case K_DEEMPH: return "deemph"; case K_FIR: return "fir"; case K_TF: return "tf"; case K_BAM: return "broadcast_am"; case K_DELAY: return "delay";
+    case K_AM: return "ampmodem"; case K_FM: return "freqdem"; case K_DEEMPH: return "deemph"; case K_FIR: return "fir"; case K_TF: return "tf"; case K_BAM: return "broadcast_am"; case K_DELAY: return "delay"; case K_FMST: return "fmstereo";
     }
     return "?";
 }
@@ -535,6 +574,7 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
     for (size_t i = 0; i < st.size();) {
         Segment g;
         if (st[i]->kind == K_FIR) { g.type = Segment::FIR; g.st = { st[i] }; g.name = "fir"; segs.push_back(g); i++; continue; }
+        if (st[i]->kind == K_FMST) { g.type = Segment::FMST; g.st = { st[i] }; g.name = "fmstereo"; segs.push_back(g); i++; continue; }
         if (st[i]->kind == K_DELAY) { g.type = Segment::DELAY; g.st = { st[i] }; g.name = "delay"; segs.push_back(g); i++; continue; }
         if (st[i]->kind == K_RESAMP && static_cast<ResampStage *>(st[i])->variant != 0) {      // real-tap resamplers: time-parallel kernel
             g.type = Segment::RESAMP_PAR; g.st = { st[i] }; g.name = "par[resamp]"; segs.push_back(g); i++; continue;
@@ -621,6 +661,13 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         }
         LQB_CUDA(amtail_launch(has_agc, has_de, a, stream));
         *launches += amtail_launch_count(has_agc, a) - 1;
+        return LQB_OK;
+    }
+    if (g.type == Segment::FMST) {
+        FmstArgs a{};
+        a.x = (const float2 *)x; a.y = (float *)y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.n = (long long)n; a.n_out = (long long)(n_out / 2);
+        LQB_TRY(static_cast<const FmstStage *>(first)->fill(a.p));
+        LQB_CUDA(fmstereo_launch(a, stream));
         return LQB_OK;
     }
     if (g.type == Segment::DELAY) {
@@ -1281,6 +1328,37 @@ int lqb_ampmodem_create(float mod, int type, int suppressed, int C, lqb_stage *o
     design::firdes_notch(kAmDelay, 0.0f, 20.0f, q->dc);
     *out = q; return LQB_OK;
 }
+// ---- FMStereo
+int lqb_fmstereo_create(float iq_rate, float pcm_rate, int C, lqb_stage *out)
+{
+    LQB_TRY(check_channels(C));
+    if (!out || !(iq_rate > 0.f) || !(pcm_rate > 0.f)) return fail(LQB_EINVAL, "FMStereo: rates must be positive");
+    const float rate = pcm_rate / iq_rate;
+    if (rate > 1.0f) return fail(LQB_ENOTIMPL, "FMStereo: pcm_rate above iq_rate (the reference keeps an output pair only when each resampler yields exactly one sample)");
+    if (rate < 0.004f) return fail(LQB_EINVAL, "FMStereo: pcm_rate / iq_rate %g below 0.004", rate);
+    FmstStage *q = new FmstStage(C);
+    // demod.hpp:20-32: 75 us de-emphasis at the I/Q rate, freqdem(4.0), resamp_rrrf_create_default(pcm_rate / iq_rate)
+    const float a1 = (float)(-std::exp(-1.0 / (75.0E-6 * (double)iq_rate)));
+    q->a1 = a1; q->b0 = (float)(1.0 + (double)a1);
+    if (!design::resamp_design(7, 0.5f * rate > 0.49f ? 0.49f : 0.5f * rate, 60.0f, 64, q->d) || q->d.sublen > (unsigned)kFmstMaxSub) {
+        delete q; return fail(LQB_EINVAL, "FMStereo: resampler design failed");
+    }
+    q->step = design::resamp_step(rate);
+    *out = q; return LQB_OK;
+}
+int lqb_fmstereo_get_state(lqb_stage s, uint32_t *theta, uint32_t *d_theta, float *pe, int n)
+{
+    LQB_GET(FmstStage, q, s, K_FMST);
+    if (n < 0 || n > q->C) return fail(LQB_EINVAL, "bad channel count");
+    LQB_TRY(q->ensure());
+    LQB_CUDA(cudaDeviceSynchronize());
+    if (theta) LQB_TRY(q->theta.download(theta, n));
+    if (d_theta) LQB_TRY(q->dtheta.download(d_theta, n));
+    if (pe) LQB_TRY(q->pe.download(pe, n));
+    return LQB_OK;
+}
+int lqb_fmstereo_get_deemph(lqb_stage s, float *b0, float *a1) { LQB_GET(FmstStage, q, s, K_FMST); *b0 = q->b0; *a1 = q->a1; return LQB_OK; }
+
 // ---- BroadcastAM
 int lqb_broadcast_am_create(int m, int C, lqb_stage *out)
 {

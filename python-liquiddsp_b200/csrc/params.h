@@ -123,6 +123,28 @@ struct BamArgs {
     BamP p; DeP de;
 };
 
+// FMStereo (demod.hpp:4-85): discriminator, pilot mixer with its PLL, two one-pole de-emphasis filters, two real
+// resamplers with a common phase
+constexpr int kFmstMaxSub = 32;    // taps per sub-filter of the audio resamplers (create_default: 14)
+struct FmstP {
+    float ref;                     // freqdem: 1 / (2 pi kf)
+    float pll_alpha, pll_beta;
+    float b0, a1;                  // de-emphasis: v0 = x - a1 v1, y = b0 v0
+    const float2 *sincos;
+    ResampP rs;                    // step, phase, bits, sublen, npfb, bank, count (ring unused)
+    float2 *rprime;                // [Ctot] previous input sample
+    uint32_t *theta, *dtheta;      // [Ctot]
+    float *pe, *vL, *vR;           // [Ctot] filtered phase error, de-emphasis states
+    float *ringL, *ringR;          // [sublen][Ctot] resampler windows, slot = count % sublen
+};
+struct FmstArgs {
+    const float2 *x;               // [C][n]
+    float *y;                      // [C][2 * n_out] interleaved left, right
+    int C, ch0, Ctot;
+    long long n, n_out;
+    FmstP p;
+};
+
 enum { FIR_PLAIN = 0, FIR_SSB_LSB, FIR_SSB_USB, FIR_R2C, FIR_C2R };
 struct FirArgs {
     const float2 *x; float2 *y;    // [C][n]

@@ -85,6 +85,8 @@ _SIG = {
     "lqb_ampmodem_get_nco_u32": [_P, _P, _P, _I],
     "lqb_freqdem_create": [_F, _I, _PP],
     "lqb_firhilbf_create": [_I, _I, _F, _I, _PP], "lqb_firhilbf_get_hq": [_P, _P, C.POINTER(_I)],
+    "lqb_fmstereo_create": [_F, _F, _I, _PP], "lqb_fmstereo_get_state": [_P, _P, _P, _P, _I],
+    "lqb_fmstereo_get_deemph": [_P, C.POINTER(_F), C.POINTER(_F)],
     "lqb_broadcast_am_create": [_I, _I, _PP], "lqb_broadcast_am_get_design": [_P, _P, C.POINTER(_I), _P, _P],
     "lqb_broadcast_am_get_nco_u32": [_P, _P, _P, _I],
     "lqb_chain_create": [_PP], "lqb_chain_append": [_P, _P], "lqb_chain_destroy": [_P],
@@ -617,6 +619,23 @@ class HilbertTransform:
         if x.dtype == np.float32:
             return self._r2c(x)
         return None
+
+
+class FMStereo(_Stage):
+    """wrapper.cpp:264-267 / demod.hpp:4-85.  Output: interleaved [L0, R0, L1, R1, ...] float32 (per channel row);
+    reset() resets the two audio resamplers only, as the reference does."""
+    _out_dtype = np.float32
+
+    def __init__(self, iq_rate=600000.0, pcm_rate=48000.0, channels=1):
+        super().__init__()
+        _ck(_lib.lqb_fmstereo_create(iq_rate, pcm_rate, channels, C.byref(self._h)))
+
+    def state(self):
+        n = self.channels; t = np.zeros(n, np.uint32); d = np.zeros(n, np.uint32); pe = np.zeros(n, np.float32)
+        _ck(_lib.lqb_fmstereo_get_state(self._h, _ptr(t), _ptr(d), _ptr(pe), n)); return t, d, pe
+
+    def deemph(self):
+        b0, a1 = _F(), _F(); _ck(_lib.lqb_fmstereo_get_deemph(self._h, C.byref(b0), C.byref(a1))); return b0.value, a1.value
 
 
 class BroadcastAM(_Stage):

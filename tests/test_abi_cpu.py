@@ -73,6 +73,11 @@ def test_reference_api_surface():
         assert np.array_equal(L.RResampler(rate).bank(), o.bank())
     assert np.array_equal(L.RealResampler(0.3, Fc=0.1).bank(), O.RealResampler(0.3, Fc=0.1).bank())
     assert L.Chain(L.FreqDem(0.1), L.RResampler(0.08), L.DeemphasisFilter()).plan() == "seq[freqdem] -> par[resamp] -> seq[deemph]"
+    assert sig(L.FMStereo) == dict(iq_rate=600000.0, pcm_rate=48000.0)
+    assert L.FMStereo().deemph() == O.FMStereo().deemph() and L.FMStereo().out_len(600000) == 96000
+    assert L.FMStereo(240000.0, 44100.0).deemph() == O.FMStereo(240000.0, 44100.0).deemph()
+    with pytest.raises(NotImplementedError):
+        L.FMStereo(48000.0, 96000.0)
     assert sig(L.BroadcastAM) == dict(slen=25) and sig(L.SSBDemod) == dict(band=inspect._empty)
     assert sig(L.HilbertTransform) == dict(m=5, As=60.0)
     assert np.array_equal(L.SSBDemod("usb").hq(), O.SSBDemod("usb").hq()) and L.SSBDemod("anything").usb is False

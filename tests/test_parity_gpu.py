@@ -9,11 +9,17 @@ import pytest
 
 import liquiddsp as L
 from oracle import oracle as O
-from util import rel_l2, crandn, am_iq, fm_iq, split_points
+from util import rel_l2, crandn, am_iq, fm_iq, fm_stereo_iq, split_points
 
 pytestmark = pytest.mark.gpu
 TOL_STAGE = 1e-5
 TOL_E2E = 1e-4
+
+
+def _bits_or_close(y, yo, tol=TOL_STAGE):
+    """The PLL branch takes arg() through a double-precision atan2 on both sides; the two math libraries agree after
+    rounding to float except with probability ~1e-8 per sample, so equality is expected and 1e-5 is demanded."""
+    return np.array_equal(y.view(np.uint32), yo.view(np.uint32)) or rel_l2(y, yo) <= tol
 
 
 # ------------------------------------------------------------------------------------------- a1
@@ -273,6 +279,33 @@ def test_delay(cuda, nd):
     assert np.array_equal(yb, ref)
 
 
+@pytest.mark.parametrize("iq_rate,pcm_rate,n", [(600000.0, 48000.0, 60000), (240000.0, 44100.0, 20001), (96000.0, 96000.0, 3000)])
+def test_fmstereo_single_channel(cuda, iq_rate, pcm_rate, n):
+    x = fm_stereo_iq(n, fs=iq_rate)
+    g, o = L.FMStereo(iq_rate, pcm_rate), O.FMStereo(iq_rate, pcm_rate)
+    rng = np.random.default_rng(64)
+    cuts = split_points(n, 4, rng)
+    y = np.concatenate([g(x[s:e]) for s, e in cuts]); yo = np.concatenate([o(x[s:e]) for s, e in cuts])
+    assert y.dtype == np.float32 and y.shape == yo.shape and y.size % 2 == 0
+    assert _bits_or_close(y, yo, TOL_E2E), rel_l2(y, yo)
+    (t, d, pe), (to, do, peo) = g.state(), o.state()
+    assert (int(t[0]), int(d[0])) == (to, do) or rel_l2(y, yo) > 0           # PLL words identical when the run was bit-exact
+    g.reset(); o.reset()                                                      # resamplers only: the PLL keeps its lock
+    assert _bits_or_close(g(x[:2000]), o(x[:2000]), TOL_E2E)
+
+
+def test_fmstereo_batched(cuda):
+    C, n = 70, 24000
+    x = np.stack([fm_stereo_iq(n, fl=800.0 + 20 * c, fr=1500.0 + 10 * c, seed=c, phase=0.1 * c) for c in range(C)])
+    g = L.FMStereo(channels=C)
+    y = np.concatenate([g(x[:, :10001]), g(x[:, 10001:])], axis=1)
+    assert y.shape == (C, 2 * 1920)
+    for c in (0, 31, 64, 69):
+        o = O.FMStereo()
+        yo = np.concatenate([o(x[c, :10001]), o(x[c, 10001:])])
+        assert _bits_or_close(y[c], yo, TOL_E2E), (c, rel_l2(y[c], yo))
+
+
 # ------------------------------------------------------------------------- 8f row 3: SSBDemod, HilbertTransform
 @pytest.mark.parametrize("band", ["usb", "lsb"])
 def test_ssb_demod(cuda, band):
@@ -307,12 +340,6 @@ def test_hilbert_transform_both_branches(cuda, m):
 
 
 # ------------------------------------------------------------------------- 8f row 3: BroadcastAM
-def _bits_or_close(y, yo, tol=TOL_STAGE):
-    """The PLL branch takes arg() through a double-precision atan2 on both sides; the two math libraries agree after
-    rounding to float except with probability ~1e-8 per sample, so equality is expected and 1e-5 is demanded."""
-    return np.array_equal(y.view(np.uint32), yo.view(np.uint32)) or rel_l2(y, yo) <= tol
-
-
 @pytest.mark.parametrize("m,n", [(25, 30000), (7, 5001), (40, 3000), (64, 777), (25, 5)])
 def test_broadcast_am_single_channel(cuda, m, n):
     x = am_iq(n, fs=48000.0, f_off=35.0, noise=0.01, amp=1.0)

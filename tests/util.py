@@ -38,3 +38,14 @@ def split_points(n, k, rng):
     cuts = sorted(set(int(c) for c in rng.integers(1, n, size=k - 1)))
     edges = [0] + cuts + [n]
     return [(edges[i], edges[i + 1]) for i in range(len(edges) - 1)]
+
+
+def fm_stereo_iq(n, fs=600e3, fl=1000.0, fr=1700.0, dev=75e3, seed=3, noise=0.005, phase=0.0):
+    """Broadcast FM stereo multiplex: L+R, 19 kHz pilot, L-R on the 38 kHz suppressed carrier."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / fs
+    left, right = np.sin(2 * np.pi * fl * t), np.sin(2 * np.pi * fr * t + 0.4)
+    mpx = 0.45 * (left + right) + 0.1 * np.sin(2 * np.pi * 19e3 * t) + 0.45 * (left - right) * np.sin(2 * np.pi * 38e3 * t)
+    x = np.exp(1j * (2 * np.pi * dev / fs * np.cumsum(mpx) + phase))
+    x = x + noise * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    return x.astype(np.complex64)
