@@ -137,16 +137,45 @@ def side_config(args, L, torch, dev, rank, world, barrier, max_over_ranks):
         nco = L.NCO(channels=C); nco.set_frequencies((2 * np.pi * (0.05 + 0.4 * np.arange(C) / 4096)).astype(np.float32)); nco.set_direction(True)
         chain = L.Chain(nco, L.ComplexResampler(0.024, Fc=0.024, channels=C))
         name, out_real = "config3: NCO mix-down + ComplexResampler 2e6->48e3, 4096 channels x 64K blocks", False
-    else:
+    elif args.config == 4:
         C, n, kind, bps = 16384, 65536, 3, 12.0
         chain = L.Chain(L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=C), L.AGC(channels=C), L.FreqDem(0.1, channels=C))
         name, out_real = "config4: ComplexIIRFilter cheby2-8 + AGC + FreqDem, 16384 channels x 64K blocks", True
+    in_real = False
+    if args.next:                                       # the classes either side of the hot path
+        out_real = True
+        if args.next == "bam":
+            C, n, kind, bps = 65536, 65536, 0, 8.096
+            iir, rs, agc, _, de = build_radio(L, C)
+            chain = L.Chain(iir, rs, agc, L.BroadcastAM(25, channels=C), de)
+            name = "8f-3: bandpass + resampler + AGC + BroadcastAM + de-emphasis, 65536 channels x 64K blocks"
+        elif args.next == "ssb":
+            C, n, kind, bps = 1024, 1 << 20, 1, 12.0
+            chain = L.Chain(L.SSBDemod("usb", channels=C)); name = "8f-3: SSBDemod (firhilbf 25, 60 dB), 1024 channels x 1M samples"
+        elif args.next == "fmstereo":
+            C, n, kind, bps = 16384, 65536, 3, 8.64
+            chain = L.Chain(L.FMStereo(channels=C)); name = "8f-4: FMStereo 600 kHz -> 48 kHz stereo, 16384 channels x 64K blocks"
+        elif args.next == "rrrf":
+            C, n, kind, bps, in_real = 65536, 65536, 1, 8.0, True
+            chain = L.Chain(L.RealIIRFilter("cheby2", "lowpass", 8, 0.05, channels=C)); name = "8f-1: RealIIRFilter cheby2-8, 65536 channels x 64K real samples"
+        elif args.next == "cresamp":
+            C, n, kind, bps, out_real = 4096, 65536, 1, 8.64, False
+            chain = L.Chain(L.CResampler(0.08, channels=C)); name = "8f-4: CResampler(0.08), 4096 channels x 64K blocks"
+        elif args.next == "rfir":
+            C, n, kind, bps, in_real = 2048, 1 << 20, 1, 8.0, True
+            chain = L.Chain(L.RealKaiserBessel(63, 0.1, 60.0, channels=C)); name = "8f-1: RealKaiserBessel 63 taps, 2048 channels x 1M real samples"
+        else:
+            raise SystemExit("unknown --next row")
     if args.block != BLOCK:
         n = args.block                      # profiling runs use a shorter block
-    x = torch.empty((C, n), dtype=torch.complex64, device=dev)
+    if in_real:
+        x = torch.randn((C, n), dtype=torch.float32, device=dev)
+    else:
+        x = torch.empty((C, n), dtype=torch.complex64, device=dev)
     cap = chain.out_len(n) + 2
     y = torch.empty((C, cap), dtype=torch.float32 if out_real else torch.complex64, device=dev)
-    L.synth_fill(kind, x.data_ptr(), C, n, channel0=rank * C, stream=stream)
+    if not in_real:
+        L.synth_fill(kind, x.data_ptr(), C, n, channel0=rank * C, stream=stream)
     # inputs smaller than L2 (config 3: 2.1 GB, fine; all are > 126 MB) -- every config streams > L2 per step
     for _ in range(max(args.warmup, 3)):
         chain.execute_dev(x.data_ptr(), n, y.data_ptr(), cap, stream)
@@ -165,7 +194,7 @@ def side_config(args, L, torch, dev, rank, world, barrier, max_over_ranks):
     peak = peaks.get("hbm_gbs", 6650.0)
     val = world * C * n / (ms * 1e-3) / 1e6
     if rank == 0:
-        print(json.dumps({"metric": METRIC.replace("AM-chain", "config %d" % args.config), "value": val, "unit": UNIT, "n_gpus": world,
+        print(json.dumps({"metric": METRIC.replace("AM-chain", args.next or "config %d" % args.config), "value": val, "unit": UNIT, "n_gpus": world,
                           "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": name, "plan": chain.plan(), "l2": "%.1f GB streamed per step, larger than L2" % (C * n * bps / 1e9)},
@@ -185,6 +214,7 @@ def main():
     ap.add_argument("--e2e-channels", type=int, default=8192, help="channels per GPU of the host-buffer (e2e) leg")
     ap.add_argument("--fuse", type=int, default=1, help="chain fusion level (0, 1, 2)")
     ap.add_argument("--block", type=int, default=BLOCK, help="samples per channel per step (profiling runs use a shorter block)")
+    ap.add_argument("--next", default="", help="SURVEY 8(f) side line: bam, ssb, fmstereo, rrrf, cresamp, rfir")
     ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 5 (default, the headline AM receiver), 2 FIR, 3 NCO+resampler, 4 IIR+AGC+FM")
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
@@ -252,7 +282,7 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
                "sample": "%d processes x 1 channel of config 1 (README AMRadio, 64K blocks) for %.0f s each; CPU restatement of liquid-dsp, not liquid-dsp" % (cores, args.cpu_seconds)}
 
-    if args.config != 5:
+    if args.config != 5 or args.next:
         side_config(args, L, torch, dev, rank, world, barrier, max_over_ranks)
         if world > 1:
             dist.destroy_process_group()
