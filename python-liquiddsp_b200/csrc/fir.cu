@@ -34,17 +34,19 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
 // real lane of the same arithmetic.  The firhilbf users (SSBDemod, HilbertTransform) run the two lanes with different
 // taps -- a pure delay in one, the quadrature filter in the other -- and combine them when the tile is written.
 template <bool IN_REAL, bool OUT_REAL>
-__global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntiles, const int ntaps_pad)
+__global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntiles, const int ntaps_pad, const int tpc, const int groups)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int halo = ntaps_pad - 1;
-    float2 *s_x = (float2 *)smem_raw;                                  // phys(TN + halo) samples
-    float2 *s_h = s_x + phys(TN + halo) + 1;                           // ntaps_pad duplicated taps
+    const int bufsz = (phys(TN + halo) + 2) & ~1;                      // float2 slots per staged tile
+    float2 *s_buf = (float2 *)smem_raw;                                // two tiles: one computing, one arriving
+    float2 *s_h = s_buf + 2 * bufsz;                                   // ntaps_pad taps, (in-phase lane, quadrature lane)
 
     const int tid = threadIdx.x;
-    const long long ch = blockIdx.x / ntiles;
-    const long long tile = blockIdx.x % ntiles;
-    const long long t0 = tile * TN;                                    // first output of this CTA
+    // a CTA walks tpc consecutive tiles of one channel: the next tile streams in (cp.async) while this one is computed
+    const long long ch = blockIdx.x / groups;
+    const long long tile_first = (long long)(blockIdx.x % groups) * tpc;
+    const int my_tiles = (int)((ntiles - tile_first) < tpc ? (ntiles - tile_first) : tpc);
     const long long gch = a.ch0 + ch;
     const float2 *xrow = a.x + ch * a.n;
     const float *xrow_r = (const float *)a.x + ch * a.n;
@@ -57,94 +59,141 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
         const float h = k < a.ntaps ? a.taps[k] : 0.f;
         s_h[k] = make_float2(h, a.taps_q ? (k < a.ntaps ? a.taps_q[k] : 0.f) : h);
     }
-    // i advances by NT = 8 * 16 per pass, so its padded position advances by a constant 8 * 17
-    for (int i = tid, pi = phys(tid); i < TN + halo; i += NT, pi += (NT / 16) * 17) {
-        const long long g = t0 - halo + i;                             // global sample index
-        float2 *dst = &s_x[pi];
-        if (g >= 0) {
-            if (g >= a.n) *dst = make_float2(0.f, 0.f);
-            else if (IN_REAL) *dst = lift(xrow_r[g]);
-            else cp_async8(dst, xrow + g);
+    auto stage_tile = [&](long long tile, float2 *s_x) {
+        const long long t0 = tile * TN;
+        if (!IN_REAL && t0 - halo >= 0 && t0 + TN <= a.n) {
+            // interior tile of complex samples: no range checks
+            const float2 *src = xrow + (t0 - halo);
+            for (int i = tid, pi = phys(tid); i < TN + halo; i += NT, pi += (NT / 16) * 17) cp_async8(&s_x[pi], src + i);
+            return;
         }
-        else if (g + nh >= 0) cp_async8(dst, hrow + (g + nh));
-        else *dst = make_float2(0.f, 0.f);
-    }
+        // i advances by NT = 8 * 16 per pass, so its padded position advances by a constant 8 * 17
+        for (int i = tid, pi = phys(tid); i < TN + halo; i += NT, pi += (NT / 16) * 17) {
+            const long long g = t0 - halo + i;                         // global sample index
+            float2 *dst = &s_x[pi];
+            if (g >= 0) {
+                if (g >= a.n) *dst = make_float2(0.f, 0.f);
+                else if (IN_REAL) *dst = lift(xrow_r[g]);
+                else cp_async8(dst, xrow + g);
+            }
+            else if (g + nh >= 0) cp_async8(dst, hrow + (g + nh));
+            else *dst = make_float2(0.f, 0.f);
+        }
+    };
+    stage_tile(tile_first, s_buf);
     cp_async_commit();
 
-    // the last CTA of a channel hands the newest ntaps-1 inputs to the next call
-    if (tile == ntiles - 1) {
+    // the CTA holding a channel's last tile hands the newest ntaps-1 inputs to the next call
+    if (tile_first + my_tiles == ntiles) {
         float2 *ho = a.hist_out + gch * (long long)nh;
         for (int j = tid; j < nh; j += NT) {
             const long long g = a.n - nh + j;
             ho[j] = g >= 0 ? (IN_REAL ? lift(xrow_r[g]) : xrow[g]) : hrow[g + nh];
         }
     }
-    cp_async_wait<0>();
-    __syncthreads();
 
-    // window W[q] holds the sample at logical index ibase + q; output r with tap k = kb + kk reads
-    // logical index o + r + halo - k = ibase + (r - kk + 15) with ibase = o + halo - kb - 15
-    u64 acc[R];
+    for (int tt = 0; tt < my_tiles; tt++) {
+        float2 *s_x = s_buf + (tt & 1) * bufsz;
+        const long long t0 = (tile_first + tt) * TN;                   // first output of this tile
+        if (tt + 1 < my_tiles) stage_tile(tile_first + tt + 1, s_buf + ((tt + 1) & 1) * bufsz);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+
+        // window slot q holds the sample at logical index ibase + q; output r with tap k = kb + kk reads
+        // logical index o + r + halo - k = ibase + (r - kk + 15) with ibase = o + halo - kb - 15
+        u64 acc[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) acc[r] = 0ull;
-    // halo + 1 = ntaps_pad is a multiple of 16 and o = 16 * tid, so ibase = 16 * m with m = tid + ntaps_pad/16 - 1 - kb/16:
-    // the padded position of ibase + q is 17 * m + q + (q >> 4) -- a per-chunk base plus compile-time offsets
-    u64 W[2 * R - 1];
-    const float2 *wb = s_x + 17 * (tid + ntaps_pad / R - 1);
+        for (int r = 0; r < R; r++) acc[r] = 0ull;
+        // halo + 1 = ntaps_pad is a multiple of 16 and o = 16 * tid, so ibase = 16 * m with m = tid + ntaps_pad/16 - 1 - kb/16:
+        // the padded position of ibase + q is 17 * m + q + (q >> 4) -- a per-chunk base plus compile-time offsets.
+        // Two register windows that swap roles every 16 taps: the outputs of a chunk read window slots 0..30, of which
+        // 0..15 are the chunk's own (older) samples and 16..30 are slots 0..14 of the chunk before -- so the previous
+        // chunk's array simply becomes the upper half and nothing is moved.
+        u64 Wa[R], Wb[R];
+        const float2 *wb = s_x + 17 * (tid + ntaps_pad / R - 1);
 #pragma unroll
-    for (int q = 0; q < 2 * R - 1; q++) W[q] = pk(wb[q + (q >> 4)]);
-    for (int kb = 0; kb < ntaps_pad; kb += R) {
+        for (int q = 0; q < R; q++) Wa[q] = pk(wb[q]);
 #pragma unroll
-        for (int kk = 0; kk < R; kk++) {
-            const u64 tap = pk(s_h[kb + kk]);
+        for (int q = 0; q < R - 1; q++) Wb[q] = pk(wb[R + 1 + q]);      // slots 16..30 sit one pad further (q + (q >> 4))
+        auto chunk = [&](const u64 (&lo)[R], const u64 (&hi)[R], int kb) {
 #pragma unroll
-            for (int r = 0; r < R; r++) acc[r] = fma2(tap, W[r - kk + (R - 1)], acc[r]);
-        }
-        if (kb + R < ntaps_pad) {
-            wb -= 17;
+            for (int kk = 0; kk < R; kk += 2) {
+                const float4 t2 = *(const float4 *)&s_h[kb + kk];       // two taps per load
+                const u64 tap0 = pk(t2.x, t2.y), tap1 = pk(t2.z, t2.w);
 #pragma unroll
-            for (int q = 2 * R - 2; q >= R; q--) W[q] = W[q - R];
+                for (int r = 0; r < R; r++) {
+                    const int q = r - kk + (R - 1);
+                    acc[r] = fma2(tap0, q < R ? lo[q] : hi[q - R], acc[r]);
+                }
 #pragma unroll
-            for (int q = 0; q < R; q++) W[q] = pk(wb[q]);
-        }
-    }
-    __syncthreads();
-    const u64 sc = pk(a.scale, a.scale);
+                for (int r = 0; r < R; r++) {
+                    const int q = r - kk - 1 + (R - 1);
+                    acc[r] = fma2(tap1, q < R ? lo[q] : hi[q - R], acc[r]);
+                }
+            }
+        };
+        for (int kb = 0; kb < ntaps_pad; kb += 2 * R) {
+            chunk(Wa, Wb, kb);
+            if (kb + R < ntaps_pad) {
+                wb -= 17;
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-        float2 v = upk(mul2(acc[r], sc));
-        if (a.mode != FIR_PLAIN) {
-            const unsigned long long kabs = a.count + (unsigned long long)(t0 + R * tid + r);
-            const long long kloc = t0 + R * tid + r;
-            if (a.mode == FIR_SSB_LSB) v.x = __fadd_rn(v.x, v.y);
-            else if (a.mode == FIR_SSB_USB) v.x = __fsub_rn(v.x, v.y);
-            else if (a.mode == FIR_C2R) v.x = kabs < (unsigned long long)a.delay ? 0.f : (((kabs - a.delay) & 1ull) ? -v.y : v.y);
-            else {                                                      // FIR_R2C
-                if (kloc == a.zero_at[0] || kloc == a.zero_at[1] || kloc == a.zero_at[2] || kloc == a.zero_at[3]) v.x = 0.f;
-                if (kabs & 1ull) { v.x = -v.x; v.y = -v.y; }
+                for (int q = 0; q < R; q++) Wb[q] = pk(wb[q]);
+                chunk(Wb, Wa, kb + R);
+                if (kb + 2 * R < ntaps_pad) {
+                    wb -= 17;
+#pragma unroll
+                    for (int q = 0; q < R; q++) Wa[q] = pk(wb[q]);
+                }
             }
         }
-        s_x[17 * tid + r] = v;                                                       // phys(16 * tid + r)
-    }
-    __syncthreads();
-    float2 *yrow = a.y + ch * a.n;
-    if (OUT_REAL) {
-        float *yr = (float *)a.y + ch * a.n;
-        for (int i = tid; i < TN; i += NT) { const long long g = t0 + i; if (g < a.n) yr[g] = s_x[phys(i)].x; }
-        return;
-    }
-    const bool vec = ((a.n & 1) == 0) && ((((size_t)a.y) & 15) == 0);
-    if (vec) {
-        // sample pair 2i, 2i+1 sits at padded position 2i + (i >> 3); i advances by NT = 128, the position by 272
-        for (int i = tid, pi = 2 * tid + (tid >> 3); i < TN / 2; i += NT, pi += 2 * NT + NT / 8) {
-            const long long g = t0 + 2 * i;
-            if (g < a.n) {
-                const float2 u = s_x[pi], v = s_x[pi + 1];
-                *(float4 *)(yrow + g) = make_float4(u.x, u.y, v.x, v.y);
+        __syncthreads();                                               // every thread is done reading this tile's samples
+        const u64 sc = pk(a.scale, a.scale);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            float2 v = upk(mul2(acc[r], sc));
+            if (a.mode != FIR_PLAIN) {
+                const unsigned long long kabs = a.count + (unsigned long long)(t0 + R * tid + r);
+                const long long kloc = t0 + R * tid + r;
+                if (a.mode == FIR_SSB_LSB) v.x = __fadd_rn(v.x, v.y);
+                else if (a.mode == FIR_SSB_USB) v.x = __fsub_rn(v.x, v.y);
+                else if (a.mode == FIR_C2R) v.x = kabs < (unsigned long long)a.delay ? 0.f : (((kabs - a.delay) & 1ull) ? -v.y : v.y);
+                else {                                                  // FIR_R2C
+                    if (kloc == a.zero_at[0] || kloc == a.zero_at[1] || kloc == a.zero_at[2] || kloc == a.zero_at[3]) v.x = 0.f;
+                    if (kabs & 1ull) { v.x = -v.x; v.y = -v.y; }
+                }
+            }
+            s_x[17 * tid + r] = v;                                      // phys(16 * tid + r): the tile buffer doubles as output staging
+        }
+        __syncthreads();
+        float2 *yrow = a.y + ch * a.n;
+        if (OUT_REAL) {
+            float *yr = (float *)a.y + ch * a.n;
+            for (int i = tid; i < TN; i += NT) { const long long g = t0 + i; if (g < a.n) yr[g] = s_x[phys(i)].x; }
+        } else {
+            const bool vec = ((a.n & 1) == 0) && ((((size_t)a.y) & 15) == 0);
+            if (vec && t0 + TN <= a.n) {
+                // sample pair 2i, 2i+1 sits at padded position 2i + (i >> 3); i advances by NT = 128, the position by 272
+                float2 *yo = yrow + t0;
+#pragma unroll
+                for (int it = 0; it < TN / 2 / NT; it++) {
+                    const int i = tid + it * NT, pi = 2 * tid + (tid >> 3) + it * (2 * NT + NT / 8);
+                    const float2 u = s_x[pi], v = s_x[pi + 1];
+                    *(float4 *)(yo + 2 * i) = make_float4(u.x, u.y, v.x, v.y);
+                }
+            } else if (vec) {
+                for (int i = tid, pi = 2 * tid + (tid >> 3); i < TN / 2; i += NT, pi += 2 * NT + NT / 8) {
+                    const long long g = t0 + 2 * i;
+                    if (g < a.n) {
+                        const float2 u = s_x[pi], v = s_x[pi + 1];
+                        *(float4 *)(yrow + g) = make_float4(u.x, u.y, v.x, v.y);
+                    }
+                }
+            } else {
+                for (int i = tid; i < TN; i += NT) { const long long g = t0 + i; if (g < a.n) yrow[g] = s_x[phys(i)]; }
             }
         }
-    } else {
-        for (int i = tid; i < TN; i += NT) { const long long g = t0 + i; if (g < a.n) yrow[g] = s_x[phys(i)]; }
+        __syncthreads();                                               // staging slots are free before the tile after next lands here
     }
 }
 
@@ -156,14 +205,20 @@ cudaError_t fir_launch(const FirArgs &a, cudaStream_t stream)
     const int ntaps_pad = (a.ntaps + R - 1) / R * R;
     const int halo = ntaps_pad - 1;
     const long long ntiles = (a.n + TN - 1) / TN;
-    const size_t smem = (size_t)(TN + halo + ((TN + halo) >> 4) + 2 + ntaps_pad) * sizeof(float2);
-    if (smem > 200 * 1024 || ntiles * (long long)a.C > 0x7fffffffLL) return cudaErrorInvalidValue;
+    // consecutive tiles per CTA: as many (up to 8) as still leave ~8 CTAs per SM
+    long long tpc = ntiles * (long long)a.C / (148 * 8);
+    tpc = tpc < 1 ? 1 : (tpc > 8 ? 8 : tpc);
+    if (tpc > ntiles) tpc = ntiles;
+    const long long groups = (ntiles + tpc - 1) / tpc;
+    const size_t bufsz = (size_t)((TN + halo + ((TN + halo) >> 4) + 2) & ~1);
+    const size_t smem = (2 * bufsz + (size_t)ntaps_pad) * sizeof(float2);
+    if (smem > 200 * 1024 || groups * (long long)a.C > 0x7fffffffLL) return cudaErrorInvalidValue;
     const bool in_real = a.real_io || a.in_real, out_real = a.real_io || a.out_real;
     auto fn = in_real ? (out_real ? fir_kernel<true, true> : fir_kernel<true, false>)
                       : (out_real ? fir_kernel<false, true> : fir_kernel<false, false>);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
-    fn<<<(unsigned)(ntiles * a.C), NT, smem, stream>>>(a, (int)ntiles, ntaps_pad);
+    fn<<<(unsigned)(groups * a.C), NT, smem, stream>>>(a, (int)ntiles, ntaps_pad, (int)tpc, (int)groups);
     return cudaGetLastError();
 }
 

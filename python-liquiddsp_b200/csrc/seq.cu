@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     const int cpw = FULL ? 32 : a.cpw, RCTA = (BT / 32) * cpw;     // rows (channels) per CTA
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // the swizzled TMA boxes need 1024-byte alignment
-    unsigned char *smem = TMA ? (unsigned char *)(((size_t)smem_raw + 1023) & ~(size_t)1023) : smem_raw;
+    // (offset arithmetic on the shared symbol, not an integer round trip: the pointers stay in the shared address space)
+    unsigned char *smem = smem_raw;
+    if constexpr (TMA) smem += (1024u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u;
     constexpr int PINS = TMA ? TS * IELEM : PIN;                   // staged row pitch: dense under TMA, padded otherwise
     unsigned char *s_in  = smem;                                   // NST stages of [RCTA][PINS]
     unsigned char *s_out = s_in + NST * RCTA * PINS;               // [RCTA][POUT] when the output is full rate
