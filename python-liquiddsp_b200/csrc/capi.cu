@@ -761,6 +761,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
     // idle lanes would only cost slots)
     const bool light = (g.mask & (F_AGC | F_FM | F_AM)) == 0;
     a.cpw = !light ? 32 : (nch >= 148 * 12 * 32 ? 32 : (nch >= 148 * 12 * 16 ? 16 : 8));
+    if (const char *e = getenv("LQB_CPW")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) a.cpw = (g.mask & F_AM) ? 32 : v; }   // tuning override
     a.out_tmajor = out_tmajor ? 1 : 0; a.out_pitch = out_tmajor ? (long long)nch : (long long)n_out;
     a.vec_in  = ((n * (in_real ? 4 : 8)) % 16 == 0) && (((size_t)x) % 16 == 0);
     a.vec_out = ((n_out * (out_real ? 4 : 8)) % 16 == 0) && (((size_t)y) % 16 == 0);

@@ -94,6 +94,32 @@ __device__ __forceinline__ float2 mix_down(float2 x, float2 sc)
 {
     return make_float2(__fmaf_rn(x.x, sc.y, __fmul_rn(x.y, sc.x)), __fmaf_rn(x.y, sc.y, -__fmul_rn(x.x, sc.x)));
 }
+// atan2f for the feed-forward frequency discriminator (FreqDem): branch-free, ~2 ulp.  The octant is folded to
+// t = min/max in [0, 1]; atan(t) = t + t s P(s), s = t^2, P a degree-7 fit (1.3 ulp on [0, 1]); the quotient is the
+// hardware reciprocal times the numerator.  (The PLL demodulators do not use this: their arg() feeds a loop and is
+// taken correctly rounded.)
+__device__ __forceinline__ float atan2_fast(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float t = __fdividef(mn, mx);
+    t = mx == 0.f ? 0.f : t;
+    const float s = __fmul_rn(t, t);
+    float r = 0x1.7ed1eap-9f;
+    r = __fmaf_rn(r, s, -0x1.0c2bf2p-6f);
+    r = __fmaf_rn(r, s, 0x1.61fdcp-5f);
+    r = __fmaf_rn(r, s, -0x1.3556acp-4f);
+    r = __fmaf_rn(r, s, 0x1.b4e126p-4f);
+    r = __fmaf_rn(r, s, -0x1.230adcp-3f);
+    r = __fmaf_rn(r, s, 0x1.9978f4p-3f);
+    r = __fmaf_rn(r, s, -0x1.5554dcp-2f);
+    r = __fmul_rn(r, s);
+    r = __fmaf_rn(r, t, t);
+    r = ay > ax ? __fsub_rn(1.57079637f, r) : r;
+    r = x < 0.f ? __fsub_rn(3.14159274f, r) : r;
+    return copysignf(r, y);
+}
+
 // exp(a) rounded once to float.  The AGC multiplies its gain by exp(-alpha/2 * ln(y2')) every sample, a
 // factor within a few ulp of 1; a one-ulp bias there (CUDA's expf is allowed two) accumulates to
 // bias/alpha = 1e-5 in the gain.  For the small arguments the loop produces a degree-9 Taylor series in

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             // freqdem_demodulate: arg(conj(r') * r) / (2 pi kf)
             const float re = __fmaf_rn(fm_prev.x, z.x, __fmul_rn(fm_prev.y, z.y));
             const float im = __fmaf_rn(fm_prev.x, z.y, -__fmul_rn(fm_prev.y, z.x));
-            r = __fmul_rn(atan2f(im, re), a.fm.ref);
+            r = __fmul_rn(atan2_fast(im, re), a.fm.ref);
             fm_prev = z;
         }
         if constexpr (IN_REAL) r = z.x;
