@@ -113,6 +113,23 @@ static int log_table_dev(const double2 **out)
     return LQB_OK;
 }
 
+static std::map<int, double *> g_atantab;
+static int atan_table_dev(const double **out)
+{
+    int dev = 0; LQB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    auto it = g_atantab.find(dev);
+    if (it == g_atantab.end()) {
+        std::vector<double> t = design::atan_table();
+        double *d = nullptr;
+        LQB_CUDA(cudaMalloc((void **)&d, t.size() * sizeof(double)));
+        LQB_CUDA(cudaMemcpy(d, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+        it = g_atantab.emplace(dev, d).first;
+    }
+    *out = it->second;
+    return LQB_OK;
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -423,6 +440,7 @@ struct BamStage : lqb_stage_s {
         p.m = m; p.ntaps_pad = ntaps_pad; p.hrev = hrev.p; p.pll_alpha = 0.001f; p.pll_beta = std::sqrt(0.001f);
         for (int s = 0; s < 2; s++) for (int k = 0; k < 3; k++) { p.b[s][k] = B[3 * s + k]; p.a[s][k] = A[3 * s + k]; }
         p.hist = hist.p; p.dcv = dcv.p; p.theta = theta.p; p.dtheta = dtheta.p;
+        LQB_TRY(atan_table_dev(&p.atantab));
         return sincos_table(&p.sincos);
     }
 };
@@ -461,6 +479,7 @@ struct FmstStage : lqb_stage_s {
         p.rs.step = step; p.rs.phase = phase; p.rs.bits = (int)d.bits; p.rs.sublen = (int)d.sublen; p.rs.npfb = (int)d.npfb;
         p.rs.bank = bank.p; p.rs.ring = nullptr; p.rs.count = count; p.rs.variant = 2;
         p.rprime = rprime.p; p.theta = theta.p; p.dtheta = dtheta.p; p.pe = pe.p; p.vL = vL.p; p.vR = vR.p; p.ringL = ringL.p; p.ringR = ringR.p;
+        LQB_TRY(atan_table_dev(&p.atantab));
         return sincos_table(&p.sincos);
     }
 };

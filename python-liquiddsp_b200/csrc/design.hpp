@@ -462,6 +462,19 @@ inline std::vector<double> log_table()
 // radians -> 32-bit phase.  float product with 1/(2 pi) held in double, fractional part in float,
 // scale by 2^32 in float; a fractional part that rounds up to 1.0f wraps to 0 (what the x86-64
 // float -> uint32 conversion of liquid's expression yields).
+// Taylor table for atan2_rn (devmath.cuh): node c_i = i/64, i = 0..64; row i holds atan(c_i) and the coefficients
+// a_k = cos^k(t) sin(k (t + pi/2)) / k, t = atan(c_i), k = 1..7 -- atan(c_i + d) to 2e-18 for |d| <= 1/128
+inline std::vector<double> atan_table()
+{
+    std::vector<double> t(65 * 8);
+    for (int i = 0; i <= 64; i++) {
+        const long double th = atanl((long double)i / 64.0L);
+        t[8 * i] = (double)th;
+        for (int k = 1; k < 8; k++) t[8 * i + k] = (double)(powl(cosl(th), k) * sinl(k * (th + 1.5707963267948966192313216916398L)) / k);
+    }
+    return t;
+}
+
 inline uint32_t nco_constrain(float theta)
 {
     float p = (float)(theta * 0.159154943091895);

@@ -120,6 +120,29 @@ __device__ __forceinline__ float atan2_fast(float y, float x)
     return copysignf(r, y);
 }
 
+// arg() for the PLL demodulators: atan2 evaluated in double to ~1 ulp(double) and rounded once to float -- the same
+// number as (float)atan2((double)y, (double)x) except when the double result sits within an ulp of a float tie
+// (probability ~1e-8).  The quotient of the smaller by the larger magnitude lands in [0, 1]; the nearest of 65
+// nodes c_i = i/64 supplies atan(c_i) and a degree-7 Taylor expansion around it (table in shared memory, 4160 B).
+// Inline, so independent evaluations overlap; the library routine is a call.
+__device__ __forceinline__ float atan2_rn(float y, float x, const double *__restrict__ tab)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const bool swap = ay > ax;
+    const double mx = (double)(swap ? ay : ax), mn = (double)(swap ? ax : ay);
+    double q = mn / mx;
+    q = mx == 0.0 ? 0.0 : q;
+    const int i = __double2int_rn(q * 64.0);
+    const double d = fma((double)i, -0.015625, q);
+    const double *t = tab + 8 * i;
+    double p = t[7];
+    p = fma(p, d, t[6]); p = fma(p, d, t[5]); p = fma(p, d, t[4]); p = fma(p, d, t[3]);
+    p = fma(p, d, t[2]); p = fma(p, d, t[1]); p = fma(p, d, t[0]);
+    p = swap ? 1.5707963267948966 - p : p;
+    p = __float_as_int(x) < 0 ? 3.141592653589793 - p : p;
+    return copysignf((float)p, y);
+}
+
 // exp(a) rounded once to float.  The AGC multiplies its gain by exp(-alpha/2 * ln(y2')) every sample, a
 // factor within a few ulp of 1; a one-ulp bias there (CUDA's expf is allowed two) accumulates to
 // bias/alpha = 1e-5 in the gain.  For the small arguments the loop produces a degree-9 Taylor series in

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
     float *s_R   = s_L + L * BT;
     float *s_b   = s_R + L * BT;                                  // bank [npfb][L]
     float *s_sin = s_b + ((a.p.rs.npfb * L + 3) & ~3);            // [1024]
+    double *s_at = (double *)(s_sin + 1024);                      // [65][8] atan2_rn table
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const long long chl = (long long)blockIdx.x * BT + tid;
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
     const long long gch = a.ch0 + (active ? chl : 0), CT = a.Ctot, N = a.n;
 
     for (int i = tid; i < 1024; i += BT) s_sin[i] = a.p.sincos[i].x;
+    for (int i = tid; i < 65 * 8; i += BT) s_at[i] = a.p.atantab[i];
     for (int i = tid; i < a.p.rs.npfb * L; i += BT) s_b[i] = a.p.rs.bank[i];
     for (int i = 0; i < L; i++) { s_L[i * BT + tid] = a.p.ringL[i * CT + gch]; s_R[i * BT + tid] = a.p.ringR[i * CT + gch]; }
     float2 prev = a.p.rprime[gch];
@@ -76,20 +78,26 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
-        const unsigned char *row = s_in + stage * (BT * PITCH) + tid * PITCH;
+        unsigned char *row = s_in + stage * (BT * PITCH) + tid * PITCH;
         const int nv = (int)((N - t * TS) < TS ? (N - t * TS) : TS);
-#pragma unroll 1
-        for (int j = 0; j < nv; j++) {
+        // the discriminator has no feedback: its 16 arguments are independent work, done ahead of the PLL loop (the
+        // result replaces the sample in the thread's own staged row)
+#pragma unroll 4
+        for (int j = 0; j < TS; j++) {
             const float2 z = *(const float2 *)(row + j * 8);
             // freqdem_demodulate: arg(conj(r') r) / (2 pi kf), the argument taken correctly rounded
             const float re = __fmaf_rn(prev.x, z.x, __fmul_rn(prev.y, z.y));
             const float im = __fmaf_rn(prev.x, z.y, -__fmul_rn(prev.y, z.x));
-            const float s = __fmul_rn((float)atan2((double)im, (double)re), a.p.ref);
-            prev = z;
+            *(float *)(row + j * 8) = __fmul_rn(atan2_rn(im, re, s_at), a.p.ref);
+            if (j < nv) prev = z;
+        }
+#pragma unroll 1
+        for (int j = 0; j < nv; j++) {
+            const float s = *(const float *)(row + j * 8);
             const unsigned idx = nco_index(theta);
             const float2 osc = make_float2(s_sin[idx], s_sin[(idx + 256) & 0x3ffu]);
             float2 sc = mix_down(make_float2(s, 0.f), osc);
-            const float arg = (float)atan2((double)sc.y, (double)sc.x);
+            const float arg = atan2_rn(sc.y, sc.x, s_at);
             pe = (float)fma(0.999, (double)pe, 0.001 * (double)arg);
             sc = mix_down(sc, osc);
             dtheta += nco_constrain_dev(__fmul_rn(pe, a.p.pll_alpha));
@@ -133,7 +141,7 @@ cudaError_t fmstereo_launch(const FmstArgs &a, cudaStream_t stream)
     const int L = a.p.rs.sublen;
     if (L < 1 || L > kFmstMaxSub || a.p.rs.step < (1u << 24)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)2 * BT * PITCH + (size_t)2 * L * BT * sizeof(float) + (size_t)((a.p.rs.npfb * L + 3) & ~3) * sizeof(float)
-                      + 1024 * sizeof(float);
+                      + 1024 * sizeof(float) + 65 * 8 * sizeof(double);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fmstereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     fmstereo_kernel<<<(unsigned)((a.C + BT - 1) / BT), BT, smem, stream>>>(a);

@@ -107,6 +107,7 @@ struct AmTailArgs {
 constexpr int kBamMaxM = 64;
 struct BamP {
     int m, ntaps_pad;              // lowpass taps padded (leading zeros) to a multiple of 8
+    const double *atantab;         // [65][8] table of atan2_rn
     const float *hrev;             // [ntaps_pad] taps in window order: hrev[i] multiplies the sample (ntaps_pad-1-i) steps old
     float pll_alpha, pll_beta;
     float b[2][3], a[2][3];        // DC-block sections (iirfilt_rrrf, SOS)
@@ -130,6 +131,7 @@ struct FmstP {
     float ref;                     // freqdem: 1 / (2 pi kf)
     float pll_alpha, pll_beta;
     float b0, a1;                  // de-emphasis: v0 = x - a1 v1, y = b0 v0
+    const double *atantab;         // [65][8] table of atan2_rn
     const float2 *sincos;
     ResampP rs;                    // step, phase, bits, sublen, npfb, bank, count (ring unused)
     float2 *rprime;                // [Ctot] previous input sample
