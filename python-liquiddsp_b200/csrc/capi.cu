@@ -515,6 +515,7 @@ struct lqb_chain_s {
     static constexpr int kStreams = 3;
     cudaStream_t streams[kStreams] = { nullptr, nullptr, nullptr };
     lqb::DevArr<char> h_in[kStreams], h_out[kStreams], h_tmp[kStreams][2], h_cvt[kStreams];
+    cudaEvent_t ev_ready[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr };   // time-sliced host pipeline
     // device-execute scratch
     lqb::DevArr<char> d_tmp[2], d_cvt;
     // optional per-segment timing of execute_dev: one event pair per segment per call, on the caller's stream
@@ -525,7 +526,12 @@ struct lqb_chain_s {
         for (auto &call : timed_calls) for (auto &p : call) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
         timed_calls.clear();
     }
-    ~lqb_chain_s() { clear_timing(); for (auto &s : streams) if (s) cudaStreamDestroy(s); }
+    ~lqb_chain_s()
+    {
+        clear_timing();
+        for (auto &s : streams) if (s) cudaStreamDestroy(s);
+        for (int b = 0; b < 2; b++) { if (ev_ready[b]) cudaEventDestroy(ev_ready[b]); if (ev_free[b]) cudaEventDestroy(ev_free[b]); }
+    }
 };
 
 lqb_stage_s::~lqb_stage_s() { delete self_chain; }
@@ -893,6 +899,55 @@ static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, s
     return LQB_OK;
 }
 
+// Host-pointer call, large input, decimating chain: the block is cut along TIME.  Every slice carries all channels
+// (so the kernels run at full occupancy and a slice's kernels take a fraction of the call's), slice k+1 crosses PCIe
+// (one strided 2-D copy from the caller's rows) while slice k is processed, the stages carry their state from slice
+// to slice exactly as they do from call to call, and the small output collects on the device and goes back once.
+// What stays exposed behind the H2D stream is one slice's kernels instead of a whole channel group's recurrence.
+static int chain_execute_host_sliced(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, size_t n, void *y, size_t on_total,
+                                     bool in_i16, size_t ib, size_t ob, bool need_cvt)
+{
+    const int C = c->stages[0]->C;
+    size_t nsl = 16;
+    if (const char *e = getenv("LQB_SLICES")) { const int v = atoi(e); if (v >= 1 && v <= 64) nsl = (size_t)v; }
+    size_t slice = ((n + nsl - 1) / nsl + 255) / 256 * 256;
+    slice = std::max<size_t>(slice, 4096);
+    for (int s = 0; s < 2; s++) if (!c->streams[s]) LQB_CUDA(cudaStreamCreate(&c->streams[s]));
+    for (int b = 0; b < 2; b++) {
+        if (!c->ev_ready[b]) LQB_CUDA(cudaEventCreateWithFlags(&c->ev_ready[b], cudaEventDisableTiming));
+        if (!c->ev_free[b]) LQB_CUDA(cudaEventCreateWithFlags(&c->ev_free[b], cudaEventDisableTiming));
+        LQB_TRY(c->h_in[b].reserve((size_t)C * slice * ib));
+    }
+    cudaStream_t copy = c->streams[0], comp = c->streams[1];
+    const size_t tmpb = max_intermediate_bytes(segs, slice, (size_t)C);
+    if (segs.size() > 1) LQB_TRY(c->h_tmp[0][0].reserve(tmpb));
+    if (segs.size() > 2) LQB_TRY(c->h_tmp[0][1].reserve(tmpb));
+    if (need_cvt) LQB_TRY(c->h_cvt[0].reserve((size_t)C * slice * 8));
+    LQB_TRY(c->h_out[0].reserve(std::max<size_t>(16, (size_t)C * on_total * ob)));
+    size_t on_max = 0; { size_t v; chain_out_len(c, slice, &v); on_max = v + 4 * c->stages.size() + 16; }
+    LQB_TRY(c->h_out[1].reserve(std::max<size_t>(16, (size_t)C * on_max * ob)));
+    size_t off = 0; int k = 0;
+    for (size_t t0 = 0; t0 < n; t0 += slice, k++) {
+        const size_t ns = std::min(slice, n - t0);
+        const int b = k & 1;
+        if (k >= 2) LQB_CUDA(cudaStreamWaitEvent(copy, c->ev_free[b], 0));
+        LQB_CUDA(cudaMemcpy2DAsync(c->h_in[b].p, ns * ib, (const char *)x + t0 * ib, n * ib, ns * ib, (size_t)C, cudaMemcpyHostToDevice, copy));
+        LQB_CUDA(cudaEventRecord(c->ev_ready[b], copy));
+        LQB_CUDA(cudaStreamWaitEvent(comp, c->ev_ready[b], 0));
+        size_t on_k; chain_out_len(c, ns, &on_k);
+        if (on_k > on_max || off + on_k > on_total) return fail(LQB_ESIZE, "internal: slice produced %zu samples, expected at most %zu", on_k, on_max);
+        LQB_TRY(run_all(c, segs, c->h_in[b].p, c->h_out[1].p, ns, 0, C, c->h_tmp[0][0].p, c->h_tmp[0][1].p, comp, &c->last_launches, false, in_i16, c->h_cvt[0].p));
+        LQB_CUDA(cudaEventRecord(c->ev_free[b], comp));
+        if (on_k) LQB_CUDA(cudaMemcpy2DAsync(c->h_out[0].p + off * ob, on_total * ob, c->h_out[1].p, on_k * ob, on_k * ob, (size_t)C, cudaMemcpyDeviceToDevice, comp));
+        advance_all(c, ns);
+        off += on_k;
+    }
+    LQB_CUDA(cudaStreamSynchronize(comp));
+    if (off != on_total) return fail(LQB_ESIZE, "internal: slices produced %zu samples, the call %zu", off, on_total);
+    if (on_total) LQB_CUDA(cudaMemcpy(y, c->h_out[0].p, (size_t)C * on_total * ob, cudaMemcpyDeviceToHost));
+    return LQB_OK;
+}
+
 static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, size_t cap, size_t *n_out, bool in_i16 = false)
 {
     LQB_TRY(chain_validate(c));
@@ -907,6 +962,18 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
     const int C = c->stages[0]->C;
     const size_t ib = in_i16 ? 4 : elem_bytes(c->stages.front()->in_real()), ob = elem_bytes(c->stages.back()->out_real());
     const bool need_cvt = in_i16 && !first_takes_i16(segs);
+    {
+        // time slices when the call is big, decimates (output fits the device-side collection buffer) and no stage
+        // gives meaning to call boundaries (blocked-scan IIR sizes its blocks per call; HilbertTransform's real branch
+        // reproduces the reference's per-call overrun)
+        bool sliceable = (size_t)C * n * ib >= ((size_t)32 << 20) && n >= 32768 && (size_t)C * on * ob <= ((size_t)256 << 20) && on * 4 <= n;
+        for (auto *st : c->stages) {
+            if (st->kind == K_IIR && static_cast<IirStage *>(st)->mode == 2) sliceable = false;
+            if (st->kind == K_FIR && static_cast<FirStage *>(st)->mode == FIR_R2C) sliceable = false;
+        }
+        if (const char *e = getenv("LQB_HOST_MODE")) sliceable = sliceable && strcmp(e, "chunk") != 0;
+        if (sliceable) return chain_execute_host_sliced(c, segs, x, n, y, on, in_i16, ib, ob, need_cvt);
+    }
     // Channel chunks on three streams: the H2D of chunk i+1 overlaps the kernels of chunk i.  A sequential
     // kernel takes about as long for 64 channels as for 64K (it is bound by the per-channel recurrence), so
     // chunks are few and large: an eighth of the call, at least 64 MB of input.

@@ -780,3 +780,24 @@ def test_execute_dev_and_chunked_host_agree(cuda):
     y2 = yb.download((C, got), np.float32)
     assert got == n_out == y1.shape[1]
     assert np.array_equal(y1.view(np.uint32), y2.view(np.uint32))
+
+
+def test_host_call_time_sliced_equals_channel_chunked(cuda, monkeypatch):
+    """Large host-pointer calls are pipelined in time slices (all channels per slice, state carried between slices);
+    the older channel-chunk pipeline must give the same bits -- c64 and int16 input."""
+    C, n = 192, 65536 + 4096
+    x = np.stack([am_iq(n, f_off=50.0 + c, phase=0.01 * c, seed=c % 7) for c in range(C)])
+    iq16 = np.empty((C, n, 2), np.int16)
+    iq16[..., 0] = np.clip(np.round(x.real * 20000), -32767, 32767); iq16[..., 1] = np.clip(np.round(x.imag * 20000), -32767, 32767)
+    outs = {}
+    for mode in ("slice", "chunk"):
+        monkeypatch.setenv("LQB_HOST_MODE", mode)
+        st = (L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=C), L.ComplexResampler(0.024, Fc=0.024, channels=C), L.AGC(channels=C),
+              L.AmpModem(0.5, "dsb", True, channels=C), L.DeemphasisFilter(48000, channels=C))
+        st[2].scale = 0.01
+        ch = L.Chain(*st)
+        a = ch(x); b = ch(x[:, :40000])                         # second call: carried state after a sliced call
+        ch.reset()
+        outs[mode] = (a, b, ch(iq16.reshape(C, 2 * n)))
+    for u, v in zip(outs["slice"], outs["chunk"]):
+        assert u.shape == v.shape and np.array_equal(u.view(np.uint32), v.view(np.uint32))
