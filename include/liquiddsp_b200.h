@@ -183,8 +183,8 @@ int lqb_agc_take_rise_count(lqb_stage s, unsigned *count);       /* RISE transit
 
 /* ---------------- ampmodem : AmpModem, demod.hpp:228-307 ------------------------------------
  * replaces ampmodem_create(mod, type, suppressed) (:305), ampmodem_demodulate_block (:294),
- * ampmodem_reset (:287).  complex in -> real out.  Built scope: DSB, carrier present (PLL) and
- * suppressed (Costas); USB/LSB return LQB_ENOTIMPL. */
+ * ampmodem_reset (:287).  complex in -> real out.  DSB with carrier (PLL) or suppressed (Costas); USB / LSB
+ * suppressed (Hilbert pair, 0.5 * side-band / mod_index) or with carrier (carrier loop, Hilbert pair, DC blocker). */
 int lqb_ampmodem_create(float mod_index, int type, int suppressed_carrier, int n_channels, lqb_stage *out);
 int lqb_ampmodem_get_taps(lqb_stage s, float *lowpass, int *n_lowpass, float *dcblock, int *n_dcblock);
 int lqb_ampmodem_get_nco_u32(lqb_stage s, uint32_t *theta, uint32_t *d_theta, int n);

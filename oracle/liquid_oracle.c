@@ -977,6 +977,76 @@ unsigned orc_wrap_agc_execute(orc_agc q, const orc_cf *x, unsigned n, orc_cf *y,
 }
 
 /* ==========================================================================================
+ *  firhilbf    liquid: src/filter/src/firhilb.proto.c (>= 1.3.2: four windows, toggle, two-output c2r)
+ *  reached from: SSBDemod (demod.hpp:163 create(25, 60), :181/:184 c2r_execute), HilbertTransform
+ *  (utility.hpp:79-80 create, :93 interp_execute, :101 decim_execute)
+ *  Half-band Kaiser prototype of 4m+1 taps, modulated by sin(pi t / 2); the 2m odd-offset taps, reversed,
+ *  form the quadrature branch; the in-phase branch is a pure delay.
+ * ======================================================================================== */
+struct orc_firhilbf_s { unsigned m, L; float *hq; float *w[4]; unsigned wi[4]; unsigned toggle; };
+
+orc_firhilbf orc_firhilbf_create(unsigned m, float as)
+{
+    if (m < 2) return NULL;
+    orc_firhilbf q = calloc(1, sizeof *q);
+    unsigned h_len = 4 * m + 1, i, j = 0;
+    q->m = m; q->L = 2 * m;
+    float *h = malloc(h_len * sizeof(float));
+    orc_firdes_kaiser(h_len, 0.25f, fabsf(as), 0.0f, h);
+    for (i = 0; i < h_len; i++) {
+        float t = (float)i - (float)(h_len - 1) / 2.0f;
+        h[i] = h[i] * sinf((float)(0.5f * M_PI * t));          /* imag(h[i] * cexpf(j 0.5 pi t)) */
+    }
+    q->hq = malloc(q->L * sizeof(float));
+    for (i = 1; i < h_len; i += 2) q->hq[j++] = h[h_len - i - 1];
+    free(h);
+    for (i = 0; i < 4; i++) q->w[i] = calloc(2 * q->L, sizeof(float));
+    return q;
+}
+void orc_firhilbf_destroy(orc_firhilbf q) { if (!q) return; free(q->hq); for (int i = 0; i < 4; i++) free(q->w[i]); free(q); }
+void orc_firhilbf_reset(orc_firhilbf q)
+{
+    for (int i = 0; i < 4; i++) { memset(q->w[i], 0, 2 * q->L * sizeof(float)); q->wi[i] = 0; }
+    q->toggle = 0;
+}
+unsigned orc_firhilbf_get_hq(orc_firhilbf q, float *hq) { memcpy(hq, q->hq, q->L * sizeof(float)); return q->L; }
+static void hw_push(orc_firhilbf q, int k, float x) { q->w[k][q->wi[k]] = q->w[k][q->wi[k] + q->L] = x; q->wi[k] = (q->wi[k] + 1) % q->L; }
+static const float *hw_read(orc_firhilbf q, int k) { return q->w[k] + q->wi[k]; }     /* oldest first */
+static float hw_dot(orc_firhilbf q, const float *r) { float s = 0.0f; for (unsigned i = 0; i < q->L; i++) s = FMA(q->hq[i], r[i], s); return s; }
+
+void orc_firhilbf_r2c_execute(orc_firhilbf q, float x, orc_cf *y)
+{
+    float yi, yq;
+    if (q->toggle == 0) { hw_push(q, 0, x); yi = hw_read(q, 0)[q->m - 1]; yq = hw_dot(q, hw_read(q, 1)); }
+    else                { hw_push(q, 1, x); yi = hw_read(q, 1)[q->m - 1]; yq = hw_dot(q, hw_read(q, 0)); }
+    q->toggle = 1 - q->toggle;
+    y->re = yi; y->im = yq;
+}
+void orc_firhilbf_c2r_execute(orc_firhilbf q, orc_cf x, float *y_lsb, float *y_usb)
+{
+    float yi, yq;
+    if (q->toggle == 0) { hw_push(q, 0, x.re); hw_push(q, 1, x.im); yi = hw_read(q, 0)[q->m - 1]; yq = hw_dot(q, hw_read(q, 3)); }
+    else                { hw_push(q, 2, x.re); hw_push(q, 3, x.im); yi = hw_read(q, 2)[q->m - 1]; yq = hw_dot(q, hw_read(q, 1)); }
+    q->toggle = 1 - q->toggle;
+    *y_lsb = yi + yq; *y_usb = yi - yq;
+}
+void orc_firhilbf_decim_execute(orc_firhilbf q, const float *x, orc_cf *y)
+{
+    float yi, yq;
+    hw_push(q, 1, x[0]); yq = hw_dot(q, hw_read(q, 1));
+    hw_push(q, 0, x[1]); yi = hw_read(q, 0)[q->m - 1];
+    if (q->toggle) { y->re = -yi; y->im = -yq; } else { y->re = yi; y->im = yq; }
+    q->toggle = 1 - q->toggle;
+}
+void orc_firhilbf_interp_execute(orc_firhilbf q, orc_cf x, float *y)
+{
+    float vr = q->toggle ? -x.re : x.re, vi = q->toggle ? -x.im : x.im;
+    hw_push(q, 0, vi); y[0] = hw_read(q, 0)[q->m - 1];
+    hw_push(q, 1, vr); y[1] = hw_dot(q, hw_read(q, 1));
+    q->toggle = 1 - q->toggle;
+}
+
+/* ==========================================================================================
  *  ampmodem (DSB)    liquid: src/modem/src/ampmodem.c, src/buffer/src/wdelay.proto.c
  *  reached from: AmpModem (demod.hpp:294 demodulate_block, :305 create)
  *  constants of ampmodem_create (liquid >= 1.4): m = 25, PLL bandwidth 0.001, lowpass
@@ -985,12 +1055,12 @@ unsigned orc_wrap_agc_execute(orc_agc q, const orc_cf *x, unsigned n, orc_cf *y,
  * ======================================================================================== */
 struct orc_ampmodem_s {
     float mod_index; int type, suppressed; unsigned m;
-    orc_nco mixer; orc_firfilt dcblock, lowpass;
+    orc_nco mixer; orc_firfilt dcblock, lowpass; orc_firhilbf hilbert;     /* hilbert: USB / LSB only */
     float *dr, *di; unsigned dlen, dpos;     /* wdelaycf(m): buffer of m+1 */
 };
 orc_ampmodem orc_ampmodem_create(float mod_index, int type, int suppressed)
 {
-    if (type != ORC_AMPMODEM_DSB) return NULL;      /* USB/LSB (Hilbert path): SURVEY 8f row 3 */
+    if (type != ORC_AMPMODEM_DSB && type != ORC_AMPMODEM_USB && type != ORC_AMPMODEM_LSB) return NULL;
     orc_ampmodem q = calloc(1, sizeof *q);
     q->mod_index = mod_index; q->type = type; q->suppressed = suppressed; q->m = 25;
     q->mixer = orc_nco_create(ORC_NCO);
@@ -998,17 +1068,19 @@ orc_ampmodem orc_ampmodem_create(float mod_index, int type, int suppressed)
     q->dcblock = orc_firfilt_create_dc_blocker(25, 20.0f);
     q->lowpass = orc_firfilt_create_kaiser(2 * q->m + 1, 0.01f, 40.0f, 0.0f);
     q->dlen = q->m + 1; q->dr = calloc(q->dlen, sizeof(float)); q->di = calloc(q->dlen, sizeof(float));
+    q->hilbert = orc_firhilbf_create(q->m, 60.0f);          /* firhilbf_create(m, 60): single side-band recovery */
     return q;
 }
 void orc_ampmodem_destroy(orc_ampmodem q)
 {
     if (!q) return;
+    orc_firhilbf_destroy(q->hilbert);
     orc_nco_destroy(q->mixer); orc_firfilt_destroy(q->dcblock); orc_firfilt_destroy(q->lowpass);
     free(q->dr); free(q->di); free(q);
 }
 void orc_ampmodem_reset(orc_ampmodem q)
 {
-    orc_nco_reset(q->mixer); orc_firfilt_reset(q->dcblock); orc_firfilt_reset(q->lowpass);
+    orc_nco_reset(q->mixer); orc_firfilt_reset(q->dcblock); orc_firfilt_reset(q->lowpass); orc_firhilbf_reset(q->hilbert);
     memset(q->dr, 0, q->dlen * sizeof(float)); memset(q->di, 0, q->dlen * sizeof(float)); q->dpos = 0;
 }
 unsigned orc_ampmodem_get_lowpass_taps(orc_ampmodem q, float *h) { return orc_firfilt_get_taps(q->lowpass, h); }
@@ -1039,8 +1111,36 @@ static float ampmodem_demod_dsb_pll_costas(orc_ampmodem q, orc_cf x)
     orc_nco_step(q->mixer);
     return v.re / q->mod_index;
 }
+/* ampmodem_demod_ssb: Hilbert pair, then 0.5 * side-band / mod_index */
+static float ampmodem_demod_ssb(orc_ampmodem q, orc_cf x)
+{
+    float m_lsb, m_usb;
+    orc_firhilbf_c2r_execute(q->hilbert, x, &m_lsb, &m_usb);
+    return 0.5f * (q->type == ORC_AMPMODEM_USB ? m_usb : m_lsb) / q->mod_index;
+}
+/* ampmodem_demod_ssb_pll_carrier: the DSB carrier loop, then the Hilbert pair on the mixed-down delayed branch,
+ * then the DC blocker */
+static float ampmodem_demod_ssb_pll_carrier(orc_ampmodem q, orc_cf x)
+{
+    orc_cf x0, x1, v0, v1; float y, m_lsb, m_usb;
+    orc_firfilt_crcf_push(q->lowpass, x); orc_firfilt_crcf_execute(q->lowpass, &x0);
+    q->dr[q->dpos] = x.re; q->di[q->dpos] = x.im; q->dpos = (q->dpos + 1) % q->dlen;
+    x1.re = q->dr[q->dpos]; x1.im = q->di[q->dpos];
+    orc_nco_mix_down(q->mixer, x0, &v0);
+    orc_nco_mix_down(q->mixer, x1, &v1);
+    orc_nco_pll_step(q->mixer, v0.im);
+    orc_nco_step(q->mixer);
+    orc_firhilbf_c2r_execute(q->hilbert, v1, &m_lsb, &m_usb);
+    float m = 0.5f * (q->type == ORC_AMPMODEM_USB ? m_usb : m_lsb) / q->mod_index;
+    orc_firfilt_rrrf_push(q->dcblock, m); orc_firfilt_rrrf_execute(q->dcblock, &y);
+    return y;
+}
 void orc_ampmodem_demodulate_block(orc_ampmodem q, const orc_cf *x, unsigned n, float *y)
 {
+    if (q->type != ORC_AMPMODEM_DSB) {
+        for (unsigned i = 0; i < n; i++) y[i] = q->suppressed ? ampmodem_demod_ssb(q, x[i]) : ampmodem_demod_ssb_pll_carrier(q, x[i]);
+        return;
+    }
     for (unsigned i = 0; i < n; i++)
         y[i] = q->suppressed ? ampmodem_demod_dsb_pll_costas(q, x[i]) : ampmodem_demod_dsb_pll_carrier(q, x[i]);
 }
@@ -1148,76 +1248,6 @@ void orc_wrap_bam_execute(orc_bam q, const orc_cf *x, unsigned n, float *y)
         orc_iirfilt_crcf_execute_block(q->dcblock, &in, 1, &out);
         y[i] = out.re;
     }
-}
-
-/* ==========================================================================================
- *  firhilbf    liquid: src/filter/src/firhilb.proto.c (>= 1.3.2: four windows, toggle, two-output c2r)
- *  reached from: SSBDemod (demod.hpp:163 create(25, 60), :181/:184 c2r_execute), HilbertTransform
- *  (utility.hpp:79-80 create, :93 interp_execute, :101 decim_execute)
- *  Half-band Kaiser prototype of 4m+1 taps, modulated by sin(pi t / 2); the 2m odd-offset taps, reversed,
- *  form the quadrature branch; the in-phase branch is a pure delay.
- * ======================================================================================== */
-struct orc_firhilbf_s { unsigned m, L; float *hq; float *w[4]; unsigned wi[4]; unsigned toggle; };
-
-orc_firhilbf orc_firhilbf_create(unsigned m, float as)
-{
-    if (m < 2) return NULL;
-    orc_firhilbf q = calloc(1, sizeof *q);
-    unsigned h_len = 4 * m + 1, i, j = 0;
-    q->m = m; q->L = 2 * m;
-    float *h = malloc(h_len * sizeof(float));
-    orc_firdes_kaiser(h_len, 0.25f, fabsf(as), 0.0f, h);
-    for (i = 0; i < h_len; i++) {
-        float t = (float)i - (float)(h_len - 1) / 2.0f;
-        h[i] = h[i] * sinf((float)(0.5f * M_PI * t));          /* imag(h[i] * cexpf(j 0.5 pi t)) */
-    }
-    q->hq = malloc(q->L * sizeof(float));
-    for (i = 1; i < h_len; i += 2) q->hq[j++] = h[h_len - i - 1];
-    free(h);
-    for (i = 0; i < 4; i++) q->w[i] = calloc(2 * q->L, sizeof(float));
-    return q;
-}
-void orc_firhilbf_destroy(orc_firhilbf q) { if (!q) return; free(q->hq); for (int i = 0; i < 4; i++) free(q->w[i]); free(q); }
-void orc_firhilbf_reset(orc_firhilbf q)
-{
-    for (int i = 0; i < 4; i++) { memset(q->w[i], 0, 2 * q->L * sizeof(float)); q->wi[i] = 0; }
-    q->toggle = 0;
-}
-unsigned orc_firhilbf_get_hq(orc_firhilbf q, float *hq) { memcpy(hq, q->hq, q->L * sizeof(float)); return q->L; }
-static void hw_push(orc_firhilbf q, int k, float x) { q->w[k][q->wi[k]] = q->w[k][q->wi[k] + q->L] = x; q->wi[k] = (q->wi[k] + 1) % q->L; }
-static const float *hw_read(orc_firhilbf q, int k) { return q->w[k] + q->wi[k]; }     /* oldest first */
-static float hw_dot(orc_firhilbf q, const float *r) { float s = 0.0f; for (unsigned i = 0; i < q->L; i++) s = FMA(q->hq[i], r[i], s); return s; }
-
-void orc_firhilbf_r2c_execute(orc_firhilbf q, float x, orc_cf *y)
-{
-    float yi, yq;
-    if (q->toggle == 0) { hw_push(q, 0, x); yi = hw_read(q, 0)[q->m - 1]; yq = hw_dot(q, hw_read(q, 1)); }
-    else                { hw_push(q, 1, x); yi = hw_read(q, 1)[q->m - 1]; yq = hw_dot(q, hw_read(q, 0)); }
-    q->toggle = 1 - q->toggle;
-    y->re = yi; y->im = yq;
-}
-void orc_firhilbf_c2r_execute(orc_firhilbf q, orc_cf x, float *y_lsb, float *y_usb)
-{
-    float yi, yq;
-    if (q->toggle == 0) { hw_push(q, 0, x.re); hw_push(q, 1, x.im); yi = hw_read(q, 0)[q->m - 1]; yq = hw_dot(q, hw_read(q, 3)); }
-    else                { hw_push(q, 2, x.re); hw_push(q, 3, x.im); yi = hw_read(q, 2)[q->m - 1]; yq = hw_dot(q, hw_read(q, 1)); }
-    q->toggle = 1 - q->toggle;
-    *y_lsb = yi + yq; *y_usb = yi - yq;
-}
-void orc_firhilbf_decim_execute(orc_firhilbf q, const float *x, orc_cf *y)
-{
-    float yi, yq;
-    hw_push(q, 1, x[0]); yq = hw_dot(q, hw_read(q, 1));
-    hw_push(q, 0, x[1]); yi = hw_read(q, 0)[q->m - 1];
-    if (q->toggle) { y->re = -yi; y->im = -yq; } else { y->re = yi; y->im = yq; }
-    q->toggle = 1 - q->toggle;
-}
-void orc_firhilbf_interp_execute(orc_firhilbf q, orc_cf x, float *y)
-{
-    float vr = q->toggle ? -x.re : x.re, vi = q->toggle ? -x.im : x.im;
-    hw_push(q, 0, vi); y[0] = hw_read(q, 0)[q->m - 1];
-    hw_push(q, 1, vr); y[1] = hw_dot(q, hw_read(q, 1));
-    q->toggle = 1 - q->toggle;
 }
 
 /* SSBDemod::execute, demod.hpp:172-186 */

@@ -30,7 +30,9 @@ constexpr int NG = 2;                // groups between window slides
 constexpr int H  = kAmTaps - 1;      // history samples a window needs: 50
 constexpr int W  = H + NG * G;       // window length: 66
 
-template <bool HAS_AGC, bool HAS_DE>
+// OUT_V1 (ampmodem USB / LSB with carrier): the kernel stops after the carrier loop and writes the mixed-down delayed
+// branch v1 as complex samples; the Hilbert pair and the DC blocker are feed-forward and follow as FIR launches
+template <bool HAS_AGC, bool HAS_DE, bool OUT_V1>
 __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ AmTailArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -163,10 +165,12 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
                         const float2 x1 = lw[(H + g - kAmDelay) * BT];
                         const float2 v0 = mix_down(upk(s2[g]), sc), v1 = mix_down(x1, sc);
                         pll(v0.y);
-                        m[g] = __fdiv_rn(v1.x, a.am.mod_index);
+                        if (OUT_V1) { if (active) ((float2 *)a.y)[cl * a.out_pitch + k0 + g] = v1; }
+                        else m[g] = __fdiv_rn(v1.x, a.am.mod_index);
                     }
                     dw[(H + g) * BT] = m[g];
                 }
+                if constexpr (!OUT_V1) {
                 // dc blocker, same blocking
                 float acc[G];
 #pragma unroll
@@ -192,6 +196,7 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
                         for (int g = 0; g < G; g++) if (g < ng) yo[g] = acc[g];
                     }
                 }
+                }   // !OUT_V1
             }
             // slide both windows by the samples consumed
             // (loads in batches ahead of the stores: the source lies above everything a batch writes)
@@ -304,8 +309,10 @@ cudaError_t amtail_launch(bool has_agc, bool has_de, const AmTailArgs &a, cudaSt
         if (rc0 != cudaSuccess) return rc0;
         has_agc = false;
     }
-    AmFn fn = has_agc ? (has_de ? amtail_kernel<true, true> : amtail_kernel<true, false>)
-                      : (has_de ? amtail_kernel<false, true> : amtail_kernel<false, false>);
+    if (a.am.out_v1 && (has_de || a.am.suppressed)) return cudaErrorInvalidValue;
+    AmFn fn = a.am.out_v1 ? (has_agc ? amtail_kernel<true, false, true> : amtail_kernel<false, false, true>)
+            : has_agc ? (has_de ? amtail_kernel<true, true, false> : amtail_kernel<true, false, false>)
+                      : (has_de ? amtail_kernel<false, true, false> : amtail_kernel<false, false, false>);
     const size_t smem = (size_t)W * BT * (sizeof(float2) + sizeof(float)) + 1024 * sizeof(float) + (has_agc ? 128 * sizeof(double2) : 0);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;

@@ -273,6 +273,7 @@ struct FirStage : lqb_stage_s {
     bool real_io = false;                               // firfilt_rrrf
     // firhilbf users: the imaginary lane has its own taps and the epilogue combines the lanes (fir.cu)
     std::vector<float> hlane_q, hq; DevArr<float> taps_q; int mode = FIR_PLAIN, delay = 0; bool in_r = false, out_r = false;
+    float post_div = 0.f;                                                   // ampmodem SSB: (0.5 * side-band) / mod_index
     unsigned long long count = 0; std::vector<unsigned long long> ends;     // samples since reset; ends of recent calls (R2C)
     bool in_real() const override { return real_io || in_r; }
     bool out_real() const override { return real_io || out_r; }
@@ -400,18 +401,31 @@ struct AgcStage : lqb_stage_s {
 struct AmStage : lqb_stage_s {
     float mod = 0.75f; int type = 0, suppressed = 1; std::vector<float> lp, dc; uint32_t count = 0;
     DevArr<float2> lp_ring; DevArr<float> dc_ring; DevArr<uint32_t> theta, dtheta;
+    // USB / LSB: the Hilbert pair (and, with carrier, the DC blocker behind it) are feed-forward filters run by the FIR
+    // kernel; they live here as sub-stages the planner expands into their own segments
+    FirStage *hil = nullptr, *dcb = nullptr;
     AmStage(int c) : lqb_stage_s(K_AM, c) {}
+    ~AmStage() override { delete hil; delete dcb; }
+    bool ssb() const { return type != LQB_AMPMODEM_DSB; }
     int materialize() override
     {
+        if (hil) LQB_TRY(hil->ensure());
+        if (dcb) LQB_TRY(dcb->ensure());
         LQB_TRY(lp_ring.alloc((size_t)kAmRing * C)); LQB_TRY(dc_ring.alloc((size_t)kAmRing * C));
         LQB_TRY(theta.alloc(C)); return dtheta.alloc(C);
     }
-    void host_reset() override { count = 0; }
-    int clear() override { LQB_TRY(lp_ring.zero()); LQB_TRY(dc_ring.zero()); LQB_TRY(theta.zero()); return dtheta.zero(); }
+    void host_reset() override { count = 0; if (hil) hil->host_reset(); if (dcb) dcb->host_reset(); }
+    int clear() override
+    {
+        if (hil && hil->ready) LQB_TRY(hil->clear());
+        if (dcb && dcb->ready) LQB_TRY(dcb->clear());
+        LQB_TRY(lp_ring.zero()); LQB_TRY(dc_ring.zero()); LQB_TRY(theta.zero()); return dtheta.zero();
+    }
     bool out_real() const override { return true; }
-    void advance(size_t n) override { count = (uint32_t)((count + n) % kAmRing); }
+    void advance(size_t n) override { count = (uint32_t)((count + n) % kAmRing); if (hil) hil->advance(n); if (dcb) dcb->advance(n); }
     int fill(AmP &p) const
     {
+        p.out_v1 = ssb() && !suppressed ? 1 : 0;
         p.mod_index = mod; p.pll_alpha = 0.001f; p.pll_beta = std::sqrt(0.001f); p.suppressed = suppressed;
         for (int i = 0; i < kAmTaps; i++) { p.lp[i] = lp[kAmTaps - 1 - i]; p.dc[i] = dc[kAmTaps - 1 - i]; }
         p.lp_ring = lp_ring.p; p.dc_ring = dc_ring.p; p.theta = theta.p; p.dtheta = dtheta.p; p.count = count;
@@ -500,6 +514,7 @@ constexpr int kParChannels = 16384;
 struct Segment {
     enum Type { SEQ, FIR, RESAMP_PAR, AMTAIL, NCO_PAR, BAM, DELAY, FMST } type = SEQ;
     unsigned mask = 0; int nsos = 0, sos0 = 0;
+    int out_real = -1;                         // element type of this segment's output when it is not its last stage's (0 / 1)
     std::vector<lqb_stage_s *> st;
     std::string name;
 };
@@ -582,6 +597,7 @@ static bool run_fusable(const std::vector<lqb_stage_s *> &st, size_t i0, size_t 
         prev = r;
         if (s->kind == K_RESAMP && !static_cast<const ResampStage *>(s)->decimating()) return false;
         if (s->kind == K_IIR && static_cast<const IirStage *>(s)->mode == 2) return false;
+        if (s->kind == K_AM && static_cast<const AmStage *>(s)->ssb()) return false;
         has_rs |= s->kind == K_RESAMP; has_am |= s->kind == K_AM;
     }
     // level 1 keeps the ampmodem's shared-memory windows out of the full-rate kernel: they would cut
@@ -616,10 +632,20 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
                 b.name = "bam[" + nm + "]"; segs.push_back(b); i = j; continue;
             }
         }
+        // ampmodem USB / LSB: [carrier loop ->] Hilbert pair [-> DC blocker], the last two on the FIR kernel
+        if (st[i]->kind == K_AM && static_cast<AmStage *>(st[i])->ssb()) {
+            AmStage *am = static_cast<AmStage *>(st[i]);
+            if (!am->suppressed) {
+                Segment p; p.type = Segment::AMTAIL; p.st = { am }; p.name = "am[carrier-loop]"; p.out_real = 0; segs.push_back(p);
+            }
+            Segment h; h.type = Segment::FIR; h.st = { am->hil }; h.name = "fir[hilbert]"; segs.push_back(h);
+            if (!am->suppressed) { Segment d; d.type = Segment::FIR; d.st = { am->dcb }; d.name = "fir[dcblock]"; segs.push_back(d); }
+            i++; continue;
+        }
         // [AGC ->] ampmodem [-> de-emphasis] : the decimated-rate tail kernel (am.cu)
         if (c->fuse < 2) {
             size_t j = i; std::string nm;
-            if (c->fuse >= 1 && st[j]->kind == K_AGC && j + 1 < st.size() && st[j + 1]->kind == K_AM) { g.st.push_back(st[j++]); nm = "agc+"; }
+            if (c->fuse >= 1 && st[j]->kind == K_AGC && j + 1 < st.size() && st[j + 1]->kind == K_AM && !static_cast<AmStage *>(st[j + 1])->ssb()) { g.st.push_back(st[j++]); nm = "agc+"; }
             if (st[j]->kind == K_AM) {
                 g.type = Segment::AMTAIL; g.st.push_back(st[j++]); nm += "ampmodem";
                 if (c->fuse >= 1 && j < st.size() && st[j]->kind == K_DEEMPH) { g.st.push_back(st[j++]); nm += "+deemph"; }
@@ -727,6 +753,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         a.real_io = f->real_io ? 1 : 0;
         a.in_real = f->in_r ? 1 : 0; a.out_real = f->out_r ? 1 : 0; a.mode = f->mode; a.delay = f->delay; a.count = f->count;
         a.taps_q = f->hlane_q.empty() ? nullptr : f->taps_q.p;
+        a.post_div = f->post_div;
         for (int k = 0; k < 4; k++) a.zero_at[k] = -1;
         if (f->mode == FIR_R2C) {
             int nz = 0;
@@ -869,7 +896,7 @@ static size_t max_intermediate_bytes(const std::vector<Segment> &segs, size_t n,
     size_t worst = 0, cur = n;
     for (size_t k = 0; k + 1 < segs.size(); k++) {
         cur = seg_out_len(segs[k], cur);
-        worst = std::max(worst, cur * rows * elem_bytes(segs[k].st.back()->out_real()));
+        worst = std::max(worst, cur * rows * elem_bytes(segs[k].out_real >= 0 ? segs[k].out_real != 0 : segs[k].st.back()->out_real()));
     }
     return worst;
 }
@@ -1407,9 +1434,18 @@ int lqb_ampmodem_create(float mod, int type, int suppressed, int C, lqb_stage *o
 {
     LQB_TRY(check_channels(C));
     if (!out || !(mod > 0.f)) return fail(LQB_EINVAL, "ampmodem: modulation index must be > 0");
-    if (type != LQB_AMPMODEM_DSB) return fail(LQB_ENOTIMPL, "ampmodem: USB/LSB (Hilbert path) is outside the built scope; DSB only");
+    if (type != LQB_AMPMODEM_DSB && type != LQB_AMPMODEM_USB && type != LQB_AMPMODEM_LSB) return fail(LQB_EINVAL, "ampmodem: unknown type %d", type);
     AmStage *q = new AmStage(C);
     q->mod = mod; q->type = type; q->suppressed = suppressed ? 1 : 0;
+    if (type != LQB_AMPMODEM_DSB) {
+        // firhilbf_create(m = 25, 60 dB) as in ampmodem_create; with carrier the DC blocker follows the Hilbert pair
+        lqb_stage h = nullptr, d = nullptr;
+        int rc = lqb_firhilbf_create(type == LQB_AMPMODEM_USB ? LQB_FIRHILB_SSB_USB : LQB_FIRHILB_SSB_LSB, kAmDelay, 60.0f, C, &h);
+        if (rc == LQB_OK && !suppressed) rc = lqb_firfilt_rrrf_create_dc_blocker(kAmDelay, 20.0f, C, &d);
+        if (rc != LQB_OK) { delete static_cast<FirStage *>(h); delete q; return rc; }
+        q->hil = static_cast<FirStage *>(h); q->dcb = static_cast<FirStage *>(d);
+        q->hil->post_div = mod;
+    }
     // constants of liquid's ampmodem_create: m = 25, lowpass kaiser(2m+1, 0.01, 40 dB), dc blocker (25, 20 dB)
     design::firdes_kaiser(kAmTaps, 0.01f, 40.0f, 0.0f, q->lp);
     design::firdes_notch(kAmDelay, 0.0f, 20.0f, q->dc);

@@ -155,8 +155,10 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
             if (a.mode != FIR_PLAIN) {
                 const unsigned long long kabs = a.count + (unsigned long long)(t0 + R * tid + r);
                 const long long kloc = t0 + R * tid + r;
-                if (a.mode == FIR_SSB_LSB) v.x = __fadd_rn(v.x, v.y);
-                else if (a.mode == FIR_SSB_USB) v.x = __fsub_rn(v.x, v.y);
+                if (a.mode == FIR_SSB_LSB || a.mode == FIR_SSB_USB) {
+                    v.x = a.mode == FIR_SSB_LSB ? __fadd_rn(v.x, v.y) : __fsub_rn(v.x, v.y);
+                    if (a.post_div != 0.f) v.x = __fdiv_rn(__fmul_rn(0.5f, v.x), a.post_div);
+                }
                 else if (a.mode == FIR_C2R) v.x = kabs < (unsigned long long)a.delay ? 0.f : (((kabs - a.delay) & 1ull) ? -v.y : v.y);
                 else {                                                  // FIR_R2C
                     if (kloc == a.zero_at[0] || kloc == a.zero_at[1] || kloc == a.zero_at[2] || kloc == a.zero_at[3]) v.x = 0.f;

@@ -61,6 +61,7 @@ struct AgcP {
 struct AmP {
     float mod_index, pll_alpha, pll_beta;
     int suppressed;
+    int out_v1;                    // USB / LSB with carrier: write the mixed-down delayed branch (complex) instead of audio
     float lp[kAmTaps];             // lowpass taps reversed: lp[i] multiplies the sample (50 - i) steps old
     float dc[kAmTaps];             // dc-block taps reversed
     const float2 *sincos;          // NCO table
@@ -159,6 +160,7 @@ struct FirArgs {
     unsigned long long count;      // absolute index of this call's first sample since reset
     long long zero_at[4];          // FIR_R2C: local output indices whose in-phase part is forced to zero (-1 = none)
     const float *taps_q;           // taps of the imaginary lane (nullptr: same as taps)
+    float post_div;                // SSB modes inside ampmodem: y = (0.5 * side-band) / post_div; 0 = off
     long long n;
     float scale;
     const float *taps;             // device [ntaps] in design order h[0..ntaps-1]

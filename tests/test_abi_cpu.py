@@ -190,8 +190,8 @@ def test_argument_checking():
         L.ComplexIIRFilter("butter", order=2, Fc=0.7)
     with pytest.raises(ValueError):
         L.ComplexIIRFilter("ellip", order=4, Fc=0.1, As=-3.0)
-    with pytest.raises(NotImplementedError):
-        L.AmpModem(0.5, "usb", True)
+    assert L.Chain(L.AmpModem(0.5, "usb", True)).plan() == "am[carrier-loop] -> fir[hilbert] -> fir[dcblock]"
+    assert L.Chain(L.AGC(), L.AmpModem(0.5, "lsb", False), L.DeemphasisFilter()).plan() == "seq[agc] -> fir[hilbert] -> seq[deemph]"
     with pytest.raises(ValueError):
         L.ComplexResampler(1e-4, Fc=0.1)
     with pytest.raises(ValueError):
