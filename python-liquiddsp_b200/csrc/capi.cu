@@ -25,6 +25,7 @@
 #include "am.h"
 #include "bam.h"
 #include "fmst.h"
+#include "front.h"
 #include "par.h"
 #include "scan.h"
 #include "synth.h"
@@ -145,14 +146,16 @@ static EncodeTiledFn encode_tiled()
     return fn;
 }
 // rows of n complex64 samples as a 2-D float tensor [rows][2n]; box = one warp's tile: 32 rows x 16 samples (128 B), 128B swizzle
-static bool make_input_tmap(CUtensorMap *tm, const void *x, size_t n, size_t rows)
+static bool make_input_tmap(CUtensorMap *tm, const void *x, size_t n, size_t rows, unsigned box_rows = 32, unsigned box_floats = 32)
 {
     EncodeTiledFn enc = encode_tiled();
     if (!enc || (((size_t)x) & 15) || (n & 1) || n * 2 > 0xffffffffull) return false;
     const cuuint64_t gdim[2] = { (cuuint64_t)n * 2, (cuuint64_t)rows }, gstride[1] = { (cuuint64_t)n * 8 };
-    const cuuint32_t box[2] = { 32, 32 }, estr[2] = { 1, 1 };
+    const cuuint32_t box[2] = { box_floats, box_rows }, estr[2] = { 1, 1 };
+    // the 32-float box is the staged tile (128-byte swizzle); wider boxes are L2-prefetch shapes and carry no swizzle
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               box_floats == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ------------------------------------------------------------------------------------ stages
@@ -828,6 +831,16 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         case K_DEEMPH: static_cast<DeemphStage *>(s)->fill(a.de); break;
         case K_TF:     static_cast<TfStage *>(s)->fill(a.tf); break;
         default: return fail(LQB_EINVAL, "stage kind %d cannot run in the sequential kernel", (int)s->kind);
+        }
+    }
+    // the headline front (cascade + decimating resampler) with many channels: two channels per thread (front.cu)
+    {
+        bool two = nch >= 32768 && extra_mask == 0 && !in_real && front2_supported(g.mask, g.nsos);
+        if (const char *e = getenv("LQB_FRONT2")) two = two && atoi(e) != 0;
+        if (two && make_input_tmap(&a.tmap, x, n, (size_t)nch, kFront2BoxRows)) {
+            a.cpw = 32; a.use_tma = 1;
+            LQB_CUDA(front2_launch(g.nsos, a, stream));
+            return LQB_OK;
         }
     }
     // Blackwell data path for the many-channel front kernels: TMA tiled loads instead of per-lane cp.async

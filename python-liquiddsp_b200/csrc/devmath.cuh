@@ -71,6 +71,12 @@ __device__ __forceinline__ void tma_load_2d(unsigned smem_dst, const void *tmap,
                  :: "r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+// L2 prefetch of a tensor-map box (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_2d(const void *tmap, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
+
 // radians -> uint32 phase, the oscillator's own arithmetic (see design.hpp nco_constrain): the
 // 1/(2 pi) product is taken in double and rounded to float, everything after is float; a
 // fractional part that rounds up to 1.0f wraps to phase 0.

@@ -1,0 +1,10 @@
+// front.h -- launcher of the two-channels-per-thread front kernel (front.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "params.h"
+
+namespace lqb {
+constexpr int kFront2BoxRows = 64;     // rows of the TMA box the kernel expects in SeqArgs::tmap
+bool front2_supported(unsigned mask, int nsos);
+cudaError_t front2_launch(int nsos, const SeqArgs &a, cudaStream_t stream);
+}  // namespace lqb
