@@ -343,7 +343,8 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("bytes_per_launch")
         except (OSError, ValueError):
             pass
-        roof = {"bound": "hbm", "kernel": "seq_kernel<F_IIR|F_RS, 4> (seq[iir4+resamp])", "achieved": ach, "peak": peak, "unit": "GB/s",
+        kname = "front2_kernel<4>" if C >= 32768 and os.environ.get("LQB_FRONT2", "1") != "0" else "seq_kernel<F_IIR|F_RS, 4, TMA>"
+        roof = {"bound": "hbm", "kernel": kname + " (seq[iir4+resamp])", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "peak_source": peak_src, "traffic": traffic, "kernel_ms": kms,
                 "algorithmic_bytes_per_launch": bytes_launch, "share_of_step": kms / ms_step,
                 "segments_ms": [t / seg_calls for t in seg_ms],
