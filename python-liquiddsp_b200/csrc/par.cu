@@ -13,6 +13,7 @@
 #include "devmath.cuh"
 #include "par.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace lqb {
 namespace {
@@ -54,21 +55,37 @@ resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, vo
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *s_x = (float2 *)smem_raw;                   // span_max samples (float2 slots also when the samples are real)
     float  *s_xr = (float *)smem_raw;
-    float  *s_b = (float *)(s_x + span_max);            // bank [npfb][sublen]
-    float2 *s_t = (float2 *)(s_b + ((p.npfb * p.sublen + 3) & ~3));   // oscillator table (HAS_NCO)
+    float  *s_b = (float *)(s_x + span_max);            // bank [npfb][sublen]  (span_max leaves room for the alignment shifts below)
     const int tid = threadIdx.x, L = p.sublen;
     const long long ch = blockIdx.x / ntiles, tile = blockIdx.x % ntiles;
     const long long k0 = tile * KT;
     const int nk = (int)((n_out - k0) < KT ? (n_out - k0) : KT);
     const unsigned long long P0 = (unsigned long long)p.phase + (unsigned long long)k0 * p.step;
     const unsigned long long P1 = (unsigned long long)p.phase + (unsigned long long)(k0 + nk - 1) * p.step;
-    const long long i_lo = (long long)(P0 >> 24) - (L - 1), i_hi = (long long)(P1 >> 24);
-    const int span = (int)(i_hi - i_lo + 1);
+    const long long i_hi = (long long)(P1 >> 24);
+    long long i_lo = (long long)(P0 >> 24) - (L - 1);
     const float2 *xrow = (const float2 *)xv + ch * n;
     const float *xrow_r = (const float *)xv + ch * n;
     const long long gch = ch0 + ch;
-
+    // Complex rows that are 16-byte aligned arrive as ONE bulk copy (cp.async.bulk, the TMA engine) issued by one thread:
+    // the staged origin moves down to an even sample so source and destination are 16-byte aligned; the few samples from
+    // before the call (history ring) and an odd last sample are filled in by the threads.
+    const bool bulk = !REAL && ((((size_t)xv) & 15) == 0) && ((n & 1) == 0);
+    __shared__ unsigned long long s_bar;
+    if (bulk) {
+        if (i_lo >= 0) i_lo &= ~1LL;
+        else if ((-i_lo) & 1) s_x += 1;                 // sample 0 of the call lands on an even slot
+    }
+    const int span = (int)(i_hi - i_lo + 1);
+    const long long gA = i_lo > 0 ? i_lo : 0;           // first sample of this call in the span (even when bulk)
+    const int cnt2 = bulk ? (int)((i_hi + 1 - gA) & ~1LL) : 0;
+    if (bulk && tid == 0) { mbar_init(&s_bar, 1); mbar_init_fence(); }
     for (int i = tid; i < p.npfb * L; i += NT) s_b[i] = p.bank[i];
+    __syncthreads();
+    if (bulk && tid == 0 && cnt2 > 0) {
+        mbar_arrive_expect_tx(&s_bar, (unsigned)cnt2 * 8u);
+        bulk_g2s((unsigned)__cvta_generic_to_shared(&s_x[gA - i_lo]), xrow + gA, (unsigned)cnt2 * 8u, &s_bar);
+    }
     for (int i = tid; i < span; i += NT) {
         const long long g = i_lo + i;
         if (REAL) {
@@ -76,13 +93,13 @@ resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, vo
             else if (g >= -(long long)L) s_xr[i] = p.ring[(long long)(((long long)p.count + g + 4LL * L) % L) * Ctot + gch].x;
             else s_xr[i] = 0.f;
         } else {
-            if (g >= 0) cp_async8(&s_x[i], xrow + g);
+            if (g >= 0) { if (!bulk || g >= gA + cnt2) cp_async8(&s_x[i], xrow + g); }
             else if (g >= -(long long)L) s_x[i] = p.ring[(long long)(((long long)p.count + g + 4LL * L) % L) * Ctot + gch];
             else s_x[i] = make_float2(0.f, 0.f);
         }
     }
-    if (HAS_NCO) for (int i = tid; i < 1024; i += NT) s_t[i] = q.sincos[i];
     cp_async_commit(); cp_async_wait<0>();
+    if (bulk && cnt2 > 0) mbar_wait(&s_bar, 0);
     __syncthreads();
     if (HAS_NCO) {
         // the mixer runs in front of the filter: rotate the staged samples of this call in place (history samples
@@ -90,7 +107,8 @@ resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, vo
         const uint32_t th0 = q.theta[gch], dth = q.dtheta[gch];
         for (int i = tid; i < span; i += NT) {
             const long long g = i_lo + i;
-            if (g >= 0) { const float2 sc = nco_at(q, s_t, th0, dth, g); s_x[i] = q.dir == 2 ? mix_down(s_x[i], sc) : mix_up(s_x[i], sc); }
+            // the 8 KB oscillator table is read through L1 (copying it into every CTA's shared memory cost a sixth of the staging)
+            if (g >= 0) { const float2 sc = nco_at(q, q.sincos, th0, dth, g); s_x[i] = q.dir == 2 ? mix_down(s_x[i], sc) : mix_up(s_x[i], sc); }
         }
         __syncthreads();
     }
@@ -225,13 +243,14 @@ cudaError_t resamp_par_launch(const ResampP &p, const NcoP *nco, const void *x, 
     const NcoP q = nco ? *nco : NcoP{};
     if (n_out > 0) {
         // outputs per CTA: as many as keep the staged input span within ~48 KB
-        const int span_budget = 6000;
+        int span_budget = 3000;          // staged samples per CTA (24 KB): measured best on config 3 and on CResampler
+        if (const char *e = getenv("LQB_PAR_SPAN")) { const int v = atoi(e); if (v >= 256 && v <= 6000) span_budget = v; }
         long long kt = ((long long)(span_budget - p.sublen - 2) << 24) / p.step;
         const int KT = (int)(kt < 1 ? 1 : (kt > NT ? NT : kt));
-        const int span_max = (int)((((unsigned long long)KT * p.step) >> 24) + p.sublen + 3);
+        const int span_max = (int)((((unsigned long long)KT * p.step) >> 24) + p.sublen + 3) + 3;
         const long long ntiles = (n_out + KT - 1) / KT;
         if (ntiles * (long long)nch > 0x7fffffffLL) return cudaErrorInvalidValue;
-        const size_t smem = (size_t)span_max * sizeof(float2) + (size_t)((p.npfb * p.sublen + 3) & ~3) * sizeof(float) + (nco ? 1024 * sizeof(float2) : 0);
+        const size_t smem = (size_t)span_max * sizeof(float2) + (size_t)((p.npfb * p.sublen + 3) & ~3) * sizeof(float);
         if (smem > 200 * 1024) return cudaErrorInvalidValue;
         auto fn = p.variant == 2 ? resamp_par_kernel<false, 2>
                 : p.variant == 1 ? (nco ? resamp_par_kernel<true, 1> : resamp_par_kernel<false, 1>)
