@@ -164,6 +164,20 @@ def side_config(args, L, torch, dev, rank, world, barrier, max_over_ranks):
         elif args.next == "rfir":
             C, n, kind, bps, in_real = 2048, 1 << 20, 1, 8.0, True
             chain = L.Chain(L.RealKaiserBessel(63, 0.1, 60.0, channels=C)); name = "8f-1: RealKaiserBessel 63 taps, 2048 channels x 1M real samples"
+        elif args.next in ("iir", "nco", "agc", "fm", "deemph"):        # the path's stages one at a time
+            C, n, kind = 65536, 16384, 1
+            if args.next == "iir":
+                chain = L.Chain(L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=C)); bps, out_real = 16.0, False
+            elif args.next == "nco":
+                o = L.NCO(channels=C); o.set_frequencies((0.3 + 1e-5 * np.arange(C)).astype(np.float32)); o.set_direction(True)
+                chain = L.Chain(o); bps, out_real = 16.0, False
+            elif args.next == "agc":
+                chain = L.Chain(L.AGC(channels=C)); bps, out_real = 16.0, False
+            elif args.next == "fm":
+                chain = L.Chain(L.FreqDem(0.1, channels=C)); bps, out_real, kind = 12.0, True, 3
+            else:
+                chain = L.Chain(L.DeemphasisFilter(48000, channels=C)); bps, out_real, in_real = 8.0, True, True
+            name = "8a: %s alone, 65536 channels x 16384 samples" % args.next
         else:
             raise SystemExit("unknown --next row")
     if args.block != BLOCK:
@@ -214,7 +228,7 @@ def main():
     ap.add_argument("--e2e-channels", type=int, default=8192, help="channels per GPU of the host-buffer (e2e) leg")
     ap.add_argument("--fuse", type=int, default=1, help="chain fusion level (0, 1, 2)")
     ap.add_argument("--block", type=int, default=BLOCK, help="samples per channel per step (profiling runs use a shorter block)")
-    ap.add_argument("--next", default="", help="SURVEY 8(f) side line: bam, ssb, fmstereo, rrrf, cresamp, rfir")
+    ap.add_argument("--next", default="", help="side line: bam, ssb, fmstereo, rrrf, cresamp, rfir (SURVEY 8f); iir, nco, agc, fm, deemph (8a stages alone)")
     ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 5 (default, the headline AM receiver), 2 FIR, 3 NCO+resampler, 4 IIR+AGC+FM")
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
