@@ -164,6 +164,9 @@ def side_config(args, L, torch, dev, rank, world, barrier, max_over_ranks):
         elif args.next == "rfir":
             C, n, kind, bps, in_real = 2048, 1 << 20, 1, 8.0, True
             chain = L.Chain(L.RealKaiserBessel(63, 0.1, 60.0, channels=C)); name = "8f-1: RealKaiserBessel 63 taps, 2048 channels x 1M real samples"
+        elif args.next == "resamp":
+            C, n, kind, bps, out_real = 65536, 65536, 1, 8.192, False
+            chain = L.Chain(L.ComplexResampler(0.024, Fc=0.024, channels=C)); name = "8a: ComplexResampler(0.024) alone, 65536 channels x 64K blocks"
         elif args.next in ("iir", "nco", "agc", "fm", "deemph"):        # the path's stages one at a time
             C, n, kind = 65536, 16384, 1
             if args.next == "iir":

@@ -845,6 +845,10 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
     }
     // Blackwell data path for the many-channel front kernels: TMA tiled loads instead of per-lane cp.async
     a.use_tma = (a.cpw == 32 && extra_mask == 0 && !in_real && seq_has_tma(g.mask, g.nsos) && make_input_tmap(&a.tmap, x, n, (size_t)nch)) ? 1 : 0;
+    // full-rate complex results leave through a bulk tensor store when the rows allow the same box shape
+    a.tma_out = 0;
+    if (a.use_tma && !(g.mask & F_RS) && !out_real && (n_out & 1) == 0 && make_input_tmap(&a.tmap_out, y, n_out, (size_t)nch)) a.tma_out = 1;
+    if (a.use_tma && !(g.mask & F_RS) && !out_real && !a.tma_out) a.use_tma = 0;     // the TMA instantiation stores by TMA only
     LQB_CUDA(seq_launch(g.mask | extra_mask, g.nsos, a, stream));
     return LQB_OK;
 }

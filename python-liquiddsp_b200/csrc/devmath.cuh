@@ -77,6 +77,16 @@ __device__ __forceinline__ void tma_prefetch_2d(const void *tmap, int c0, int c1
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(tmap), "r"(c0), "r"(c1) : "memory");
 }
 
+// TMA store of a shared-memory box to a tensor-map box (bulk async group) and its bookkeeping
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int c0, int c1, unsigned smem_src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" :: "l"(tmap), "r"(c0), "r"(c1), "r"(smem_src) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // radians -> uint32 phase, the oscillator's own arithmetic (see design.hpp nco_constrain): the
 // 1/(2 pi) product is taken in double and rounded to float, everything after is float; a
 // fractional part that rounds up to 1.0f wraps to phase 0.

@@ -81,9 +81,11 @@ struct TfP {
 };
 
 struct alignas(64) SeqArgs {
+    CUtensorMap tmap_out;          // TMA mode, full-rate complex output: [C rows][2 out_pitch floats], same box and swizzle
     CUtensorMap tmap;              // TMA mode: the input as a 2-D tensor [C rows][2n floats], box 32 floats x 32 rows, 128B swizzle
     const void *x;                 // [C][n] input rows (complex64, or float32 when F_INREAL)
     void *y;                       // [C][out_pitch] output rows
+    int tma_out;                   // the output tile leaves through tmap_out (one bulk tensor store per warp and tile)
     int C;                         // channels in this launch
     int ch0;                       // first channel's index into the [.. ][Ctot] state arrays
     int Ctot;                      // channel stride of the state arrays

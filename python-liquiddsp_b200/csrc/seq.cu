@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     constexpr bool OUT_REAL = HAS_AM || HAS_FM || IN_REAL;
     constexpr int  IELEM = (IN_REAL || IN_I16) ? 4 : 8, OELEM = OUT_REAL ? 4 : 8;
     static_assert(!IN_I16 || HAS_RS, "int16 ingest is compiled for the decimating front kernels");
-    static_assert(!TMA || (IELEM == 8 && HAS_RS), "TMA staging is compiled for complex64 input of the decimating front kernels");
+    static_assert(!TMA || IELEM == 8, "TMA staging is compiled for complex64 input");
     using GI = Geo<IELEM>; using GO = Geo<OELEM>;
     constexpr int  PIN = GI::PITCH, POUT = GO::PITCH;
     constexpr int  NS = NSOS > 0 ? NSOS : 1;
@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     constexpr int PINS = TMA ? TS * IELEM : PIN;                   // staged row pitch: dense under TMA, padded otherwise
     unsigned char *s_in  = smem;                                   // NST stages of [RCTA][PINS]
     unsigned char *s_out = s_in + NST * RCTA * PINS;               // [RCTA][POUT] when the output is full rate
-    unsigned char *s_nxt = s_out + (HAS_RS ? 0 : RCTA * POUT);
+    // TMA mode with complex output: two dense swizzled [RCTA][128 B] buffers, sent by bulk tensor stores
+    constexpr bool TMA_OUT = TMA && !HAS_RS && !OUT_REAL;
+    unsigned char *s_nxt = s_out + (HAS_RS ? 0 : (TMA_OUT ? 2 * RCTA * (TS * 8) : RCTA * POUT));
     float2 *s_tap = (float2 *)s_nxt;                               // [warp][NST][TS] (tap, keep)
     s_nxt += HAS_RS ? (BT / 32) * NST * TS * sizeof(float2) : 0;
     int *s_emit = (int *)s_nxt;                                    // [warp][NST] sample of the tile an output falls on, or -1
@@ -115,6 +117,10 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     float2 fm_prev = make_float2(0.f, 0.f);
     float de_v1 = 0.f;
     long long kout = 0;
+    int obuf = 0;                                                  // TMA_OUT: result buffer of the tile in flight
+    const unsigned swz = TMA ? (unsigned)(lane & 7) : 0u;          // this lane's chunk permutation under the 128-byte swizzle
+    // byte offset of sample j within a staged row (chunks are permuted under the 128-byte swizzle)
+    auto soff = [&](int j) -> unsigned { return TMA ? (((((unsigned)j >> 1) ^ swz) << 4) + (unsigned)(j & 1) * 8u) : (unsigned)j * 8u; };
 
     if constexpr (HAS_NCO) {
         for (int i = tid; i < 1024; i += BT) s_sincos[i] = a.nco.sincos[i];
@@ -380,6 +386,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
             kout++;
         } else {
             if constexpr (OUT_REAL) *(float *)(s_out + myrow * POUT + jtile * 4) = r;
+            else if constexpr (TMA_OUT) *(float2 *)(s_out + obuf * (RCTA * (TS * 8)) + myrow * (TS * 8) + soff(jtile)) = z;
             else                    *(float2 *)(s_out + myrow * POUT + jtile * 8) = z;
         }
     };
@@ -425,7 +432,6 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
         return x;
     };
     // one staged sample / a whole staged row as complex floats (int16 I/Q pairs are converted on the way)
-    const unsigned swz = TMA ? (unsigned)(lane & 7) : 0u;        // this lane's chunk permutation under the 128-byte swizzle
     auto ld1 = [&](const unsigned char *rw, int j) -> float2 {
         if constexpr (IN_I16) return i16_to_iq(*(const unsigned *)(rw + j * 4));
         else if constexpr (TMA) return *(const float2 *)(rw + ((((unsigned)j >> 1) ^ swz) << 4) + (j & 1) * 8);
@@ -549,7 +555,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 }
             } else if constexpr (BIG_TAIL) {
 #pragma unroll 1
-                for (int j = 0; j < TS; j++) tail(upk(head(*(const float2 *)(row + j * 8))), j);
+                for (int j = 0; j < TS; j++) tail(upk(head(ld1(row, j))), j);
             } else if constexpr (HAS_IIR && !HAS_NCO) {
                 // full-rate chains behind the biquad cascade: the cascade runs skewed over the tile (see above) and
                 // leaves its outputs in the thread's own staged row; the stages after it then walk the row in a
@@ -557,11 +563,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 // instruction cache
                 {
                     u64 xs[TS], yy[NS];
-#pragma unroll
-                    for (int j = 0; j < TS; j += 2) {
-                        const float4 v = *(const float4 *)(row + j * 8);
-                        xs[j] = pk(v.x, v.y); xs[j + 1] = pk(v.z, v.w);
-                    }
+                    ld_row(row, xs);
 #pragma unroll
                     for (int k = 0; k < TS + NS - 1; k++) {
 #pragma unroll
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                                 y = fma2(cb2[sct], iv2[sct], y);
                                 iv2[sct] = iv1[sct]; iv1[sct] = v0; yy[sct] = y;
                                 if (sct == NS - 1) {
-                                    if constexpr (HAS_AGC || HAS_FM) *(float2 *)(const_cast<unsigned char *>(row) + j * 8) = upk(y);
+                                    if constexpr (HAS_AGC || HAS_FM) *(float2 *)(const_cast<unsigned char *>(row) + soff(j)) = upk(y);
                                     else tail(upk(y), j);
                                 }
                             }
@@ -586,21 +588,21 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 // then one pass per remaining stage: the gain loop is a long serial chain per sample and runs rolled;
                 // the discriminator has no feedback, so its 16 samples are independent work for the scheduler
                 if constexpr (HAS_AGC) {
-                    float2 *rw = (float2 *)const_cast<unsigned char *>(row);
+                    unsigned char *rw = const_cast<unsigned char *>(row);
 #pragma unroll 1
-                    for (int j = 0; j < TS; j++) rw[j] = agc_apply(rw[j]);
+                    for (int j = 0; j < TS; j++) { float2 *pz = (float2 *)(rw + soff(j)); *pz = agc_apply(*pz); }
                 }
                 if constexpr (HAS_AGC || HAS_FM) {
 #pragma unroll 4
-                    for (int j = 0; j < TS; j++) post(*(const float2 *)(row + j * 8), j);
+                    for (int j = 0; j < TS; j++) post(ld1(row, j), j);
                 }
             } else if constexpr (HAS_AGC || HAS_FM) {
 #pragma unroll 2
-                for (int j = 0; j < TS; j++) tail(upk(head(*(const float2 *)(row + j * 8))), j);
+                for (int j = 0; j < TS; j++) tail(upk(head(ld1(row, j))), j);
             } else {
 #pragma unroll
                 for (int j = 0; j < TS; j += 2) {
-                    const float4 v = *(const float4 *)(row + j * 8);
+                    const float4 v = *(const float4 *)(row + soff(j));
                     tail(upk(head(make_float2(v.x, v.y))), j);
                     tail(upk(head(make_float2(v.z, v.w))), j + 1);
                 }
@@ -624,13 +626,27 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 }
             }
         }
-        if constexpr (!HAS_RS) {
+        if constexpr (TMA_OUT) {
+            // the warp's [32 rows x 128 B] result box goes out as one bulk tensor store; the other buffer takes the next
+            // tile, and a buffer is written again only after the store that last read it has drained
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&a.tmap_out, (int)(t * (TS * 2)), (int)(blockIdx.x * RCTA + wid * 32),
+                             (unsigned)__cvta_generic_to_shared(s_out + obuf * (RCTA * (TS * 8)) + wid * (32 * TS * 8)));
+                bulk_commit();
+                bulk_wait_read<1>();
+            }
+            obuf ^= 1;
+            __syncwarp();
+        } else if constexpr (!HAS_RS) {
             __syncwarp();
             store_tile(t);
         }
         stage = stage + 1 == NST ? 0 : stage + 1;
     }
 
+    if constexpr (TMA_OUT) { if (lane == 0) bulk_wait_all<0>(); }
     // ---- carried state back to HBM ----
     if (active) {
         if constexpr (HAS_NCO) a.nco.theta[gch] = nco_theta;
@@ -669,8 +685,8 @@ struct Entry { unsigned mask; int nsos; SeqFn fn, fn_part, fn_tma; };       // f
 #define LQB_E_IIR(M) LQB_E(M, 1), LQB_E(M, 2), LQB_E(M, 3), LQB_E(M, 4)
 const Entry kTable[] = {
     // single stages
-    LQB_E(F_NCO, 0), LQB_E(F_RS, 0), LQB_E(F_AGC, 0), LQB_E(F_FM, 0), LQB_E(F_DE | F_INREAL, 0),
-    LQB_E_IIR(F_IIR), LQB_E(F_IIR, 5), LQB_E(F_IIR, 6), LQB_E(F_IIR, 7), LQB_E(F_IIR, 8),
+    LQB_T(F_NCO, 0), LQB_T(F_RS, 0), LQB_T(F_AGC, 0), LQB_T(F_FM, 0), LQB_E(F_DE | F_INREAL, 0),
+    LQB_T(F_IIR, 1), LQB_T(F_IIR, 2), LQB_T(F_IIR, 3), LQB_T(F_IIR, 4), LQB_E(F_IIR, 5), LQB_E(F_IIR, 6), LQB_E(F_IIR, 7), LQB_E(F_IIR, 8),
     LQB_E_IIR(F_IIR | F_INREAL), LQB_E(F_IIR | F_INREAL, 5), LQB_E(F_IIR | F_INREAL, 6), LQB_E(F_IIR | F_INREAL, 7), LQB_E(F_IIR | F_INREAL, 8),
     // transfer-function IIR (CIIRFilter / RIIRFilter), delay elements padded to 1, 2, 4, 8, 15
     LQB_E(F_TF, 1), LQB_E(F_TF, 2), LQB_E(F_TF, 4), LQB_E(F_TF, 8), LQB_E(F_TF, 15),
@@ -699,7 +715,7 @@ size_t smem_bytes(unsigned m, const SeqArgs &a, bool tma)
     const int pin = TS * (in_real ? 4 : 8) + 16, pout = TS * (out_real ? 4 : 8) + 16;
     const size_t rows = (size_t)(BT / 32) * a.cpw;
     size_t b = tma ? (size_t)NST * rows * (pin - 16) + 1024 : (size_t)NST * rows * pin;
-    if (!(m & F_RS)) b += rows * pout;
+    if (!(m & F_RS)) b += (tma && !out_real) ? 2 * rows * (size_t)(TS * 8) : rows * pout;
     if (m & F_RS)  b += (BT / 32) * NST * TS * sizeof(float2) + 32 + (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15);
     if (m & F_NCO) b += 1024 * sizeof(float2);
     if (m & F_AGC) b += 128 * sizeof(double2);

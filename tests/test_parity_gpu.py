@@ -826,3 +826,23 @@ def test_host_call_time_sliced_equals_channel_chunked(cuda, monkeypatch):
         outs[mode] = (a, b, ch(iq16.reshape(C, 2 * n)))
     for u, v in zip(outs["slice"], outs["chunk"]):
         assert u.shape == v.shape and np.array_equal(u.view(np.uint32), v.view(np.uint32))
+
+
+def test_full_rate_stages_wide_batches_tma(cuda):
+    """ComplexIIRFilter and NCO alone at a channel count that selects 32 channels per warp: TMA tile loads and bulk
+    tensor stores, ragged last box (C not a multiple of 32) and ragged last tile (n not a multiple of 16)."""
+    rng = np.random.default_rng(81)
+    C, n = 56832 + 13, 1000 + 6
+    base = crandn(rng, 64, n)
+    x = np.tile(base, (C // 64 + 1, 1))[:C].copy()
+    iir = L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=C)
+    ys = [iir(x), iir(x)]
+    for c in (0, 31, 32, C - 14, C - 1):
+        o = O.ComplexIIRFilter(_sos=iir.sos())
+        for k in range(2):
+            assert np.array_equal(ys[k][c].view(np.uint32), o(x[c]).view(np.uint32)), (c, k)
+    nco = L.NCO(channels=C); nco.set_frequencies((0.2 + 1e-5 * np.arange(C)).astype(np.float32))
+    y = nco.mix_down(x)
+    for c in (0, 33, C - 1):
+        o = O.NCO(); o.freq = float(np.float32(0.2 + 1e-5 * c))
+        assert np.array_equal(y[c].view(np.uint32), o.mix_down(x[c]).view(np.uint32)), c
