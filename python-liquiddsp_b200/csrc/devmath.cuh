@@ -189,10 +189,13 @@ __device__ __forceinline__ float exp_rn_small(float a)
 // instructions and a fifth of the dependent chain.  Valid for normal positive x (the AGC calls it for x > 1e-6).
 __device__ __forceinline__ float log_rn(float x, const double2 *__restrict__ tab)
 {
-    const long long bits = __double_as_longlong((double)x);
-    const int e = (int)(bits >> 52) - 1023;
-    const int idx = (int)(bits >> 45) & 127;
-    const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+    // exponent, table index and the mantissa as a double in [1, 2) straight from the float's bits (x is a normal
+    // float here: the gain loop only takes the logarithm above 1e-6) -- the same numbers as widening first, minus
+    // one conversion on the loop's critical path
+    const unsigned fb = __float_as_uint(x);
+    const int e = (int)((fb >> 23) & 0xffu) - 127;
+    const int idx = (int)(fb >> 16) & 127;
+    const double m = __hiloint2double((int)(0x3ff00000u | ((fb & 0x007fffffu) >> 3)), (int)((fb & 7u) << 29));
     const double2 t = tab[idx];
     const double r = fma(m, t.x, -1.0);
     // r - r^2/2 + r^3/3 - r^4/4 + r^5/5 as two short chains
