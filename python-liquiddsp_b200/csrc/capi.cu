@@ -721,6 +721,9 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         FmstArgs a{};
         a.x = (const float2 *)x; a.y = (float *)y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.n = (long long)n; a.n_out = (long long)(n_out / 2);
         LQB_TRY(static_cast<const FmstStage *>(first)->fill(a.p));
+        // enough warps to cover the loop's FP64 dependency chain: ~4 warps per scheduler when the channels allow
+        a.cpw = nch >= 32768 ? 32 : (nch >= 4096 ? 16 : 8);        // (measured at 16384 channels: 23.5 / 25.0 / 13.6 GS/s at 32 / 16 / 8 -- idle lanes still cost conversion-unit slots)
+        if (const char *e = getenv("LQB_CPW")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) a.cpw = v; }
         LQB_CUDA(fmstereo_launch(a, stream));
         return LQB_OK;
     }

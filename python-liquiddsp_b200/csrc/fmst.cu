@@ -29,15 +29,19 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
     float *s_sin = s_b + ((a.p.rs.npfb * L + 3) & ~3);            // [1024]
     double *s_at = (double *)(s_sin + 1024);                      // [65][8] atan2_rn table
 
-    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const long long chl = (long long)blockIdx.x * BT + tid;
-    const bool active = chl < a.C;
+    // cpw channels per warp: the loop is one long FP64 dependency chain per sample, so with few channels they are
+    // spread over more warps (8 or 16 working lanes each) and the schedulers get independent chains to interleave
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, cpw = a.cpw, RC = (BT / 32) * cpw;
+    const bool worker = lane < cpw;
+    const int myrow = wid * cpw + (worker ? lane : 0);
+    const long long chl = (long long)blockIdx.x * RC + myrow;
+    const bool active = worker && chl < a.C;
     const long long gch = a.ch0 + (active ? chl : 0), CT = a.Ctot, N = a.n;
 
     for (int i = tid; i < 1024; i += BT) s_sin[i] = a.p.sincos[i].x;
     for (int i = tid; i < 65 * 8; i += BT) s_at[i] = a.p.atantab[i];
     for (int i = tid; i < a.p.rs.npfb * L; i += BT) s_b[i] = a.p.rs.bank[i];
-    for (int i = 0; i < L; i++) { s_L[i * BT + tid] = a.p.ringL[i * CT + gch]; s_R[i * BT + tid] = a.p.ringR[i * CT + gch]; }
+    if (worker) for (int i = 0; i < L; i++) { s_L[i * BT + myrow] = a.p.ringL[i * CT + gch]; s_R[i * BT + myrow] = a.p.ringR[i * CT + gch]; }
     float2 prev = a.p.rprime[gch];
     uint32_t theta = a.p.theta[gch], dtheta = a.p.dtheta[gch];
     float pe = a.p.pe[gch], vL = a.p.vL[gch], vR = a.p.vR[gch];
@@ -46,15 +50,16 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
     long long kout = 0;
     float *yrow = a.y + (active ? chl : 0) * 2 * a.n_out;
 
-    // a warp stages its own 32 rows: 8 lanes cover one 128-byte row segment, 4 rows per pass
-    const long long row0 = (long long)blockIdx.x * BT + wid * 32;
+    // a warp stages its own cpw rows: 8 lanes cover one 128-byte row segment, 4 rows per pass
+    const long long row0 = (long long)blockIdx.x * RC + wid * cpw;
     const bool vec = ((N & 1) == 0) && ((((size_t)a.x) & 15) == 0);
     auto load_tile = [&](long long t, int stage) {
-        unsigned char *dst = s_in + stage * (BT * PITCH) + (wid * 32) * PITCH;
+        unsigned char *dst = s_in + stage * (BT * PITCH) + (wid * cpw) * PITCH;
         const long long n0 = t * TS;
 #pragma unroll
         for (int ps = 0; ps < 8; ps++) {
             const int r = ps * 4 + (lane >> 3), c = lane & 7;     // row within the warp, 16-byte chunk within the row
+            if (r >= cpw) break;
             const long long ch = row0 + r, s0 = n0 + 2 * c;
             unsigned char *d = dst + r * PITCH + c * 16;
             if (ch < a.C && vec && s0 + 1 < N) cp_async16(d, a.x + ch * N + s0, 16);
@@ -78,8 +83,9 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
-        unsigned char *row = s_in + stage * (BT * PITCH) + tid * PITCH;
-        const int nv = (int)((N - t * TS) < TS ? (N - t * TS) : TS);
+        unsigned char *row = s_in + stage * (BT * PITCH) + myrow * PITCH;
+        const int nv = worker ? (int)((N - t * TS) < TS ? (N - t * TS) : TS) : 0;
+        if (worker) {
         // the discriminator has no feedback: its 16 arguments are independent work, done ahead of the PLL loop (the
         // result replaces the sample in the thread's own staged row)
 #pragma unroll 4
@@ -90,6 +96,7 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
             const float im = __fmaf_rn(prev.x, z.y, -__fmul_rn(prev.y, z.x));
             *(float *)(row + j * 8) = __fmul_rn(atan2_rn(im, re, s_at), a.p.ref);
             if (j < nv) prev = z;
+        }
         }
 #pragma unroll 1
         for (int j = 0; j < nv; j++) {
@@ -107,14 +114,14 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
             vL = __fmaf_rn(-a.p.a1, vL, __fadd_rn(s, sc.x)); const float left  = __fmaf_rn(a.p.b0, vL, 0.f);
             vR = __fmaf_rn(-a.p.a1, vR, __fsub_rn(s, sc.x)); const float right = __fmaf_rn(a.p.b0, vR, 0.f);
             // resamp_rrrf_execute on both: push, then one output while the phase is inside this sample
-            s_L[slot * BT + tid] = left; s_R[slot * BT + tid] = right;
+            s_L[slot * BT + myrow] = left; s_R[slot * BT + myrow] = right;
             slot = slot + 1 == L ? 0 : slot + 1;
             if (phase <= 0x00ffffffu) {                            // rate <= 1: at most one output per input
                 const float *h = s_b + (phase >> (24 - a.p.rs.bits)) * L;
                 float aL = 0.f, aR = 0.f;
                 int q = slot;                                      // oldest sample first
                 for (int i = 0; i < L; i++) {
-                    aL = __fmaf_rn(h[i], s_L[q * BT + tid], aL); aR = __fmaf_rn(h[i], s_R[q * BT + tid], aR);
+                    aL = __fmaf_rn(h[i], s_L[q * BT + myrow], aL); aR = __fmaf_rn(h[i], s_R[q * BT + myrow], aR);
                     q = q + 1 == L ? 0 : q + 1;
                 }
                 if (active) *(float2 *)(yrow + 2 * kout) = make_float2(aL, aR);
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
     }
 
     if (active) {
-        for (int i = 0; i < L; i++) { a.p.ringL[i * CT + gch] = s_L[i * BT + tid]; a.p.ringR[i * CT + gch] = s_R[i * BT + tid]; }
+        for (int i = 0; i < L; i++) { a.p.ringL[i * CT + gch] = s_L[i * BT + myrow]; a.p.ringR[i * CT + gch] = s_R[i * BT + myrow]; }
         a.p.rprime[gch] = prev; a.p.theta[gch] = theta; a.p.dtheta[gch] = dtheta;
         a.p.pe[gch] = pe; a.p.vL[gch] = vL; a.p.vR[gch] = vR;
     }
@@ -144,7 +151,9 @@ cudaError_t fmstereo_launch(const FmstArgs &a, cudaStream_t stream)
                       + 1024 * sizeof(float) + 65 * 8 * sizeof(double);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fmstereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
-    fmstereo_kernel<<<(unsigned)((a.C + BT - 1) / BT), BT, smem, stream>>>(a);
+    if (a.cpw != 8 && a.cpw != 16 && a.cpw != 32) return cudaErrorInvalidValue;
+    const int rc_cta = (BT / 32) * a.cpw;
+    fmstereo_kernel<<<(unsigned)((a.C + rc_cta - 1) / rc_cta), BT, smem, stream>>>(a);
     return cudaGetLastError();
 }
 

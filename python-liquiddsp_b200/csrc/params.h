@@ -145,7 +145,7 @@ struct FmstP {
 struct FmstArgs {
     const float2 *x;               // [C][n]
     float *y;                      // [C][2 * n_out] interleaved left, right
-    int C, ch0, Ctot;
+    int C, ch0, Ctot, cpw;         // cpw: channels per warp (8, 16 or 32)
     long long n, n_out;
     FmstP p;
 };
