@@ -260,8 +260,11 @@ __global__ void __launch_bounds__(128) agc_tmajor_kernel(const __grid_constant__
                 const float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
                 agc_y2p = (float)fma(a.agc.one_minus_alpha, (double)agc_y2p, (double)__fmul_rn(a.agc.alpha, y2));
                 if (!a.agc.locked) {
-                    if (agc_y2p > 1e-6f) agc_g = __fmul_rn(agc_g, exp_rn_small(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), log_rn(agc_y2p, s_log))));
-                    if (agc_g > 1e6f) agc_g = 1e6f;
+                    // the gain update without data-dependent branches: the logarithm takes a harmless argument when the
+                    // level is below 1e-6 and its result is then not used
+                    const float ge = __fmul_rn(agc_g, exp_rn_warp(__fmul_rn(__fmul_rn(-0.5f, a.agc.alpha), log_rn(fmaxf(agc_y2p, 1e-30f), s_log))));
+                    agc_g = agc_y2p > 1e-6f ? ge : agc_g;
+                    agc_g = agc_g > 1e6f ? 1e6f : agc_g;
                     if (agc_mode != 7) {
                         const bool ex = (float)(-20.0 * log10((double)agc_g)) > a.agc.threshold;
                         const int before = agc_mode;

@@ -187,6 +187,18 @@ __device__ __forceinline__ float exp_rn_small(float a)
 // and ln(1+r) is a degree-5 series (next term 2^-48/6).  All in double, so the value rounded to float is the
 // correctly rounded logf except within ~1e-15 of a tie -- the same as the library log at a third of the
 // instructions and a fifth of the dependent chain.  Valid for normal positive x (the AGC calls it for x > 1e-6).
+// exp_rn_small with the settled-loop test taken once per warp: when every lane's argument is within 2^-7 (the steady
+// state of the gain loop) the warp runs the short series with no divergence bookkeeping; otherwise the general routine
+__device__ __forceinline__ float exp_rn_warp(float a)
+{
+    if (__all_sync(__activemask(), fabsf(a) <= 0.0078125f)) {
+        const double x = (double)a, x2 = x * x;
+        const double lo = fma(x, fma(x, 0.5, 1.0), 1.0);
+        const double hi = fma(x, fma(x, 1.0 / 120.0, 1.0 / 24.0), 1.0 / 6.0);
+        return (float)fma(x2 * x, hi, lo);
+    }
+    return exp_rn_small(a);
+}
 __device__ __forceinline__ float log_rn(float x, const double2 *__restrict__ tab)
 {
     // exponent, table index and the mantissa as a double in [1, 2) straight from the float's bits (x is a normal
