@@ -149,7 +149,7 @@ static EncodeTiledFn encode_tiled()
 static bool make_input_tmap(CUtensorMap *tm, const void *x, size_t n, size_t rows, unsigned box_rows = 32, unsigned box_floats = 32)
 {
     EncodeTiledFn enc = encode_tiled();
-    if (!enc || (((size_t)x) & 15) || (n & 1) || n * 2 > 0xffffffffull) return false;
+    if (!enc || (((size_t)x) & 15) || (n & 1) || n * 2 > 0x7fffffffull || rows > 0x7fffffffull) return false;   // box coordinates are int32
     const cuuint64_t gdim[2] = { (cuuint64_t)n * 2, (cuuint64_t)rows }, gstride[1] = { (cuuint64_t)n * 8 };
     const cuuint32_t box[2] = { box_floats, box_rows }, estr[2] = { 1, 1 };
     // the 32-float box is the staged tile (128-byte swizzle); wider boxes are L2-prefetch shapes and carry no swizzle
