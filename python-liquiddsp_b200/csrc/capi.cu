@@ -757,6 +757,8 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         FirArgs a{};
         a.x = (const float2 *)x; a.y = (float2 *)y; a.C = nch; a.ch0 = ch0; a.Ctot = f->C; a.ntaps = (int)f->h.size();
         a.real_io = f->real_io ? 1 : 0;
+        a.pair = f->real_io && f->mode == FIR_PLAIN ? 1 : 0;           // two real channels share one packed lane pair
+        if (a.pair && (ch0 & 1)) return fail(LQB_EINVAL, "internal: paired real FIR needs an even first channel");
         a.in_real = f->in_r ? 1 : 0; a.out_real = f->out_r ? 1 : 0; a.mode = f->mode; a.delay = f->delay; a.count = f->count;
         a.taps_q = f->hlane_q.empty() ? nullptr : f->taps_q.p;
         a.post_div = f->post_div;
@@ -1027,6 +1029,8 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
     const size_t in_total = (size_t)C * n * ib;
     size_t chunk = std::max<size_t>(1, std::max<size_t>((size_t)64 << 20, in_total / 8) / std::max<size_t>(1, n * ib));
     if (chunk >= 64) chunk = chunk / 64 * 64;
+    else if (chunk > 1) chunk &= ~(size_t)1;                       // paired real FIR rows: chunks start on even channels
+    else if (C > 1) chunk = 2;
     chunk = std::min<size_t>(chunk, (size_t)C);
     for (auto *st : c->stages) if (st->kind == K_IIR && static_cast<IirStage *>(st)->mode == 2) chunk = (size_t)C;   // scan scratch is per stage
     for (int s = 0; s < lqb_chain_s::kStreams; s++) if (!c->streams[s]) LQB_CUDA(cudaStreamCreate(&c->streams[s]));

@@ -30,6 +30,12 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
 }
 
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(gsrc) : "memory");
+}
+
 // IN_REAL / OUT_REAL: float rows instead of complex64.  firfilt_rrrf is real in, real out: the samples ride in the
 // real lane of the same arithmetic.  The firhilbf users (SSBDemod, HilbertTransform) run the two lanes with different
 // taps -- a pure delay in one, the quadrature filter in the other -- and combine them when the tile is written.
@@ -47,14 +53,19 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
     const long long ch = blockIdx.x / groups;
     const long long tile_first = (long long)(blockIdx.x % groups) * tpc;
     const int my_tiles = (int)((ntiles - tile_first) < tpc ? (ntiles - tile_first) : tpc);
-    const long long gch = a.ch0 + ch;
+    // firfilt_rrrf with a.pair: a logical row is a PAIR of real channels (2 ch, 2 ch + 1) riding in the two lanes of the
+    // same packed arithmetic -- half the multiply-adds per real sample; histories are kept per pair
+    const bool pair = IN_REAL && OUT_REAL && a.pair;
+    const long long chA = pair ? 2 * ch : ch, chB = chA + 1;
+    const bool hasB = pair && chB < a.C;
+    const long long gch = pair ? a.ch0 / 2 + ch : a.ch0 + ch;
     const float2 *xrow = a.x + ch * a.n;
-    const float *xrow_r = (const float *)a.x + ch * a.n;
+    const float *xrow_r = (const float *)a.x + chA * a.n, *xrow_b = (const float *)a.x + chB * a.n;
     const float2 *hrow = a.hist_in + gch * (long long)(a.ntaps - 1);
     const int nh = a.ntaps - 1;
 
     const bool dup = a.mode == FIR_R2C;                                // real input feeds both lanes
-    auto lift = [&](float v) { return make_float2(v, dup ? v : 0.f); };
+    auto lift = [&](long long g) { const float v = xrow_r[g]; return make_float2(v, dup ? v : (hasB ? xrow_b[g] : 0.f)); };
     for (int k = tid; k < ntaps_pad; k += NT) {
         const float h = k < a.ntaps ? a.taps[k] : 0.f;
         s_h[k] = make_float2(h, a.taps_q ? (k < a.ntaps ? a.taps_q[k] : 0.f) : h);
@@ -73,7 +84,10 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
             float2 *dst = &s_x[pi];
             if (g >= 0) {
                 if (g >= a.n) *dst = make_float2(0.f, 0.f);
-                else if (IN_REAL) *dst = lift(xrow_r[g]);
+                else if (IN_REAL) {
+                    if (dup) *dst = lift(g);
+                    else { cp_async4(&dst->x, xrow_r + g); if (hasB) cp_async4(&dst->y, xrow_b + g); else dst->y = 0.f; }
+                }
                 else cp_async8(dst, xrow + g);
             }
             else if (g + nh >= 0) cp_async8(dst, hrow + (g + nh));
@@ -88,7 +102,7 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
         float2 *ho = a.hist_out + gch * (long long)nh;
         for (int j = tid; j < nh; j += NT) {
             const long long g = a.n - nh + j;
-            ho[j] = g >= 0 ? (IN_REAL ? lift(xrow_r[g]) : xrow[g]) : hrow[g + nh];
+            ho[j] = g >= 0 ? (IN_REAL ? lift(g) : xrow[g]) : hrow[g + nh];
         }
     }
 
@@ -170,8 +184,11 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
         __syncthreads();
         float2 *yrow = a.y + ch * a.n;
         if (OUT_REAL) {
-            float *yr = (float *)a.y + ch * a.n;
-            for (int i = tid; i < TN; i += NT) { const long long g = t0 + i; if (g < a.n) yr[g] = s_x[phys(i)].x; }
+            float *yr = (float *)a.y + chA * a.n, *yb = (float *)a.y + chB * a.n;
+            for (int i = tid; i < TN; i += NT) {
+                const long long g = t0 + i;
+                if (g < a.n) { const float2 v = s_x[phys(i)]; yr[g] = v.x; if (hasB) yb[g] = v.y; }
+            }
         } else {
             const bool vec = ((a.n & 1) == 0) && ((((size_t)a.y) & 15) == 0);
             if (vec && t0 + TN <= a.n) {
@@ -207,20 +224,22 @@ cudaError_t fir_launch(const FirArgs &a, cudaStream_t stream)
     const int ntaps_pad = (a.ntaps + R - 1) / R * R;
     const int halo = ntaps_pad - 1;
     const long long ntiles = (a.n + TN - 1) / TN;
+    const long long rows = (a.pair && a.real_io) ? ((long long)a.C + 1) / 2 : (long long)a.C;      // logical rows (pairs of real channels)
     // consecutive tiles per CTA: as many (up to 8) as still leave ~8 CTAs per SM
-    long long tpc = ntiles * (long long)a.C / (148 * 8);
+    long long tpc = ntiles * rows / (148 * 8);
     tpc = tpc < 1 ? 1 : (tpc > 8 ? 8 : tpc);
     if (tpc > ntiles) tpc = ntiles;
     const long long groups = (ntiles + tpc - 1) / tpc;
     const size_t bufsz = (size_t)((TN + halo + ((TN + halo) >> 4) + 2) & ~1);
     const size_t smem = (2 * bufsz + (size_t)ntaps_pad) * sizeof(float2);
-    if (smem > 200 * 1024 || groups * (long long)a.C > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if (smem > 200 * 1024 || groups * rows > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if (a.pair && (!a.real_io || a.mode != FIR_PLAIN || (a.ch0 & 1))) return cudaErrorInvalidValue;
     const bool in_real = a.real_io || a.in_real, out_real = a.real_io || a.out_real;
     auto fn = in_real ? (out_real ? fir_kernel<true, true> : fir_kernel<true, false>)
                       : (out_real ? fir_kernel<false, true> : fir_kernel<false, false>);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
-    fn<<<(unsigned)(groups * a.C), NT, smem, stream>>>(a, (int)ntiles, ntaps_pad, (int)tpc, (int)groups);
+    fn<<<(unsigned)(groups * rows), NT, smem, stream>>>(a, (int)ntiles, ntaps_pad, (int)tpc, (int)groups);
     return cudaGetLastError();
 }
 

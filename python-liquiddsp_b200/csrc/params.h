@@ -155,6 +155,7 @@ struct FirArgs {
     const float2 *x; float2 *y;    // [C][n]
     int C, ch0, Ctot, ntaps;
     int real_io;                   // firfilt_rrrf: x and y are float rows
+    int pair;                      // firfilt_rrrf: two real channels per logical row (needs an even ch0)
     // firhilbf built on the same kernel: separate taps for the two lanes and a combining epilogue
     int in_real, out_real;         // element types when they differ (real_io sets both)
     int mode;                      // FIR_PLAIN, FIR_SSB_LSB / FIR_SSB_USB (re + / - im), FIR_R2C, FIR_C2R
