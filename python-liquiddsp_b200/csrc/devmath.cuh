@@ -132,7 +132,7 @@ __device__ __forceinline__ float atan2_fast(float y, float x)
     r = __fmul_rn(r, s);
     r = __fmaf_rn(r, t, t);
     r = ay > ax ? __fsub_rn(1.57079637f, r) : r;
-    r = x < 0.f ? __fsub_rn(3.14159274f, r) : r;
+    r = __float_as_int(x) < 0 ? __fsub_rn(3.14159274f, r) : r;      // sign bit, so that atan2(+-0, -0) = +-pi as in libm
     return copysignf(r, y);
 }
 
