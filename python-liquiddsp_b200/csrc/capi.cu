@@ -669,6 +669,12 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
         }
         size_t best = 1;
         if (c->fuse) for (size_t len = std::min<size_t>(6, st.size() - i); len >= 2; len--) if (run_fusable(st, i, len, c->fuse)) { best = len; break; }
+        if (best == 1 && st[i]->kind == K_AM) {      // (fusion level 2 without the one fully fused pattern: the tail kernel after all)
+            Segment t; t.type = Segment::AMTAIL; t.st = { st[i] }; std::string nm = "ampmodem";
+            size_t j = i + 1;
+            if (j < st.size() && st[j]->kind == K_DEEMPH) { t.st.push_back(st[j++]); nm += "+deemph"; }
+            t.name = "am[" + nm + "]"; segs.push_back(t); i = j; continue;
+        }
         if (best == 1) {
             if (st[i]->kind == K_IIR) {              // long cascades: kMaxSos sections per launch
                 IirStage *q = static_cast<IirStage *>(st[i]);

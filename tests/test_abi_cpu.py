@@ -192,6 +192,8 @@ def test_argument_checking():
         L.ComplexIIRFilter("ellip", order=4, Fc=0.1, As=-3.0)
     assert L.Chain(L.AmpModem(0.5, "usb", True)).plan() == "am[carrier-loop] -> fir[hilbert] -> fir[dcblock]"
     assert L.Chain(L.AGC(), L.AmpModem(0.5, "lsb", False), L.DeemphasisFilter()).plan() == "seq[agc] -> fir[hilbert] -> seq[deemph]"
+    # fusion level 2 away from the one fully fused pattern still finds a kernel for the ampmodem
+    assert L.Chain(L.FIRFilter(np.ones(4, np.float32)), L.AmpModem(0.5, "dsb", True), L.DeemphasisFilter(), fuse=2).plan() == "fir -> am[ampmodem+deemph]"
     with pytest.raises(ValueError):
         L.ComplexResampler(1e-4, Fc=0.1)
     with pytest.raises(ValueError):
