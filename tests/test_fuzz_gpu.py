@@ -140,3 +140,37 @@ def test_random_chain(cuda, seed):
             assert np.all(np.isfinite(y[c]))
             continue
         assert rel_l2(y[c], yo) <= tol, (rel_l2(y[c], yo), names, fuse, chain.plan(), C, n, cuts, c)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_chain_wide(cuda, seed):
+    """The same idea at channel counts that switch the kernels' regimes (8 / 16 / 32 channels per warp, TMA staging, the
+    two-channel front kernel, paired real FIR rows): 64 distinct signals tiled over the channel axis."""
+    rng = np.random.default_rng(5000 + seed)
+    C = int([20000, 30001, 33000, 60007][int(rng.integers(0, 4))])
+    n = int(rng.integers(400, 1400))
+    base = np.stack([am_iq(n, fs=48000.0, f_off=5.0 + 0.5 * c, phase=0.1 * c, seed=seed * 100 + c, noise=0.02, amp=0.6) for c in range(64)])
+    x = np.tile(base, (C // 64 + 1, 1))[:C].copy()
+    gs, os_, names, exact = [], [], [], True
+    for _ in range(int(rng.integers(1, 4))):
+        g, o, ex, nm = _complex_stage(rng, C); gs.append(g); os_.append(o); names.append(nm); exact &= ex
+    kind = None
+    if rng.integers(0, 3) > 0:
+        g, o, kind, nm = _demod(rng, C); gs.append(g); os_.append(o); names.append(nm)
+        for _ in range(int(rng.integers(0, 3))):
+            g, o, ex, nm = _real_stage(rng, C); gs.append(g); os_.append(o); names.append(nm)
+    fuse = int(rng.integers(0, 3))
+    chain = L.Chain(*gs, fuse=fuse)
+    cut = int(rng.integers(1, n))
+    y = np.concatenate([chain(x[:, :cut]), chain(x[:, cut:])], axis=1)
+    assert np.array_equal(y[:64].view(np.uint32), y[64:128].view(np.uint32)), (names, chain.plan())     # position in the grid is irrelevant
+    assert np.array_equal(y[C - 1].view(np.uint32), y[(C - 1) % 64].view(np.uint32)), (names, chain.plan())
+    if kind in ("pll", "arg-pll") and not exact:
+        return
+    v1, v2 = x[0, :cut], x[0, cut:]
+    for o in os_:
+        v1 = o(v1)
+    for o in os_:
+        v2 = o(v2)
+    yo = np.concatenate([v1, v2])
+    assert yo.shape == y[0].shape and rel_l2(y[0], yo) <= 1e-4, (rel_l2(y[0], yo), names, fuse, chain.plan(), C, n, cut)
