@@ -175,12 +175,15 @@ def side_config(args, L, torch, dev, rank, world, barrier, max_over_ranks):
                 o = L.NCO(channels=C); o.set_frequencies((0.3 + 1e-5 * np.arange(C)).astype(np.float32)); o.set_direction(True)
                 chain = L.Chain(o); bps, out_real = 16.0, False
             elif args.next == "agc":
-                chain = L.Chain(L.AGC(channels=C)); bps, out_real = 16.0, False
+                agc = L.AGC(channels=C); agc.precision = args.agc_precision
+                chain = L.Chain(agc); bps, out_real = 16.0, False
             elif args.next == "fm":
                 chain = L.Chain(L.FreqDem(0.1, channels=C)); bps, out_real, kind = 12.0, True, 3
             else:
                 chain = L.Chain(L.DeemphasisFilter(48000, channels=C)); bps, out_real, in_real = 8.0, True, True
             name = "8a: %s alone, 65536 channels x 16384 samples" % args.next
+            if args.next == "agc":
+                name += " (precision %s)" % args.agc_precision
         else:
             raise SystemExit("unknown --next row")
     if args.block != BLOCK:
@@ -234,6 +237,8 @@ def main():
     ap.add_argument("--next", default="", help="side line: bam, ssb, fmstereo, rrrf, cresamp, rfir (SURVEY 8f); iir, nco, agc, fm, deemph (8a stages alone)")
     ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 5 (default, the headline AM receiver), 2 FIR, 3 NCO+resampler, 4 IIR+AGC+FM")
+    ap.add_argument("--agc-precision", default="auto", choices=["auto", "exact", "fast"],
+                    help="--next agc: gain-loop arithmetic of the stage alone (auto = exact for a stage on its own)")
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

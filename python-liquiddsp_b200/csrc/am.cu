@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
     auto load_x = [&](long long k) -> float2 {
         return a.in_tmajor ? a.x[k * a.in_pitch + cl] : a.x[cl * a.in_pitch + k];
     };
+    const AgcFast agck{a.agc.alpha, a.agc.chi, a.agc.clo, a.agc.cl2, a.agc.chalf, a.agc.scale};
     auto agc_step = [&](float2 z) -> float2 {
+        if (HAS_AGC && a.agc.fast) return agc_step_fast(z, agc_g, agc_y2p, agck);
         // agc_crcf_execute (liquid agc.proto.c) then the wrapper's status poll, agc.hpp:115-125
         float yr = __fmul_rn(z.x, agc_g), yi = __fmul_rn(z.y, agc_g);
         const float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
@@ -234,18 +236,38 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
 // AGC alone over a time-major [sample][channel] block, in place.  The gain loop is one long dependent chain per
 // sample (double-precision smoothing, log, exp); on its own it needs no shared-memory windows, so all 2048
 // threads of an SM can be resident and the chains of ~14 warps hide each other.
+// FAST: unlocked, squelch disabled -- the single-precision gain loop (devmath.cuh agc_step_fast).  Its chain is short
+// enough that the loads become the limit, so 16 samples per thread are in flight instead of 4.
+template <bool FAST, int U>
 __global__ void __launch_bounds__(128) agc_tmajor_kernel(const __grid_constant__ AmTailArgs a)
 {
-    __shared__ double2 s_log[128];
+    __shared__ double2 s_log[FAST ? 1 : 128];
     const int tid = threadIdx.x;
     const long long chl = (long long)blockIdx.x * blockDim.x + tid;
-    for (int i = tid; i < 128; i += blockDim.x) s_log[i] = a.agc.logtab[i];
-    __syncthreads();
+    if constexpr (!FAST) {
+        for (int i = tid; i < 128; i += blockDim.x) s_log[i] = a.agc.logtab[i];
+        __syncthreads();
+    }
     if (chl >= a.C) return;
     const long long gch = a.ch0 + chl, N = a.n, P = a.in_pitch;
     float agc_g = a.agc.g[gch], agc_y2p = a.agc.y2p[gch]; int agc_mode = a.agc.mode[gch]; unsigned agc_timer = a.agc.timer[gch], agc_rises = 0;
     float2 *x = const_cast<float2 *>(a.x) + chl;
-    constexpr int U = 4;
+    if constexpr (FAST) {
+        const AgcFast k{a.agc.alpha, a.agc.chi, a.agc.clo, a.agc.cl2, a.agc.chalf, a.agc.scale};
+        float2 zn[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) zn[u] = u < N ? x[u * P] : make_float2(0.f, 0.f);
+        long long k0 = 0;
+        for (; k0 + U <= N; k0 += U) {
+            float2 z[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { z[u] = zn[u]; zn[u] = k0 + U + u < N ? x[(k0 + U + u) * P] : make_float2(0.f, 0.f); }
+#pragma unroll
+            for (int u = 0; u < U; u++) x[(k0 + u) * P] = agc_step_fast(z[u], agc_g, agc_y2p, k);
+        }
+        for (int u = 0; k0 + u < N; u++) x[(k0 + u) * P] = agc_step_fast(x[(k0 + u) * P], agc_g, agc_y2p, k);
+        a.agc.g[gch] = agc_g; a.agc.y2p[gch] = agc_y2p;
+    } else {
     float2 zn[U];
 #pragma unroll
     for (int u = 0; u < U; u++) zn[u] = u < N ? x[u * P] : make_float2(0.f, 0.f);
@@ -288,6 +310,7 @@ __global__ void __launch_bounds__(128) agc_tmajor_kernel(const __grid_constant__
     }
     a.agc.g[gch] = agc_g; a.agc.y2p[gch] = agc_y2p; a.agc.mode[gch] = agc_mode; a.agc.timer[gch] = agc_timer;
     if (agc_rises) atomicAdd(a.agc.rise_count, agc_rises);
+    }
 }
 
 typedef void (*AmFn)(const AmTailArgs);
@@ -297,7 +320,8 @@ typedef void (*AmFn)(const AmTailArgs);
 cudaError_t agc_tmajor_launch(const AmTailArgs &a, cudaStream_t stream)
 {
     if (a.C <= 0 || a.n <= 0) return cudaSuccess;
-    agc_tmajor_kernel<<<(unsigned)((a.C + 127) / 128), 128, 0, stream>>>(a);
+    if (a.agc.fast) agc_tmajor_kernel<true, 16><<<(unsigned)((a.C + 127) / 128), 128, 0, stream>>>(a);
+    else            agc_tmajor_kernel<false, 4><<<(unsigned)((a.C + 127) / 128), 128, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -307,8 +331,7 @@ cudaError_t amtail_launch(bool has_agc, bool has_de, const AmTailArgs &a, cudaSt
     if (has_agc && a.in_tmajor) {
         // time-major hand-off buffer (chain-internal scratch): gain control in place at full occupancy, then the
         // window-bound demodulator without it
-        agc_tmajor_kernel<<<(unsigned)((a.C + 127) / 128), 128, 0, stream>>>(a);
-        cudaError_t rc0 = cudaGetLastError();
+        cudaError_t rc0 = agc_tmajor_launch(a, stream);
         if (rc0 != cudaSuccess) return rc0;
         has_agc = false;
     }

@@ -377,6 +377,11 @@ struct NcoStage : lqb_stage_s {
 
 struct AgcStage : lqb_stage_s {
     float alpha = 1e-2f, scale = 1.f, threshold = 0.f; int locked = 0; bool squelch = false; unsigned timeout = 100;
+    // Which gain loop runs (devmath.cuh): the general one evaluates the oracle's operations bit for bit (double-precision
+    // smoothing, correctly rounded log / exp); the single-precision one is 1e-7 from it and 3-4x faster.  A carrier PLL
+    // behind the AGC amplifies a last-bit difference to 1e-4..1e-3, so AUTO takes the single-precision loop
+    // only where the planner sees a feed-forward discriminator (FreqDem) and no PLL demodulator downstream.
+    int precision = LQB_AGC_AUTO; bool plan_fast = false;
     DevArr<float> g, y2p; DevArr<int> mode; DevArr<unsigned> timer, rise;
     AgcStage(int c) : lqb_stage_s(K_AGC, c) {}
     int materialize() override
@@ -395,6 +400,9 @@ struct AgcStage : lqb_stage_s {
     {
         LQB_TRY(log_table_dev(&p.logtab));
         p.alpha = alpha; p.scale = scale; p.threshold = threshold; p.one_minus_alpha = 1.0 - (double)alpha;
+        p.chi = (float)p.one_minus_alpha; p.clo = (float)(p.one_minus_alpha - (double)p.chi);
+        p.chalf = -0.5f * alpha; p.cl2 = (float)((double)p.chalf * 0.6931471805599453094);
+        p.fast = (!locked && !squelch && (precision == LQB_AGC_FAST || (precision == LQB_AGC_AUTO && plan_fast))) ? 1 : 0;
         p.locked = locked; p.timeout = timeout; p.g = g.p; p.y2p = y2p.p; p.mode = mode.p; p.timer = timer.p;
         p.rise_count = rise.p;
         return LQB_OK;
@@ -698,6 +706,16 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
     }
     c->plan.clear();
     for (size_t k = 0; k < segs.size(); k++) c->plan += (k ? " -> " : "") + segs[k].name;
+    // gain-loop precision (AgcStage::precision): single precision where a discriminator follows and no carrier PLL does
+    for (size_t i = 0; i < st.size(); i++) {
+        if (st[i]->kind != K_AGC) continue;
+        bool fm = false, pll = false;
+        for (size_t k = i + 1; k < st.size(); k++) {
+            fm  = fm  || st[k]->kind == K_FM;
+            pll = pll || st[k]->kind == K_AM || st[k]->kind == K_BAM || st[k]->kind == K_FMST;
+        }
+        static_cast<AgcStage *>(st[i])->plan_fast = fm && !pll;
+    }
     return LQB_OK;
 }
 
@@ -1430,6 +1448,13 @@ int lqb_agc_get_gain_per_channel(lqb_stage s, float *g, int n)
 { LQB_GET(AgcStage, q, s, K_AGC); if (n < 0 || n > q->C) return fail(LQB_EINVAL, "bad channel count"); LQB_TRY(q->ensure()); LQB_CUDA(cudaDeviceSynchronize()); return q->g.download(g, n); }
 int lqb_agc_set_scale(lqb_stage s, float sc) { LQB_GET(AgcStage, q, s, K_AGC); if (!(sc > 0.f)) return fail(LQB_EINVAL, "agc scale must be > 0"); q->scale = sc; return LQB_OK; }
 int lqb_agc_get_scale(lqb_stage s, float *sc) { LQB_GET(AgcStage, q, s, K_AGC); *sc = q->scale; return LQB_OK; }
+int lqb_agc_set_precision(lqb_stage s, int mode)
+{
+    LQB_GET(AgcStage, q, s, K_AGC);
+    if (mode != LQB_AGC_AUTO && mode != LQB_AGC_EXACT && mode != LQB_AGC_FAST) return fail(LQB_EINVAL, "agc precision must be LQB_AGC_AUTO, _EXACT or _FAST");
+    q->precision = mode; return LQB_OK;
+}
+int lqb_agc_get_precision(lqb_stage s, int *mode) { LQB_GET(AgcStage, q, s, K_AGC); *mode = q->precision; return LQB_OK; }
 int lqb_agc_lock(lqb_stage s, int locked) { LQB_GET(AgcStage, q, s, K_AGC); q->locked = locked ? 1 : 0; return LQB_OK; }
 int lqb_agc_squelch_enable(lqb_stage s, int en)
 {

@@ -218,6 +218,44 @@ __device__ __forceinline__ float log_rn(float x, const double2 *__restrict__ tab
     return (float)fma(p, r, fma((double)e, 0.6931471805599453094, t.y));
 }
 
+// ---- the gain loop in single precision (agc_crcf_execute, unlocked, squelch disabled) ----------------------------
+// liquid: y = x g;  y2' = (1.0 - alpha) y2' + alpha |y|^2 (double product, one rounding);  g *= expf(-alpha/2 logf(y2'))
+// The loop is one dependent chain per sample and the kernel's speed IS that chain's latency, so it is kept to
+// FP32 pipe operations and one MUFU:
+//   * (1 - alpha) is split into two floats chi + clo = 1 - alpha exactly; chi y2' + clo y2' is formed as a
+//     head + tail pair while the previous sample's logarithm is still in flight; the chain adds alpha |y|^2 into the
+//     tail and then the head, so y2' is rounded once at full magnitude as liquid's double expression is;
+//   * a = -alpha/2 ln(y2') = (-alpha/2 ln 2) lg2.approx(y2'): absolute error 2^-22 ln2 alpha/2 = 8e-10 at alpha = 0.01,
+//     against the 3e-8 granularity of the factor exp(a) near 1;
+//   * exp(a) = 1 + (a + a^2 q(a)), q of degree 5: the sum is rounded ONCE, which is expf correctly rounded except
+//     within ~ulp(a) of a tie, so the loop has liquid's own dead zone around y2' = 1 and no bias (a one-ulp bias in
+//     the factor would shift the settled gain by bias / alpha).  |a| > 1/4 (the first samples of an acquisition at
+//     large alpha) takes ex2.approx instead.
+// Measured against the oracle's correctly rounded double evaluation: relative L2 1e-7 (tests/test_parity_gpu.py).
+struct AgcFast {
+    float alpha, chi, clo, cl2, c, scale;      // cl2 = -alpha/2 ln 2, c = -alpha/2
+};
+__device__ __forceinline__ float2 agc_step_fast(float2 z, float &g, float &y2p, const AgcFast &k)
+{
+    // off the chain (y2' is a sample old): chi y2' as head + tail, clo y2' folded into the tail
+    const float h = __fmul_rn(k.chi, y2p), l = __fmaf_rn(k.clo, y2p, __fmaf_rn(k.chi, y2p, -h));
+    const float yr = __fmul_rn(z.x, g), yi = __fmul_rn(z.y, g);
+    const float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
+    y2p = __fadd_rn(h, __fmaf_rn(k.alpha, y2, l));
+    float l2; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(y2p));
+    const float a = __fmul_rn(k.cl2, l2);
+    float eb; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(__fmul_rn(k.c, l2)));
+    const float a2 = __fmul_rn(a, a);
+    const float q0 = __fmaf_rn(a, 1.0f / 6.0f, 0.5f), q1 = __fmaf_rn(a, 1.0f / 120.0f, 1.0f / 24.0f), q2 = __fmaf_rn(a, 1.0f / 5040.0f, 1.0f / 720.0f);
+    const float q = __fmaf_rn(__fmaf_rn(q2, a2, q1), a2, q0);
+    const float ep = __fadd_rn(1.0f, __fmaf_rn(a2, q, a));
+    const bool upd = y2p > 1e-6f;
+    const float ebs = upd ? eb : 1.0f;
+    const float e = (upd && fabsf(a) <= 0.25f) ? ep : ebs;
+    g = fminf(__fmul_rn(g, e), 1e6f);
+    return make_float2(__fmul_rn(yr, k.scale), __fmul_rn(yi, k.scale));
+}
+
 // bytes_to_iq (reference utility.hpp:61-69): (float)s / 32767.0f for an int16 pair.  One Newton step on s * fl(1/32767)
 // gives the correctly rounded quotient for every one of the 65536 possible inputs (checked exhaustively in
 // tests/test_oracle_kat.py), without an IEEE division per sample.

@@ -49,6 +49,8 @@ struct ResampP {
 struct AgcP {
     float alpha, scale, threshold;
     double one_minus_alpha;
+    float chi, clo, cl2, chalf;    // single-precision gain loop (devmath.cuh agc_step_fast): chi + clo = 1 - alpha, cl2 = -alpha/2 ln 2, chalf = -alpha/2
+    int fast;                      // unlocked and squelch disabled on every channel: the single-precision loop applies
     int locked;
     unsigned timeout;
     float *g, *y2p;                // [Ctot]

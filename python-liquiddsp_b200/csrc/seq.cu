@@ -294,8 +294,11 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     };
 
     // ---- what happens to one sample on the decimated / demodulated side of the chain ----
+    const AgcFast agck{a.agc.alpha, a.agc.chi, a.agc.clo, a.agc.cl2, a.agc.chalf, a.agc.scale};
+    const bool agc_fast = HAS_AGC && a.agc.fast != 0;             // unlocked, no squelch: the single-precision gain loop
     auto agc_apply = [&](float2 z) -> float2 {
         if constexpr (HAS_AGC) {
+            if (agc_fast) return agc_step_fast(z, agc_g, agc_y2p, agck);
             // agc_crcf_execute (liquid agc.proto.c) then the wrapper's status poll, agc.hpp:115-125
             float yr = __fmul_rn(z.x, agc_g), yi = __fmul_rn(z.y, agc_g);
             float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
@@ -392,6 +395,8 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     };
 
     auto tail = [&](float2 z, int jtile) { post(agc_apply(z), jtile); };
+    // the same with the gain loop known to be the short one: no branch, so an unrolled tile is one basic block
+    auto tail_fast = [&](float2 z, int jtile) { post(agc_step_fast(z, agc_g, agc_y2p, agck), jtile); };
 
     // ---- one full-rate sample: oscillator and IIR; returns the (complex) value handed on ----
     auto head = [&](float2 xin) -> u64 {
@@ -561,7 +566,12 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 // leaves its outputs in the thread's own staged row; the stages after it then walk the row in a
                 // rolled loop -- the AGC / discriminator bodies are long, 16 unrolled copies would not fit the
                 // instruction cache
-                {
+                // fused == true: the single-precision gain loop (and the discriminator) follow each cascade output in
+                // the same unrolled tile.  The gain loop is ONE dependent chain per channel (about 70 cycles a sample) and
+                // with 16384 channels a scheduler holds a single warp, so nothing but this warp's own independent work
+                // can fill the chain's latency: in one basic block the cascade of the samples ahead and the
+                // discriminator of the samples behind are exactly that work
+                auto cascade = [&](auto fused) {
                     u64 xs[TS], yy[NS];
                     ld_row(row, xs);
 #pragma unroll
@@ -578,27 +588,43 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                                 y = fma2(cb2[sct], iv2[sct], y);
                                 iv2[sct] = iv1[sct]; iv1[sct] = v0; yy[sct] = y;
                                 if (sct == NS - 1) {
-                                    if constexpr (HAS_AGC || HAS_FM) *(float2 *)(const_cast<unsigned char *>(row) + soff(j)) = upk(y);
+                                    if constexpr (decltype(fused)::value) tail_fast(upk(y), j);
+                                    else if constexpr (HAS_AGC || HAS_FM) *(float2 *)(const_cast<unsigned char *>(row) + soff(j)) = upk(y);
                                     else tail(upk(y), j);
                                 }
                             }
                         }
                     }
-                }
-                // then one pass per remaining stage: the gain loop is a long serial chain per sample and runs rolled;
-                // the discriminator has no feedback, so its 16 samples are independent work for the scheduler
-                if constexpr (HAS_AGC) {
-                    unsigned char *rw = const_cast<unsigned char *>(row);
+                };
+                if (HAS_AGC && agc_fast) {
+                    if constexpr (HAS_AGC) cascade(std::true_type{});
+                } else {
+                    cascade(std::false_type{});
+                    // then one pass per remaining stage: the general gain loop (locked / squelch: double-precision
+                    // functions, state machine) is a long serial chain per sample and runs rolled;
+                    // the discriminator has no feedback, so its 16 samples are independent work for the scheduler
+                    if constexpr (HAS_AGC) {
+                        unsigned char *rw = const_cast<unsigned char *>(row);
 #pragma unroll 1
-                    for (int j = 0; j < TS; j++) { float2 *pz = (float2 *)(rw + soff(j)); *pz = agc_apply(*pz); }
-                }
-                if constexpr (HAS_AGC || HAS_FM) {
+                        for (int j = 0; j < TS; j++) { float2 *pz = (float2 *)(rw + soff(j)); *pz = agc_apply(*pz); }
+                    }
+                    if constexpr (HAS_AGC || HAS_FM) {
 #pragma unroll 4
-                    for (int j = 0; j < TS; j++) post(ld1(row, j), j);
+                        for (int j = 0; j < TS; j++) post(ld1(row, j), j);
+                    }
                 }
             } else if constexpr (HAS_AGC || HAS_FM) {
+                if (HAS_AGC && agc_fast) {
+                    if constexpr (HAS_AGC) {
+                        u64 xs[TS];
+                        ld_row(row, xs);
+#pragma unroll
+                        for (int j = 0; j < TS; j++) tail_fast(upk(head(upk(xs[j]))), j);
+                    }
+                } else {
 #pragma unroll 2
-                for (int j = 0; j < TS; j++) tail(upk(head(ld1(row, j))), j);
+                    for (int j = 0; j < TS; j++) tail(upk(head(ld1(row, j))), j);
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < TS; j += 2) {

@@ -79,6 +79,7 @@ _SIG = {
     "lqb_agc_set_rssi": [_P, _F], "lqb_agc_get_rssi": [_P, C.POINTER(_F)],
     "lqb_agc_set_gain": [_P, _F], "lqb_agc_get_gain": [_P, C.POINTER(_F)], "lqb_agc_get_gain_per_channel": [_P, _P, _I],
     "lqb_agc_set_scale": [_P, _F], "lqb_agc_get_scale": [_P, C.POINTER(_F)], "lqb_agc_lock": [_P, _I],
+    "lqb_agc_set_precision": [_P, _I], "lqb_agc_get_precision": [_P, C.POINTER(_I)],
     "lqb_agc_squelch_enable": [_P, _I], "lqb_agc_squelch_set_threshold": [_P, _F],
     "lqb_agc_squelch_get_threshold": [_P, C.POINTER(_F)], "lqb_agc_squelch_set_timeout": [_P, _U],
     "lqb_agc_squelch_get_status": [_P, C.POINTER(_I)], "lqb_agc_take_rise_count": [_P, C.POINTER(_U)],
@@ -536,6 +537,21 @@ class AGC(_Stage):
     level_dB = property(lambda s: s._getf(_lib.lqb_agc_get_rssi), lambda s, v: _ck(_lib.lqb_agc_set_rssi(s._h, v)))
     gain = property(lambda s: s._getf(_lib.lqb_agc_get_gain), lambda s, v: _ck(_lib.lqb_agc_set_gain(s._h, v)))
     scale = property(lambda s: s._getf(_lib.lqb_agc_get_scale), lambda s, v: _ck(_lib.lqb_agc_set_scale(s._h, v)))
+
+    _PRECISIONS = ("auto", "exact", "fast")
+
+    @property
+    def precision(self):
+        """Gain-loop arithmetic (not in the reference): 'exact' is bit-identical to the oracle's liquid restatement,
+        'fast' is the single-precision loop (1e-7 from it), 'auto' (default) lets a Chain take 'fast' where a FreqDem
+        follows and no carrier-PLL demodulator does (include/liquiddsp_b200.h, lqb_agc_set_precision)."""
+        v = _I(); _ck(_lib.lqb_agc_get_precision(self._h, C.byref(v))); return self._PRECISIONS[v.value]
+
+    @precision.setter
+    def precision(self, mode):
+        if mode not in self._PRECISIONS:
+            raise ValueError("precision must be one of %r" % (self._PRECISIONS,))
+        _ck(_lib.lqb_agc_set_precision(self._h, self._PRECISIONS.index(mode)))
 
     @property
     def status(self):

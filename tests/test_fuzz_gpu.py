@@ -40,6 +40,8 @@ def _complex_stage(rng, C):
     if k == 4:
         g = L.AGC(channels=C); o = O.AGC()
         g.scale = o.scale = 0.5
+        # precision 'auto': the bit-exact loop unless a FreqDem follows and no PLL demodulator does (then 1e-7 from it,
+        # under a feed-forward discriminator checked at 1e-4)
         return g, o, True, "agc"
     if k == 5:
         b = (0.3 * rng.standard_normal(int(rng.integers(1, 6)))).astype(np.float32); a = np.array([1.0, -0.5, 0.1], np.float32)

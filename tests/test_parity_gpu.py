@@ -516,6 +516,58 @@ def test_agc_default_and_readme_settings(cuda):
         assert abs(g.gain / o.gain - 1) < 1e-5 and abs(g.level_dB - o.level_dB) < 1e-3
 
 
+def test_agc_precision_modes(cuda):
+    """'exact' reproduces the oracle's gain loop bit for bit; 'fast' (single precision, lg2.approx) stays within 1e-6 of it --
+    a tenth of the per-stage tolerance -- over acquisition, a 26 dB level step and the settled loop, at three bandwidths."""
+    rng = np.random.default_rng(14)
+    x = crandn(rng, 40000, scale=0.05)
+    x[20000:] *= 20
+    t = np.arange(40000) / 48000.0
+    am = (0.1 * (1 + 0.5 * np.sin(2 * np.pi * 1000 * t)) * np.exp(2j * np.pi * 200 * t)).astype(np.complex64) + crandn(rng, 40000, scale=0.01)
+    cw = (0.3 * np.exp(1j * (0.3 * np.arange(40000)))).astype(np.complex64)          # noise-free: liquid's dead zone around y2' = 1
+    for sig in (x, am, cw):
+        for bw in (1e-2, 1e-3, 0.2, 1.0):
+            ge, gf, o = L.AGC(), L.AGC(), O.AGC()
+            assert ge.precision == "auto"
+            ge.precision = "exact"; gf.precision = "fast"
+            assert (ge.precision, gf.precision) == ("exact", "fast")
+            for q in (ge, gf, o):
+                q.lock = False; q.scale = 0.5; q.bandwidth = bw
+            yo = np.concatenate([o(sig[:17001]), o(sig[17001:])])
+            ye = np.concatenate([ge(sig[:17001]), ge(sig[17001:])])
+            yf = np.concatenate([gf(sig[:17001]), gf(sig[17001:])])
+            assert np.array_equal(ye.view(np.uint32), yo.view(np.uint32)), bw
+            assert rel_l2(yf, yo) <= 1e-6, (bw, rel_l2(yf, yo))
+            assert abs(gf.gain / o.gain - 1) < 2e-6
+    with pytest.raises(ValueError):
+        L.AGC().precision = "sloppy"
+
+
+def test_agc_auto_precision_follows_the_chain(cuda):
+    """AUTO: single precision only where a FreqDem follows and no carrier PLL does; in front of AmpModem (the README chain)
+    and on its own the AGC stays bit-identical to the oracle."""
+    rng = np.random.default_rng(15)
+    C, n = 40, 6000
+    x = np.stack([am_iq(n, fs=48000.0, f_off=30.0 + c, phase=0.1 * c, seed=900 + c, noise=0.02, amp=0.3) for c in range(C)])
+    # AGC -> AmpModem: exact
+    chain = L.Chain(L.AGC(channels=C), L.AmpModem(0.5, "dsb", True, channels=C))
+    y = chain(x)
+    oa, om = O.AGC(), O.AmpModem(0.5, "dsb", True)
+    assert np.array_equal(y[7].view(np.uint32), om(oa(x[7])).view(np.uint32))
+    # AGC alone in a chain: exact
+    y = L.Chain(L.AGC(channels=C))(x)
+    assert np.array_equal(y[3].view(np.uint32), O.AGC()(x[3]).view(np.uint32))
+    # AGC -> FreqDem: the fast loop -- not bit-identical to the exact chain, and well inside the tolerance
+    fast = L.Chain(L.AGC(channels=C), L.FreqDem(0.2, channels=C))
+    ex_agc = L.AGC(channels=C); ex_agc.precision = "exact"
+    exact = L.Chain(ex_agc, L.FreqDem(0.2, channels=C))
+    yf, ye = fast(x), exact(x)
+    yo = O.FreqDem(0.2)(O.AGC()(x[5]))
+    assert np.linalg.norm(ye[5] - yo) / np.sqrt(n) <= 2.5 * TOL_STAGE
+    assert np.linalg.norm(yf[5] - yo) / np.sqrt(n) <= 2.5 * TOL_STAGE     # phase-difference scale: |y| <= 1 / (2 kf) = 2.5
+    assert abs(fast.stages[0].gains()[5] / exact.stages[0].gains()[5] - 1) < 2e-6
+
+
 def test_agc_lock_and_properties(cuda):
     rng = np.random.default_rng(12)
     x = crandn(rng, 5000, scale=0.2)
