@@ -263,6 +263,19 @@ int lqb_chain_get_timing(lqb_chain c, float *ms_per_segment, int capacity, int *
 /* 0 = one kernel per stage, 1 = default (full-rate front and decimated tail as two kernels),
  * 2 = longest possible runs (whole AM receiver in one kernel); results are identical */
 int lqb_chain_set_fusion(lqb_chain c, int level);
+/* Overlapped device calls (default off).  The reference's objects are called block after block with their state carried
+ * (README.md:53-58); block k+1's full-rate front depends on block k's front only.  With overlap enabled,
+ * lqb_chain_execute_dev on a chain whose plan is "full-rate decimating kernel -> decimated-rate tail" (the AM receivers)
+ * issues the tail on the chain's own low-priority stream and returns the caller's stream free for the next block's front,
+ * which then runs concurrently with it (the front stages through a shallower ring so that a tail CTA fits beside it on
+ * every SM).  Results are identical.  The output of such a call is complete only after
+ * lqb_chain_wait(chain, stream) has made `stream` wait for every tail issued so far; any non-overlapped call on the
+ * chain waits by itself.  Create the calling stream with lqb_stream_create(&s, 1) (high priority) so that a front is
+ * dispatched ahead of the tail queued before it. */
+int lqb_chain_set_overlap(lqb_chain c, int enabled);
+int lqb_chain_wait(lqb_chain c, void *stream);
+int lqb_stream_create(void **stream, int high_priority);
+int lqb_stream_destroy(void *stream);
 
 /* ---------------- synthetic input generators, device side -----------------------
  * Fill x_dev [n_channels x n] with the benchmark signal for blocks starting at absolute sample

@@ -544,7 +544,14 @@ struct lqb_chain_s {
     cudaEvent_t ev_ready[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr };   // time-sliced host pipeline
     // device-execute scratch
     lqb::DevArr<char> d_tmp[2], d_cvt;
-    // optional per-segment timing of execute_dev: one event pair per segment per call, on the caller's stream
+    // overlapped device calls (lqb_chain_set_overlap): the decimated-rate tail of call k runs on tail_stream while the
+    // caller's stream already runs the full-rate front of call k+1; the hand-off buffer alternates between d_tmp[0] / [1]
+    bool overlap = false;
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t ev_front[2] = { nullptr, nullptr }, ev_tail[2] = { nullptr, nullptr };
+    bool tail_pending[2] = { false, false };
+    unsigned ov_calls = 0;
+    // optional per-segment timing of execute_dev: one event pair per segment per call, on the stream the segment ran on
     bool timing = false;
     std::vector<std::vector<std::pair<cudaEvent_t, cudaEvent_t>>> timed_calls;
     void clear_timing()
@@ -554,6 +561,8 @@ struct lqb_chain_s {
     }
     ~lqb_chain_s()
     {
+        if (tail_stream) { cudaStreamSynchronize(tail_stream); cudaStreamDestroy(tail_stream); }
+        for (int b = 0; b < 2; b++) { if (ev_front[b]) cudaEventDestroy(ev_front[b]); if (ev_tail[b]) cudaEventDestroy(ev_tail[b]); }
         clear_timing();
         for (auto &s : streams) if (s) cudaStreamDestroy(s);
         for (int b = 0; b < 2; b++) { if (ev_ready[b]) cudaEventDestroy(ev_ready[b]); if (ev_free[b]) cudaEventDestroy(ev_free[b]); }
@@ -723,7 +732,7 @@ static size_t seg_out_len(const Segment &g, size_t n) { for (auto *s : g.st) n =
 
 // run one segment on channels [ch0, ch0 + nch) of the chain; x/y point at the first of those rows
 static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_t n_out, int ch0, int nch, cudaStream_t stream,
-                       bool in_tmajor, bool out_tmajor, int *launches, unsigned extra_mask = 0)
+                       bool in_tmajor, bool out_tmajor, int *launches, unsigned extra_mask = 0, int front_ring = 3)
 {
     (*launches)++;
     const lqb_stage_s *first = g.st.front();
@@ -868,7 +877,8 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         if (const char *e = getenv("LQB_FRONT2")) two = two && atoi(e) != 0;
         if (two && make_input_tmap(&a.tmap, x, n, (size_t)nch, kFront2BoxRows)) {
             a.cpw = 32; a.use_tma = 1;
-            LQB_CUDA(front2_launch(g.nsos, a, stream));
+            if (const char *e = getenv("LQB_FRONT_RING")) { const int v = atoi(e); if (v == 2 || v == 3) front_ring = v; }   // tuning override
+            LQB_CUDA(front2_launch(g.nsos, a, stream, front_ring));
             return LQB_OK;
         }
     }
@@ -951,6 +961,66 @@ static void advance_all(lqb_chain_s *c, size_t n) { for (auto *s : c->stages) { 
 
 static int chain_out_len(lqb_chain_s *c, size_t n, size_t *n_out) { for (auto *s : c->stages) n = s->out_len(n); *n_out = n; return LQB_OK; }
 
+// ---- overlapped device calls -------------------------------------------------------------------------------------
+// The AM receiver is a full-rate front kernel (97.6 % of the samples, FP32-pipe and HBM bound) and a decimated-rate tail
+// (gain loop, carrier PLL, two 51-tap filters: latency bound, 18 % of a call's time on 2.4 % of the samples).  Calls
+// carry state, so call k+1's front only needs call k's FRONT: with overlap enabled the tail of call k is issued on the
+// chain's own stream behind an event and the caller's stream goes straight on to the next front.  The front then
+// stages through a 2-deep ring (20 KB per CTA) so that one tail CTA fits beside its seven CTAs on every SM, and the
+// tail's dependent chains fill issue slots the front leaves empty.  The caller's stream should be created with a
+// higher priority than the default (lqb_stream_create) so that a front is dispatched ahead of the tail queued before it.
+// Results of an overlapped call are complete once lqb_chain_wait(chain, stream) has been waited on.
+static bool overlappable(const lqb_chain_s *c, const std::vector<Segment> &segs, bool in_i16)
+{
+    return c->overlap && !in_i16 && segs.size() == 2 && segs[0].type == Segment::SEQ && (segs[0].mask & F_RS) &&
+           (segs[1].type == Segment::AMTAIL || segs[1].type == Segment::BAM);
+}
+
+static int chain_join_tails(lqb_chain_s *c, cudaStream_t stream)
+{
+    for (int b = 0; b < 2; b++)
+        if (c->tail_pending[b]) { LQB_CUDA(cudaStreamWaitEvent(stream, c->ev_tail[b], 0)); }
+    return LQB_OK;
+}
+
+static int run_overlapped(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, void *y, size_t n, int C, size_t tmpb,
+                          cudaStream_t stream, bool in_i16)
+{
+    if (!c->tail_stream) {
+        int lo = 0, hi = 0;
+        LQB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        LQB_CUDA(cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, lo));
+        for (int b = 0; b < 2; b++) {
+            LQB_CUDA(cudaEventCreateWithFlags(&c->ev_front[b], cudaEventDisableTiming));
+            LQB_CUDA(cudaEventCreateWithFlags(&c->ev_tail[b], cudaEventDisableTiming));
+        }
+    }
+    LQB_TRY(c->d_tmp[0].reserve(tmpb)); LQB_TRY(c->d_tmp[1].reserve(tmpb));
+    const int b = (int)(c->ov_calls++ & 1u);
+    char *tmp = c->d_tmp[b].p;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+    if (c->timing && c->timed_calls.size() < 1024) {
+        evs.resize(2);
+        for (auto &p : evs) { LQB_CUDA(cudaEventCreate(&p.first)); LQB_CUDA(cudaEventCreate(&p.second)); }
+    }
+    const size_t on0 = seg_out_len(segs[0], n), on = seg_out_len(segs[1], on0);
+    // the front writes the hand-off buffer the tail of two calls ago read
+    if (c->tail_pending[b]) LQB_CUDA(cudaStreamWaitEvent(stream, c->ev_tail[b], 0));
+    if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[0].first, stream));
+    LQB_TRY(run_segment(segs[0], x, tmp, n, on0, 0, C, stream, false, true, &c->last_launches, 0u, 2));
+    if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[0].second, stream));
+    LQB_CUDA(cudaEventRecord(c->ev_front[b], stream));
+    LQB_CUDA(cudaStreamWaitEvent(c->tail_stream, c->ev_front[b], 0));
+    if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[1].first, c->tail_stream));
+    if (on > 0 || on0 > 0) LQB_TRY(run_segment(segs[1], tmp, y, on0, on, 0, C, c->tail_stream, true, false, &c->last_launches));
+    if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[1].second, c->tail_stream));
+    LQB_CUDA(cudaEventRecord(c->ev_tail[b], c->tail_stream));
+    c->tail_pending[b] = true;
+    if (!evs.empty()) c->timed_calls.push_back(std::move(evs));
+    (void)in_i16;
+    return LQB_OK;
+}
+
 static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, size_t cap, size_t *n_out, cudaStream_t stream, bool in_i16 = false)
 {
     LQB_TRY(chain_validate(c));
@@ -967,7 +1037,12 @@ static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, s
     if (segs.size() > 1) LQB_TRY(c->d_tmp[0].reserve(tmpb));
     if (segs.size() > 2) LQB_TRY(c->d_tmp[1].reserve(tmpb));
     if (in_i16 && !first_takes_i16(segs)) LQB_TRY(c->d_cvt.reserve((size_t)C * n * 8));
-    LQB_TRY(run_all(c, segs, x, y, n, 0, C, c->d_tmp[0].p, c->d_tmp[1].p, stream, &c->last_launches, c->timing, in_i16, c->d_cvt.p));
+    if (overlappable(c, segs, in_i16)) {
+        LQB_TRY(run_overlapped(c, segs, x, y, n, C, tmpb, stream, in_i16));
+    } else {
+        LQB_TRY(chain_join_tails(c, stream));                    // tails of earlier overlapped calls come first
+        LQB_TRY(run_all(c, segs, x, y, n, 0, C, c->d_tmp[0].p, c->d_tmp[1].p, stream, &c->last_launches, c->timing, in_i16, c->d_cvt.p));
+    }
     advance_all(c, n);
     return LQB_OK;
 }
@@ -1652,6 +1727,28 @@ int lqb_chain_get_timing(lqb_chain c, float *ms, int cap, int *n_segments, int *
         }
     return LQB_OK;
 }
+int lqb_chain_set_overlap(lqb_chain c, int enabled)
+{
+    if (!c) return fail(LQB_EINVAL, "null chain");
+    if (c->tail_stream) LQB_CUDA(cudaStreamSynchronize(c->tail_stream));
+    c->tail_pending[0] = c->tail_pending[1] = false;
+    c->overlap = enabled != 0;
+    return LQB_OK;
+}
+int lqb_chain_wait(lqb_chain c, void *stream)
+{
+    if (!c) return fail(LQB_EINVAL, "null chain");
+    return chain_join_tails(c, (cudaStream_t)stream);
+}
+int lqb_stream_create(void **stream, int high_priority)
+{
+    if (!stream) return fail(LQB_EINVAL, "null argument");
+    int lo = 0, hi = 0;
+    LQB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t s; LQB_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+    *stream = (void *)s; return LQB_OK;
+}
+int lqb_stream_destroy(void *stream) { if (stream) LQB_CUDA(cudaStreamDestroy((cudaStream_t)stream)); return LQB_OK; }
 int lqb_chain_set_fusion(lqb_chain c, int level) { if (!c || level < 0 || level > 2) return fail(LQB_EINVAL, "fusion level must be 0, 1 or 2"); c->fuse = level; return LQB_OK; }
 
 // ---- synthetic inputs

@@ -20,11 +20,13 @@
 namespace lqb {
 namespace {
 
-constexpr int BT = 32, TS = 16, NST = 3, CPT = 2;     // one warp per CTA: 1024 CTAs for 65536 channels, 6.9 per SM -- an even single wave
+constexpr int BT = 32, TS = 16, CPT = 2;     // one warp per CTA: 1024 CTAs for 65536 channels, 6.9 per SM -- an even single wave
 constexpr int ROWS_W = 32 * CPT, ROWS_CTA = (BT / 32) * ROWS_W;       // 64 rows per warp, 128 per CTA
 constexpr int ROWB = TS * 8;                                          // bytes per staged row: dense, swizzled
 
-template <int NS>
+// NST: depth of the staging ring.  3 when the kernel has the SM to itself; 2 (20 KB per CTA instead of 28) leaves room for
+// one CTA of the decimated-rate tail kernel on every SM when a chain overlaps call k's tail with call k+1's front
+template <int NS, int NST>
 __global__ void __launch_bounds__(BT, 7) front2_kernel(const __grid_constant__ SeqArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -251,15 +253,21 @@ __global__ void __launch_bounds__(BT, 7) front2_kernel(const __grid_constant__ S
 }
 
 typedef void (*FrontFn)(const SeqArgs);
-FrontFn pick(int nsos)
+FrontFn pick(int nsos, int nst)
 {
+    if (nst == 2) {
+        switch (nsos) {
+        case 1: return front2_kernel<1, 2>; case 2: return front2_kernel<2, 2>; case 3: return front2_kernel<3, 2>; case 4: return front2_kernel<4, 2>;
+        default: return nullptr;
+        }
+    }
     switch (nsos) {
-    case 1: return front2_kernel<1>; case 2: return front2_kernel<2>; case 3: return front2_kernel<3>; case 4: return front2_kernel<4>;
+    case 1: return front2_kernel<1, 3>; case 2: return front2_kernel<2, 3>; case 3: return front2_kernel<3, 3>; case 4: return front2_kernel<4, 3>;
     default: return nullptr;
     }
 }
 
-size_t smem_bytes(const SeqArgs &a)
+size_t smem_bytes(const SeqArgs &a, int NST)
 {
     return 1024 + (size_t)NST * ROWS_CTA * ROWB + (size_t)(BT / 32) * NST * TS * sizeof(float2) + 32
          + (((size_t)a.rs.npfb * a.rs.sublen * sizeof(float) + 15) & ~(size_t)15);
@@ -267,14 +275,15 @@ size_t smem_bytes(const SeqArgs &a)
 
 }  // namespace
 
-bool front2_supported(unsigned mask, int nsos) { return mask == (F_IIR | F_RS) && pick(nsos) != nullptr; }
+bool front2_supported(unsigned mask, int nsos) { return mask == (F_IIR | F_RS) && pick(nsos, 3) != nullptr; }
 
-cudaError_t front2_launch(int nsos, const SeqArgs &a, cudaStream_t stream)
+cudaError_t front2_launch(int nsos, const SeqArgs &a, cudaStream_t stream, int ring_depth)
 {
-    FrontFn fn = pick(nsos);
+    const int nst = ring_depth == 2 ? 2 : 3;
+    FrontFn fn = pick(nsos, nst);
     if (!fn) return cudaErrorInvalidValue;
     if (a.C <= 0 || a.n <= 0) return cudaSuccess;
-    const size_t smem = smem_bytes(a);
+    const size_t smem = smem_bytes(a, nst);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     const unsigned grid = (unsigned)((a.C + ROWS_CTA - 1) / ROWS_CTA);

@@ -105,10 +105,33 @@ resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, vo
         // the mixer runs in front of the filter: rotate the staged samples of this call in place (history samples
         // in the ring were rotated by the call that saw them)
         const uint32_t th0 = q.theta[gch], dth = q.dtheta[gch];
-        for (int i = tid; i < span; i += NT) {
-            const long long g = i_lo + i;
-            // the 8 KB oscillator table is read through L1 (copying it into every CTA's shared memory cost a sixth of the staging)
-            if (g >= 0) { const float2 sc = nco_at(q, q.sincos, th0, dth, g); s_x[i] = q.dir == 2 ? mix_down(s_x[i], sc) : mix_up(s_x[i], sc); }
+        const bool down = q.dir == 2;
+        // the 8 KB oscillator table is read through L1 (copying it into every CTA's shared memory cost a sixth of the staging)
+        if (q.type == 0) {
+            // table oscillator: four samples per thread and pass, so four table reads and four shared loads are in
+            // flight together instead of one dependent pair per loop trip
+            const int i0 = i_lo < 0 ? (int)(-i_lo) : 0;                  // first sample of this call in the span
+            int i = i0 + tid;
+            for (; i + 3 * NT < span; i += 4 * NT) {
+                float2 sc[4], v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t th = th0 + (uint32_t)(i_lo + i + u * NT) * dth;
+                    sc[u] = __ldg(&q.sincos[nco_index(th)]); v[u] = s_x[i + u * NT];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) s_x[i + u * NT] = down ? mix_down(v[u], sc[u]) : mix_up(v[u], sc[u]);
+            }
+            for (; i < span; i += NT) {
+                const uint32_t th = th0 + (uint32_t)(i_lo + i) * dth;
+                const float2 sc = __ldg(&q.sincos[nco_index(th)]);
+                s_x[i] = down ? mix_down(s_x[i], sc) : mix_up(s_x[i], sc);
+            }
+        } else {
+            for (int i = tid; i < span; i += NT) {
+                const long long g = i_lo + i;
+                if (g >= 0) { const float2 sc = nco_at(q, q.sincos, th0, dth, g); s_x[i] = down ? mix_down(s_x[i], sc) : mix_up(s_x[i], sc); }
+            }
         }
         __syncthreads();
     }

@@ -99,6 +99,8 @@ _SIG = {
     "lqb_chain_execute_i16_dev": [_P, _P, _SZ, _P, _SZ, C.POINTER(_SZ), _P], "lqb_bytes_to_iq": [_P, _SZ, _P],
     "lqb_chain_set_timing": [_P, _I], "lqb_chain_get_timing": [_P, _P, _I, C.POINTER(_I), C.POINTER(_I)],
     "lqb_chain_plan": [_P, C.c_char_p, _SZ], "lqb_chain_last_launches": [_P, C.POINTER(_I)], "lqb_chain_set_fusion": [_P, _I],
+    "lqb_chain_set_overlap": [_P, _I], "lqb_chain_wait": [_P, _P],
+    "lqb_stream_create": [C.POINTER(_P), _I], "lqb_stream_destroy": [_P],
     "lqb_synth_fill": [_I, _P, _I, _I, _SZ, _U64, _U64, _P],
 }
 for _name, _args in _SIG.items():
@@ -735,6 +737,7 @@ class Chain(_Stage):
             for s in self.stages:
                 _ck(_lib.lqb_chain_append(self._h, s._h))
             _ck(_lib.lqb_chain_set_fusion(self._h, int(self._fuse)))
+            _ck(_lib.lqb_chain_set_overlap(self._h, int(getattr(self, "_overlap", False))))
             self._handles = [s._h for s in self.stages]
 
     def __del__(self):
@@ -756,6 +759,17 @@ class Chain(_Stage):
 
     def last_launches(self):
         n = _I(); _ck(_lib.lqb_chain_last_launches(self._h, C.byref(n))); return n.value
+
+    def set_overlap(self, enabled=True):
+        """Overlapped execute_dev calls: the decimated-rate tail of block k runs on the chain's own stream while the
+        caller's stream already runs block k+1's full-rate front (include/liquiddsp_b200.h, lqb_chain_set_overlap).
+        Call wait(stream) before consuming the output of such calls."""
+        self._overlap = bool(enabled)
+        _ck(_lib.lqb_chain_set_overlap(self._h, int(self._overlap)))
+
+    def wait(self, stream=0):
+        """Make `stream` wait for the tails of every overlapped execute_dev call issued so far."""
+        _ck(_lib.lqb_chain_wait(self._h, C.c_void_p(stream)))
 
     def set_timing(self, enabled=True):
         """Record a CUDA-event pair per plan segment on every execute_dev call (see segment_ms)."""
@@ -822,6 +836,19 @@ def synth_fill(kind, x_ptr, n_channels, n, channel0=0, n0=0, seed=0xB200, stream
     """Fill a device buffer [n_channels x n] complex64 with a benchmark signal:
     kind 0 AM IQ, 1 complex Gaussian, 2 tone + noise, 3 FM IQ with amplitude ramp."""
     _ck(_lib.lqb_synth_fill(kind, C.c_void_p(x_ptr), n_channels, channel0, n, n0, seed, C.c_void_p(stream)))
+
+
+def stream_create(high_priority=True):
+    """A CUDA stream (cudaStream_t as int); high priority puts its kernels ahead of a chain's overlapped tails."""
+    st = C.c_void_p(); _ck(_lib.lqb_stream_create(C.byref(st), int(bool(high_priority)))); return st.value or 0
+
+
+def stream_destroy(stream):
+    _ck(_lib.lqb_stream_destroy(C.c_void_p(stream)))
+
+
+def stream_synchronize(stream=0):
+    _ck(_lib.lqb_stream_synchronize(C.c_void_p(stream)))
 
 
 def device_count():

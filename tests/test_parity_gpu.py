@@ -898,3 +898,45 @@ def test_full_rate_stages_wide_batches_tma(cuda):
     for c in (0, 33, C - 1):
         o = O.NCO(); o.freq = float(np.float32(0.2 + 1e-5 * c))
         assert np.array_equal(y[c].view(np.uint32), o.mix_down(x[c]).view(np.uint32)), c
+
+
+@pytest.mark.parametrize("C,tail", [(33000, "am"), (200, "am"), (33000, "bam")])
+def test_overlapped_device_calls_equal_serial(cuda, C, tail):
+    """lqb_chain_set_overlap: block k's decimated-rate tail on the chain's own stream under block k+1's front -- same
+    words out as the serial calls, block after block with the state carried (two hand-off buffers in rotation)."""
+    n, nblk = 4096, 5
+    def radio():
+        r = _Radio(L, channels=C)
+        st = list(r.stages())
+        if tail == "bam":
+            st[3] = L.BroadcastAM(25, channels=C)
+        return L.Chain(*st)
+    serial, over = radio(), radio()
+    over.set_overlap(True)
+    xb = L.DeviceBuffer(C * n * 8)
+    cap = serial.out_len(n) + 2
+    ys, yo = L.DeviceBuffer(C * cap * 4), [L.DeviceBuffer(C * cap * 4) for _ in range(nblk)]
+    st = L.stream_create(True)
+    outs_s, lens = [], []
+    for blk in range(nblk):
+        L.synth_fill(0, xb.ptr.value, C, n, n0=blk * n)
+        L.synchronize()
+        got = serial.execute_dev(xb.ptr.value, n, ys.ptr.value, cap, 0)
+        L.synchronize()
+        outs_s.append(ys.download((C * cap,), np.float32)[:C * got].reshape(C, got)); lens.append(got)     # rows are dense: [C][n_out]
+        assert over.execute_dev(xb.ptr.value, n, yo[blk].ptr.value, cap, st) == got
+        L.stream_synchronize(st)            # the input buffer is refilled next; the TAIL of this block may still be running
+    over.wait(st)
+    L.stream_synchronize(st)
+    for blk in range(nblk):
+        y = yo[blk].download((C * cap,), np.float32)[:C * lens[blk]].reshape(C, lens[blk])
+        d = np.argwhere(y.view(np.uint32) != outs_s[blk].view(np.uint32))
+        assert len(d) == 0, (blk, len(d), d[:4].tolist(), int(d[:, 0].min()), int(d[:, 0].max()))
+    # a serial call on the overlapped chain joins the outstanding tails by itself
+    over.set_overlap(False)
+    L.synth_fill(0, xb.ptr.value, C, n, n0=nblk * n); L.synchronize()
+    g1 = serial.execute_dev(xb.ptr.value, n, ys.ptr.value, cap, 0); L.synchronize()
+    a = ys.download((C * cap,), np.float32)[:C * g1]
+    g2 = over.execute_dev(xb.ptr.value, n, yo[0].ptr.value, cap, 0); L.synchronize()
+    assert g1 == g2 and np.array_equal(a.view(np.uint32), yo[0].download((C * cap,), np.float32)[:C * g2].view(np.uint32))
+    L.stream_destroy(st)
