@@ -597,6 +597,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                     }
                 };
                 if (HAS_AGC && agc_fast) {
+                    // (blocks of 4 or 8 samples instead of the whole skewed tile measured 4-5 % slower: instruction fetch is not the limit)
                     if constexpr (HAS_AGC) cascade(std::true_type{});
                 } else {
                     cascade(std::false_type{});

@@ -1,0 +1,7 @@
+#!/bin/bash
+TAG=${1:-c4}
+mkdir -p gpurun_out
+PROF="python bench.py --config 4 --steps 2 --warmup 3 --no-cpu --no-e2e --block 8192"
+timeout 300 $PROF > gpurun_out/plain_$TAG.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'seq_kernel|pipe_kernel' -s 3 -c 1 -f -o gpurun_out/prof_$TAG $PROF > gpurun_out/ncu_full_$TAG.log 2>&1
+tail -3 gpurun_out/ncu_full_$TAG.log
