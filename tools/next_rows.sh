@@ -6,6 +6,9 @@ mkdir -p gpurun_out
 for row in bam ssb fmstereo rrrf cresamp rfir; do
   timeout 300 python bench.py --next $row --steps 5 --warmup 3 --no-cpu --no-e2e 2>&1 | tail -1 >> gpurun_out/next_$TAG.jsonl
 done
+for row in iir nco "agc" "agc --agc-precision fast" fm deemph resamp; do
+  timeout 300 python bench.py --next $row --steps 5 --warmup 3 --no-cpu --no-e2e 2>&1 | tail -1 >> gpurun_out/next_$TAG.jsonl
+done
 for c in 2 3 4; do
   timeout 300 python bench.py --config $c --steps 5 --warmup 3 --no-cpu --no-e2e 2>&1 | tail -1 >> gpurun_out/next_$TAG.jsonl
 done
