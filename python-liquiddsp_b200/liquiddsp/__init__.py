@@ -22,7 +22,7 @@ import os
 import numpy as np
 
 __all__ = ["bytes_to_iq", "ComplexIIRFilter", "DeemphasisFilter", "FIRFilter", "ComplexResampler", "NCO", "AGC",
-           "AmpModem", "FreqDem", "Chain", "synth_fill", "lib_path"]
+           "AmpModem", "FreqDem", "Chain", "PcmFramer", "synth_fill", "lib_path"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 lib_path = os.path.join(os.path.dirname(_HERE), "lib", "libliquiddsp_b200.so")
@@ -821,6 +821,50 @@ class Chain(_Stage):
         got = _SZ()
         _ck(_lib.lqb_chain_execute_dev(self._h, C.c_void_p(x_ptr), n, C.c_void_p(y_ptr), y_capacity, C.byref(got), C.c_void_p(stream)))
         return got.value
+
+
+class PcmFramer:
+    """The step behind the receiver in the README's Radio class (README.md:53-58): every call's audio is appended
+    to a byte buffer (`pcm.tobytes()`, float32) and leaves for the audio sink in 4096-byte chunks *while more than
+    4096 bytes are pending* -- the README's `while len(self.pcm) > 4096`, so exactly one chunk's worth stays behind
+    until more audio arrives (`strict=False` hands it over at once).  Host-side bookkeeping only.
+
+    One channel: push(audio) -> list of `bytes` chunks.  Batched (`channels=C`, audio [C x n]): the channels advance in
+    lockstep, push -> list of uint8 arrays [C x chunk_bytes] (row c is channel c's chunk)."""
+
+    def __init__(self, chunk_bytes=4096, channels=1, strict=True):
+        if chunk_bytes < 1 or channels < 1:
+            raise ValueError("chunk_bytes and channels must be positive")
+        self.chunk_bytes, self.channels, self.strict = int(chunk_bytes), int(channels), bool(strict)
+        self._buf = np.zeros((self.channels, 0), np.uint8)
+
+    @property
+    def pending(self):
+        """Bytes waiting per channel."""
+        return self._buf.shape[1]
+
+    def push(self, audio):
+        a = np.ascontiguousarray(audio)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        if a.ndim != 2 or a.shape[0] != self.channels:
+            raise ValueError("PcmFramer(channels=%d) got an array of shape %r" % (self.channels, np.shape(audio)))
+        raw = a.view(np.uint8).reshape(self.channels, -1)            # tobytes() of every row, side by side
+        self._buf = np.concatenate([self._buf, raw], axis=1)
+        out = []
+        k = self.chunk_bytes
+        while self._buf.shape[1] > k or (not self.strict and self._buf.shape[1] == k):
+            chunk = self._buf[:, :k]
+            out.append(chunk[0].tobytes() if self.channels == 1 else chunk.copy())
+            self._buf = self._buf[:, k:]
+        self._buf = np.ascontiguousarray(self._buf)
+        return out
+
+    def flush(self):
+        """Whatever is pending (possibly short), and an empty buffer afterwards."""
+        rest = self._buf
+        self._buf = np.zeros((self.channels, 0), np.uint8)
+        return rest[0].tobytes() if self.channels == 1 else rest
 
 
 def bytes_to_iq(b):

@@ -231,3 +231,34 @@ def test_no_compute_without_a_gpu():
         L.DeemphasisFilter()(np.zeros(8, np.float32))
     with pytest.raises(RuntimeError):
         L.NCO().freq = 0.1
+
+
+def test_pcm_framer_follows_the_readme_loop():
+    """README.md:53-58: self.pcm += pcm.tobytes(); while len(self.pcm) > 4096: emit self.pcm[:4096]."""
+    rng = np.random.default_rng(5)
+    fr = L.PcmFramer()
+    pcm, ref_chunks, got = b"", [], []
+    for n in (1000, 24, 1024, 3000, 0, 1, 1023, 2048):
+        audio = rng.standard_normal(n).astype(np.float32)
+        pcm += audio.tobytes()
+        while len(pcm) > 4096:
+            ref_chunks.append(pcm[:4096]); pcm = pcm[4096:]
+        got += fr.push(audio)
+        assert fr.pending == len(pcm)
+    assert got == ref_chunks and len(got) >= 7
+    assert fr.flush() == pcm and fr.pending == 0
+    # exactly one chunk pending stays behind under the README's strict '>' and leaves at once with strict=False
+    a = np.zeros(1024, np.float32)
+    assert L.PcmFramer().push(a) == [] and len(L.PcmFramer(strict=False).push(a)) == 1
+    # batched: channels advance in lockstep, row c of a chunk is channel c's bytes
+    C = 3
+    frb, frs = L.PcmFramer(channels=C), [L.PcmFramer() for _ in range(C)]
+    for n in (1500, 700, 2100):
+        blk = rng.standard_normal((C, n)).astype(np.float32)
+        chunks = frb.push(blk)
+        singles = [f.push(blk[c]) for c, f in enumerate(frs)]
+        assert all(len(s_) == len(chunks) for s_ in singles)
+        for k, ch in enumerate(chunks):
+            assert ch.shape == (C, 4096) and all(ch[c].tobytes() == singles[c][k] for c in range(C))
+    with pytest.raises(ValueError):
+        frb.push(np.zeros((2, 8), np.float32))
