@@ -138,7 +138,7 @@ def side_config(args, L, torch, dev, rank, world, barrier, max_over_ranks):
         chain = L.Chain(nco, L.ComplexResampler(0.024, Fc=0.024, channels=C))
         name, out_real = "config3: NCO mix-down + ComplexResampler 2e6->48e3, 4096 channels x 64K blocks", False
     elif args.config == 4:
-        C, n, kind, bps = 16384, 65536, 3, 12.0
+        C, n, kind, bps = int(os.environ.get("LQB_BENCH_C4_CHANNELS", "16384")), 65536, 3, 12.0      # (override: occupancy experiments)
         chain = L.Chain(L.ComplexIIRFilter("cheby2", order=8, Fc=0.0075, channels=C), L.AGC(channels=C), L.FreqDem(0.1, channels=C))
         name, out_real = "config4: ComplexIIRFilter cheby2-8 + AGC + FreqDem, 16384 channels x 64K blocks", True
     in_real = False

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
     };
     const AgcFast agck{a.agc.alpha, a.agc.chi, a.agc.clo, a.agc.cl2, a.agc.chalf, a.agc.scale};
     auto agc_step = [&](float2 z) -> float2 {
-        if (HAS_AGC && a.agc.fast) return agc_step_fast(z, agc_g, agc_y2p, agck);
+        if (HAS_AGC && a.agc.fast) return a.agc.big ? agc_step_fast<true>(z, agc_g, agc_y2p, agck) : agc_step_fast<false>(z, agc_g, agc_y2p, agck);
         // agc_crcf_execute (liquid agc.proto.c) then the wrapper's status poll, agc.hpp:115-125
         float yr = __fmul_rn(z.x, agc_g), yi = __fmul_rn(z.y, agc_g);
         const float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
 // threads of an SM can be resident and the chains of ~14 warps hide each other.
 // FAST: unlocked, squelch disabled -- the single-precision gain loop (devmath.cuh agc_step_fast).  Its chain is short
 // enough that the loads become the limit, so 16 samples per thread are in flight instead of 4.
-template <bool FAST, int U>
+template <bool FAST, int U, bool BIG>
 __global__ void __launch_bounds__(128) agc_tmajor_kernel(const __grid_constant__ AmTailArgs a)
 {
     __shared__ double2 s_log[FAST ? 1 : 128];
@@ -263,9 +263,9 @@ __global__ void __launch_bounds__(128) agc_tmajor_kernel(const __grid_constant__
 #pragma unroll
             for (int u = 0; u < U; u++) { z[u] = zn[u]; zn[u] = k0 + U + u < N ? x[(k0 + U + u) * P] : make_float2(0.f, 0.f); }
 #pragma unroll
-            for (int u = 0; u < U; u++) x[(k0 + u) * P] = agc_step_fast(z[u], agc_g, agc_y2p, k);
+            for (int u = 0; u < U; u++) x[(k0 + u) * P] = agc_step_fast<BIG>(z[u], agc_g, agc_y2p, k);
         }
-        for (int u = 0; k0 + u < N; u++) x[(k0 + u) * P] = agc_step_fast(x[(k0 + u) * P], agc_g, agc_y2p, k);
+        for (int u = 0; k0 + u < N; u++) x[(k0 + u) * P] = agc_step_fast<BIG>(x[(k0 + u) * P], agc_g, agc_y2p, k);
         a.agc.g[gch] = agc_g; a.agc.y2p[gch] = agc_y2p;
     } else {
     float2 zn[U];
@@ -320,8 +320,10 @@ typedef void (*AmFn)(const AmTailArgs);
 cudaError_t agc_tmajor_launch(const AmTailArgs &a, cudaStream_t stream)
 {
     if (a.C <= 0 || a.n <= 0) return cudaSuccess;
-    if (a.agc.fast) agc_tmajor_kernel<true, 16><<<(unsigned)((a.C + 127) / 128), 128, 0, stream>>>(a);
-    else            agc_tmajor_kernel<false, 4><<<(unsigned)((a.C + 127) / 128), 128, 0, stream>>>(a);
+    const unsigned grid = (unsigned)((a.C + 127) / 128);
+    if (a.agc.fast && a.agc.big) agc_tmajor_kernel<true, 16, true><<<grid, 128, 0, stream>>>(a);
+    else if (a.agc.fast)         agc_tmajor_kernel<true, 16, false><<<grid, 128, 0, stream>>>(a);
+    else                         agc_tmajor_kernel<false, 4, false><<<grid, 128, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

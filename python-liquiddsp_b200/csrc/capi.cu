@@ -26,6 +26,7 @@
 #include "bam.h"
 #include "fmst.h"
 #include "front.h"
+#include "pipe.h"
 #include "par.h"
 #include "scan.h"
 #include "synth.h"
@@ -402,6 +403,7 @@ struct AgcStage : lqb_stage_s {
         p.alpha = alpha; p.scale = scale; p.threshold = threshold; p.one_minus_alpha = 1.0 - (double)alpha;
         p.chi = (float)p.one_minus_alpha; p.clo = (float)(p.one_minus_alpha - (double)p.chi);
         p.chalf = -0.5f * alpha; p.cl2 = (float)((double)p.chalf * 0.6931471805599453094);
+        p.big = alpha > 0.0112f ? 1 : 0;
         p.fast = (!locked && !squelch && (precision == LQB_AGC_FAST || (precision == LQB_AGC_AUTO && plan_fast))) ? 1 : 0;
         p.locked = locked; p.timeout = timeout; p.g = g.p; p.y2p = y2p.p; p.mode = mode.p; p.timer = timer.p;
         p.rise_count = rise.p;
@@ -870,6 +872,13 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         case K_TF:     static_cast<TfStage *>(s)->fill(a.tf); break;
         default: return fail(LQB_EINVAL, "stage kind %d cannot run in the sequential kernel", (int)s->kind);
         }
+    }
+    // cascade -> single-precision gain loop -> discriminator (config 4): one warp per stage, TMA input ring (pipe.cu)
+    if (extra_mask == 0 && !in_real && a.agc.fast && pipe_supported(g.mask, g.nsos) && !getenv("LQB_NO_PIPE") &&
+        make_input_tmap(&a.tmap, x, n, (size_t)nch)) {
+        a.use_tma = 1;
+        LQB_CUDA(pipe_launch(g.nsos, a, stream));
+        return LQB_OK;
     }
     // the headline front (cascade + decimating resampler) with many channels: two channels per thread (front.cu)
     {

@@ -235,6 +235,10 @@ __device__ __forceinline__ float log_rn(float x, const double2 *__restrict__ tab
 struct AgcFast {
     float alpha, chi, clo, cl2, c, scale;      // cl2 = -alpha/2 ln 2, c = -alpha/2
 };
+// BIG = false: the caller guarantees |a| <= 1/2 for every finite y2' (alpha <= 0.0112, liquid's default bandwidth is
+// 0.01: |a| <= alpha/2 * 88.8).  The degree-8 series then covers every argument and the MUFU.EX2 of the general case --
+// which ptxas merges with the series result through a predicated write, putting its latency ON the chain -- disappears.
+template <bool BIG>
 __device__ __forceinline__ float2 agc_step_fast(float2 z, float &g, float &y2p, const AgcFast &k)
 {
     // off the chain (y2' is a sample old): chi y2' as head + tail, clo y2' folded into the tail
@@ -244,14 +248,27 @@ __device__ __forceinline__ float2 agc_step_fast(float2 z, float &g, float &y2p, 
     y2p = __fadd_rn(h, __fmaf_rn(k.alpha, y2, l));
     float l2; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(y2p));
     const float a = __fmul_rn(k.cl2, l2);
-    float eb; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(__fmul_rn(k.c, l2)));
     const float a2 = __fmul_rn(a, a);
-    const float q0 = __fmaf_rn(a, 1.0f / 6.0f, 0.5f), q1 = __fmaf_rn(a, 1.0f / 120.0f, 1.0f / 24.0f), q2 = __fmaf_rn(a, 1.0f / 5040.0f, 1.0f / 720.0f);
-    const float q = __fmaf_rn(__fmaf_rn(q2, a2, q1), a2, q0);
-    const float ep = __fadd_rn(1.0f, __fmaf_rn(a2, q, a));
     const bool upd = y2p > 1e-6f;
-    const float ebs = upd ? eb : 1.0f;
-    const float e = (upd && fabsf(a) <= 0.25f) ? ep : ebs;
+    float e;
+    if constexpr (BIG) {
+        float eb; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(__fmul_rn(k.c, l2)));
+        const float q0 = __fmaf_rn(a, 1.0f / 6.0f, 0.5f), q1 = __fmaf_rn(a, 1.0f / 120.0f, 1.0f / 24.0f), q2 = __fmaf_rn(a, 1.0f / 5040.0f, 1.0f / 720.0f);
+        const float q = __fmaf_rn(__fmaf_rn(q2, a2, q1), a2, q0);
+        const float ep = __fadd_rn(1.0f, __fmaf_rn(a2, q, a));
+        const float ebs = upd ? eb : 1.0f;
+        e = (upd && fabsf(a) <= 0.25f) ? ep : ebs;
+    } else {
+        // exp(a) - 1 = a + a^2 (1/2 + a/6 + a^2 (1/24 + a/120 + a^2 (1/720 + a/5040 + a^2/40320))): |a| <= 1/2 leaves 3e-10
+        const float q0 = __fmaf_rn(a, 1.0f / 6.0f, 0.5f), q1 = __fmaf_rn(a, 1.0f / 120.0f, 1.0f / 24.0f);
+        const float q2 = __fmaf_rn(a2, 1.0f / 40320.0f, __fmaf_rn(a, 1.0f / 5040.0f, 1.0f / 720.0f));
+        const float q = __fmaf_rn(__fmaf_rn(q2, a2, q1), a2, q0);
+        const float t = __fmaf_rn(a2, q, a);
+        e = __fadd_rn(1.0f, upd ? t : 0.0f);              // y2' <= 1e-6 (or NaN): the gain keeps its value
+        // y2' = +inf (overflowed input): liquid's expf(-inf) = 0 zeroes the gain; here t is NaN and fminf(NaN, 0) = 0
+        g = fminf(__fmul_rn(g, e), y2p > 3.0e38f ? 0.0f : 1e6f);
+        return make_float2(__fmul_rn(yr, k.scale), __fmul_rn(yi, k.scale));
+    }
     g = fminf(__fmul_rn(g, e), 1e6f);
     return make_float2(__fmul_rn(yr, k.scale), __fmul_rn(yi, k.scale));
 }

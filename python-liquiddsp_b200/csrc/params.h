@@ -51,6 +51,7 @@ struct AgcP {
     double one_minus_alpha;
     float chi, clo, cl2, chalf;    // single-precision gain loop (devmath.cuh agc_step_fast): chi + clo = 1 - alpha, cl2 = -alpha/2 ln 2, chalf = -alpha/2
     int fast;                      // unlocked and squelch disabled on every channel: the single-precision loop applies
+    int big;                       // alpha > 0.0112: |alpha/2 ln y2'| can exceed 1/2, the single-precision loop keeps its ex2 branch
     int locked;
     unsigned timeout;
     float *g, *y2p;                // [Ctot]

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
     const bool agc_fast = HAS_AGC && a.agc.fast != 0;             // unlocked, no squelch: the single-precision gain loop
     auto agc_apply = [&](float2 z) -> float2 {
         if constexpr (HAS_AGC) {
-            if (agc_fast) return agc_step_fast(z, agc_g, agc_y2p, agck);
+            if (agc_fast) return a.agc.big ? agc_step_fast<true>(z, agc_g, agc_y2p, agck) : agc_step_fast<false>(z, agc_g, agc_y2p, agck);
             // agc_crcf_execute (liquid agc.proto.c) then the wrapper's status poll, agc.hpp:115-125
             float yr = __fmul_rn(z.x, agc_g), yi = __fmul_rn(z.y, agc_g);
             float y2 = __fmaf_rn(yr, yr, __fmul_rn(yi, yi));
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
 
     auto tail = [&](float2 z, int jtile) { post(agc_apply(z), jtile); };
     // the same with the gain loop known to be the short one: no branch, so an unrolled tile is one basic block
-    auto tail_fast = [&](float2 z, int jtile) { post(agc_step_fast(z, agc_g, agc_y2p, agck), jtile); };
+    auto tail_fast = [&](float2 z, int jtile, auto big) { post(agc_step_fast<decltype(big)::value>(z, agc_g, agc_y2p, agck), jtile); };
 
     // ---- one full-rate sample: oscillator and IIR; returns the (complex) value handed on ----
     auto head = [&](float2 xin) -> u64 {
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 // with 16384 channels a scheduler holds a single warp, so nothing but this warp's own independent work
                 // can fill the chain's latency: in one basic block the cascade of the samples ahead and the
                 // discriminator of the samples behind are exactly that work
-                auto cascade = [&](auto fused) {
+                auto cascade = [&](auto fused, auto big) {
                     u64 xs[TS], yy[NS];
                     ld_row(row, xs);
 #pragma unroll
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                                 y = fma2(cb2[sct], iv2[sct], y);
                                 iv2[sct] = iv1[sct]; iv1[sct] = v0; yy[sct] = y;
                                 if (sct == NS - 1) {
-                                    if constexpr (decltype(fused)::value) tail_fast(upk(y), j);
+                                    if constexpr (decltype(fused)::value) tail_fast(upk(y), j, big);
                                     else if constexpr (HAS_AGC || HAS_FM) *(float2 *)(const_cast<unsigned char *>(row) + soff(j)) = upk(y);
                                     else tail(upk(y), j);
                                 }
@@ -598,9 +598,9 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                 };
                 if (HAS_AGC && agc_fast) {
                     // (blocks of 4 or 8 samples instead of the whole skewed tile measured 4-5 % slower: instruction fetch is not the limit)
-                    if constexpr (HAS_AGC) cascade(std::true_type{});
+                    if constexpr (HAS_AGC) { if (a.agc.big) cascade(std::true_type{}, std::true_type{}); else cascade(std::true_type{}, std::false_type{}); }
                 } else {
-                    cascade(std::false_type{});
+                    cascade(std::false_type{}, std::false_type{});
                     // then one pass per remaining stage: the general gain loop (locked / squelch: double-precision
                     // functions, state machine) is a long serial chain per sample and runs rolled;
                     // the discriminator has no feedback, so its 16 samples are independent work for the scheduler
@@ -619,8 +619,13 @@ __global__ void __launch_bounds__(BT, (M & F_AM) ? 2 : 8) seq_kernel(const __gri
                     if constexpr (HAS_AGC) {
                         u64 xs[TS];
                         ld_row(row, xs);
+                        if (a.agc.big) {
 #pragma unroll
-                        for (int j = 0; j < TS; j++) tail_fast(upk(head(upk(xs[j]))), j);
+                            for (int j = 0; j < TS; j++) tail_fast(upk(head(upk(xs[j]))), j, std::true_type{});
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < TS; j++) tail_fast(upk(head(upk(xs[j]))), j, std::false_type{});
+                        }
                     }
                 } else {
 #pragma unroll 2
