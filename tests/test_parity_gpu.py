@@ -940,3 +940,28 @@ def test_overlapped_device_calls_equal_serial(cuda, C, tail):
     g2 = over.execute_dev(xb.ptr.value, n, yo[0].ptr.value, cap, 0); L.synchronize()
     assert g1 == g2 and np.array_equal(a.view(np.uint32), yo[0].download((C * cap,), np.float32)[:C * g2].view(np.uint32))
     L.stream_destroy(st)
+
+
+@pytest.mark.parametrize("C,n,order", [(1, 37, 2), (33, 4101, 4), (70, 8000, 6), (200, 16, 8), (129, 2048, 8)])
+def test_pipeline_kernel_equals_one_warp_kernel(cuda, C, n, order, monkeypatch):
+    """Config 4's chain takes the three-warp pipeline (pipe.cu); the one-warp seq_kernel (LQB_NO_PIPE) evaluates the same
+    operations -- bit-identical outputs and carried state over split calls, ragged lengths (no tensor map: odd n),
+    partial tiles and channel counts that do not fill a warp; both within tolerance of the oracle."""
+    rng = np.random.default_rng(77)
+    x = np.stack([fm_iq(n, seed=300 + c) * np.float32(0.05 + 0.9 * c / max(C - 1, 1)) for c in range(C)]).astype(np.complex64)
+    def make():
+        iir = L.ComplexIIRFilter("cheby2", order=order, Fc=0.05, channels=C)
+        return L.Chain(iir, L.AGC(channels=C), L.FreqDem(0.1, channels=C)), iir
+    cuts = split_points(n, 3, rng)
+    monkeypatch.delenv("LQB_NO_PIPE", raising=False)
+    pipe, iir = make()
+    yp = np.concatenate([pipe(x[:, s:e] if C > 1 else x[0, s:e]).reshape(C, -1) for s, e in cuts], axis=1)
+    monkeypatch.setenv("LQB_NO_PIPE", "1")
+    seq, _ = make()
+    ys = np.concatenate([seq(x[:, s:e] if C > 1 else x[0, s:e]).reshape(C, -1) for s, e in cuts], axis=1)
+    monkeypatch.delenv("LQB_NO_PIPE", raising=False)
+    assert yp.shape == (C, n) and np.array_equal(yp.view(np.uint32), ys.view(np.uint32))
+    assert np.array_equal(pipe.stages[1].gains().view(np.uint32), seq.stages[1].gains().view(np.uint32))
+    for c in sorted({0, C // 2, C - 1}):
+        yo = O.FreqDem(0.1)(O.AGC()(O.ComplexIIRFilter(_sos=iir.sos())(x[c])))
+        assert np.linalg.norm(yp[c] - yo) / np.sqrt(n) <= 5 * TOL_E2E, c
