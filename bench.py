@@ -79,11 +79,25 @@ def cpu_kind():
 
 # ------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: an NVML poll every 5 ms on a thread (the timed region of the
+    default run is ~100 ms, shorter than nvidia-smi's start-up); nvidia-smi -lms as the fallback when NVML is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.p = [], None
+        self.rows, self.p, self.nv, self.run = [], None, None, True
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True); self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -91,14 +105,35 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def _poll(self):
+        nv = self.nv
+        bits = (("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        while self.run:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.perf_counter(), [str(sm), str(self.mx), ""] + ["Active" if mask & b else "Not Active" for _, b in bits]))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.p.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self, t0, t1):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15); self.p.terminate()
+        if self.p is None and self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"]}
+        if self.nv is not None:
+            self.run = False; self.t.join(timeout=1.0)
+        else:
+            time.sleep(0.15); self.p.terminate()
         rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
         sm, mx, reasons = [], None, set()
         for r in rows:
@@ -110,7 +145,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------- GPU arm

@@ -992,8 +992,7 @@ static int chain_join_tails(lqb_chain_s *c, cudaStream_t stream)
     return LQB_OK;
 }
 
-static int run_overlapped(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, void *y, size_t n, int C, size_t tmpb,
-                          cudaStream_t stream, bool in_i16)
+static int run_overlapped(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, void *y, size_t n, int C, size_t tmpb, cudaStream_t stream)
 {
     if (!c->tail_stream) {
         int lo = 0, hi = 0;
@@ -1026,7 +1025,6 @@ static int run_overlapped(lqb_chain_s *c, const std::vector<Segment> &segs, cons
     LQB_CUDA(cudaEventRecord(c->ev_tail[b], c->tail_stream));
     c->tail_pending[b] = true;
     if (!evs.empty()) c->timed_calls.push_back(std::move(evs));
-    (void)in_i16;
     return LQB_OK;
 }
 
@@ -1047,7 +1045,7 @@ static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, s
     if (segs.size() > 2) LQB_TRY(c->d_tmp[1].reserve(tmpb));
     if (in_i16 && !first_takes_i16(segs)) LQB_TRY(c->d_cvt.reserve((size_t)C * n * 8));
     if (overlappable(c, segs, in_i16)) {
-        LQB_TRY(run_overlapped(c, segs, x, y, n, C, tmpb, stream, in_i16));
+        LQB_TRY(run_overlapped(c, segs, x, y, n, C, tmpb, stream));
     } else {
         LQB_TRY(chain_join_tails(c, stream));                    // tails of earlier overlapped calls come first
         LQB_TRY(run_all(c, segs, x, y, n, 0, C, c->d_tmp[0].p, c->d_tmp[1].p, stream, &c->last_launches, c->timing, in_i16, c->d_cvt.p));
