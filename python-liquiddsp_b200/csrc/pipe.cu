@@ -2,10 +2,11 @@
 //
 // Same arithmetic, operand for operand, as seq_kernel<F_IIR | F_AGC | F_FM> with the single-precision gain loop
 // (reference loops iirfilter.hpp:296, agc.hpp:113-127, demod.hpp:216).  What changes is who does what, and why:
-//   * one warp issues an FP32 instruction every other cycle at best (a packed FFMA2 every fourth): measured, a lone warp
-//     running the whole chain takes 193 cycles per sample however few channels there are -- 93 instructions, 20 of them
-//     packed.  Config 4 has 16384 channels = 512 such warps for 592 schedulers, so the one-warp-per-32-channels kernel
-//     runs at that single-warp pace with every scheduler half idle;
+//   * measured, a lone warp running the whole chain takes 193 cycles per sample however few channels there are -- 93
+//     instructions, 20 of them packed, strung on the gain loop's 84-cycle chain; an in-order warp stalls at the first
+//     operand that is not ready, and no static interleave of the three stages keeps it issuing (a lone warp CAN issue
+//     one FFMA per cycle given four independent chains: tools/ubench_issue.cu).  Config 4 has 16384 channels = 512
+//     such warps for 592 schedulers, so the one-warp-per-32-channels kernel runs at that single-warp pace;
 //   * with 16384 channels a row must deliver four times the bandwidth it does in the 65536-channel configs and the rows
 //     are 512 KB apart: what counts is how many bytes per row are on their way.
 // So a 32-channel group is worked by three warps of one CTA, each with about a third of the instructions,
