@@ -797,6 +797,20 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         a.in_real = f->in_r ? 1 : 0; a.out_real = f->out_r ? 1 : 0; a.mode = f->mode; a.delay = f->delay; a.count = f->count;
         a.taps_q = f->hlane_q.empty() ? nullptr : f->taps_q.p;
         a.post_div = f->post_div;
+        {
+            // every other tap zero in both lanes (Hilbert pairs: quadrature taps on one parity, the in-phase delay the lone
+            // tap on the other): the kernel skips that parity's multiply-adds
+            int nz[2] = { 0, 0 }, last[2] = { -1, -1 };
+            for (size_t k = 0; k < f->h.size(); k++) {
+                const bool z = f->h[k] == 0.f && (f->hlane_q.empty() || f->hlane_q[k] == 0.f);
+                if (!z) { nz[k & 1]++; last[k & 1] = (int)k; }
+            }
+            a.skip = 0; a.skip_keep = -1;
+            if (f->h.size() >= 8 && !getenv("LQB_FIR_NOSKIP")) {
+                if (nz[0] <= 1 && nz[1] > 1) { a.skip = 1; a.skip_keep = last[0]; }
+                else if (nz[1] <= 1 && nz[0] > 1) { a.skip = 2; a.skip_keep = last[1]; }
+            }
+        }
         for (int k = 0; k < 4; k++) a.zero_at[k] = -1;
         if (f->mode == FIR_R2C) {
             int nz = 0;

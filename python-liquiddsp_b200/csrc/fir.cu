@@ -39,8 +39,11 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 // IN_REAL / OUT_REAL: float rows instead of complex64.  firfilt_rrrf is real in, real out: the samples ride in the
 // real lane of the same arithmetic.  The firhilbf users (SSBDemod, HilbertTransform) run the two lanes with different
 // taps -- a pure delay in one, the quadrature filter in the other -- and combine them when the tile is written.
-template <bool IN_REAL, bool OUT_REAL>
-__global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntiles, const int ntaps_pad, const int tpc, const int groups)
+// SKIP: 1 / 2 = the taps at even / odd positions are zero in both lanes except (at most) position a.skip_keep -- the
+// Hilbert-pair filters (firhilbf: quadrature taps on every other position, the in-phase lane a pure delay); those
+// positions' multiply-adds are not issued
+template <bool IN_REAL, bool OUT_REAL, int SKIP>
+__global__ void __launch_bounds__(NT, 4) fir_kernel(const FirArgs a, const int ntiles, const int ntaps_pad, const int tpc, const int groups)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int halo = ntaps_pad - 1;
@@ -135,15 +138,19 @@ __global__ void __launch_bounds__(NT) fir_kernel(const FirArgs a, const int ntil
             for (int kk = 0; kk < R; kk += 2) {
                 const float4 t2 = *(const float4 *)&s_h[kb + kk];       // two taps per load
                 const u64 tap0 = pk(t2.x, t2.y), tap1 = pk(t2.z, t2.w);
+                if (SKIP != 1 || kb + kk == a.skip_keep) {
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const int q = r - kk + (R - 1);
-                    acc[r] = fma2(tap0, q < R ? lo[q] : hi[q - R], acc[r]);
+                    for (int r = 0; r < R; r++) {
+                        const int q = r - kk + (R - 1);
+                        acc[r] = fma2(tap0, q < R ? lo[q] : hi[q - R], acc[r]);
+                    }
                 }
+                if (SKIP != 2 || kb + kk + 1 == a.skip_keep) {
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const int q = r - kk - 1 + (R - 1);
-                    acc[r] = fma2(tap1, q < R ? lo[q] : hi[q - R], acc[r]);
+                    for (int r = 0; r < R; r++) {
+                        const int q = r - kk - 1 + (R - 1);
+                        acc[r] = fma2(tap1, q < R ? lo[q] : hi[q - R], acc[r]);
+                    }
                 }
             }
         };
@@ -235,8 +242,10 @@ cudaError_t fir_launch(const FirArgs &a, cudaStream_t stream)
     if (smem > 200 * 1024 || groups * rows > 0x7fffffffLL) return cudaErrorInvalidValue;
     if (a.pair && (!a.real_io || a.mode != FIR_PLAIN || (a.ch0 & 1))) return cudaErrorInvalidValue;
     const bool in_real = a.real_io || a.in_real, out_real = a.real_io || a.out_real;
-    auto fn = in_real ? (out_real ? fir_kernel<true, true> : fir_kernel<true, false>)
-                      : (out_real ? fir_kernel<false, true> : fir_kernel<false, false>);
+    const int skip = in_real ? 0 : a.skip;                             // compiled for complex input (the Hilbert-pair users)
+    auto fn = in_real ? (out_real ? fir_kernel<true, true, 0> : fir_kernel<true, false, 0>)
+            : out_real ? (skip == 1 ? fir_kernel<false, true, 1> : skip == 2 ? fir_kernel<false, true, 2> : fir_kernel<false, true, 0>)
+                       : (skip == 1 ? fir_kernel<false, false, 1> : skip == 2 ? fir_kernel<false, false, 2> : fir_kernel<false, false, 0>);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     fn<<<(unsigned)(groups * rows), NT, smem, stream>>>(a, (int)ntiles, ntaps_pad, (int)tpc, (int)groups);

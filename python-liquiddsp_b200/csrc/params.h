@@ -167,6 +167,7 @@ struct FirArgs {
     long long zero_at[4];          // FIR_R2C: local output indices whose in-phase part is forced to zero (-1 = none)
     const float *taps_q;           // taps of the imaginary lane (nullptr: same as taps)
     float post_div;                // SSB modes inside ampmodem: y = (0.5 * side-band) / post_div; 0 = off
+    int skip, skip_keep;           // 1 / 2: taps at even / odd positions are zero in both lanes, except position skip_keep (-1: none)
     long long n;
     float scale;
     const float *taps;             // device [ntaps] in design order h[0..ntaps-1]
