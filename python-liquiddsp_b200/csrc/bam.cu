@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(BT) bam_kernel(const __grid_constant__ BamArgs
     float2 *s_w   = (float2 *)smem;                       // [W][BT]
     float2 *s_h   = s_w + (size_t)W * BT;                 // [NTP] taps, duplicated for both lanes
     float  *s_sin = (float *)(s_h + NTP);                 // [1024]
-    double *s_at  = (double *)(s_sin + 1024);             // [65][8] atan2_rn table
+    double *s_at  = (double *)(s_sin + 1024);             // [65][kAtanPitch] atan2_rn table
 
     const int tid = threadIdx.x;
     const long long chl = (long long)blockIdx.x * BT + tid;
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(BT) bam_kernel(const __grid_constant__ BamArgs
     const long long gch = a.ch0 + cl, CT = a.Ctot, N = a.n;
 
     for (int i = tid; i < 1024; i += BT) s_sin[i] = a.p.sincos[i].x;
-    for (int i = tid; i < 65 * 8; i += BT) s_at[i] = a.p.atantab[i];
+    for (int i = tid; i < 65 * 8; i += BT) s_at[(i >> 3) * kAtanPitch + (i & 7)] = a.p.atantab[i];
     for (int i = tid; i < NTP; i += BT) { const float h = a.p.hrev[i]; s_h[i] = make_float2(h, h); }
     float2 *lp = s_w + tid;
     for (int i = 0; i < H; i++) lp[i * BT] = a.p.hist[i * CT + gch];
@@ -147,7 +147,7 @@ cudaError_t bam_launch(const BamArgs &a, cudaStream_t stream)
     if (a.C <= 0 || a.n <= 0) return cudaSuccess;
     const int NTP = a.p.ntaps_pad, W = NTP - 1 + NG * G;
     if (NTP % G || a.p.m < 1 || a.p.m > kBamMaxM || a.p.m > NTP - 1) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)W * BT * sizeof(float2) + (size_t)NTP * sizeof(float2) + 1024 * sizeof(float) + 65 * 8 * sizeof(double);
+    const size_t smem = (size_t)W * BT * sizeof(float2) + (size_t)NTP * sizeof(float2) + 1024 * sizeof(float) + 65 * kAtanPitch * sizeof(double);
     cudaError_t rc = cudaFuncSetAttribute((const void *)bam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     bam_kernel<<<(unsigned)((a.C + BT - 1) / BT), BT, smem, stream>>>(a);

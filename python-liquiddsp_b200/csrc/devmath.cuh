@@ -141,6 +141,9 @@ __device__ __forceinline__ float atan2_fast(float y, float x)
 // (probability ~1e-8).  The quotient of the smaller by the larger magnitude lands in [0, 1]; the nearest of 65
 // nodes c_i = i/64 supplies atan(c_i) and a degree-7 Taylor expansion around it (table in shared memory, 4160 B).
 // Inline, so independent evaluations overlap; the library routine is a call.
+// (the shared-memory copy of the table keeps its 65 nodes kAtanPitch = 9 doubles apart: with 8 -- 64 bytes -- every node
+// starts on bank 0 or 16 and the 32 lanes' loads of one coefficient collide 16 ways; 9 spreads the nodes over 16 bank pairs)
+constexpr int kAtanPitch = 9;
 __device__ __forceinline__ float atan2_rn(float y, float x, const double *__restrict__ tab)
 {
     const float ax = fabsf(x), ay = fabsf(y);
@@ -150,7 +153,7 @@ __device__ __forceinline__ float atan2_rn(float y, float x, const double *__rest
     q = mx == 0.0 ? 0.0 : q;
     const int i = __double2int_rn(q * 64.0);
     const double d = fma((double)i, -0.015625, q);
-    const double *t = tab + 8 * i;
+    const double *t = tab + kAtanPitch * i;
     double p = t[7];
     p = fma(p, d, t[6]); p = fma(p, d, t[5]); p = fma(p, d, t[4]); p = fma(p, d, t[3]);
     p = fma(p, d, t[2]); p = fma(p, d, t[1]); p = fma(p, d, t[0]);

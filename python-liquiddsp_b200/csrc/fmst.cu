@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
     float *s_R   = s_L + L * BT;
     float *s_b   = s_R + L * BT;                                  // bank [npfb][L]
     float *s_sin = s_b + ((a.p.rs.npfb * L + 3) & ~3);            // [1024]
-    double *s_at = (double *)(s_sin + 1024);                      // [65][8] atan2_rn table
+    double *s_at = (double *)(s_sin + 1024);                      // [65][kAtanPitch] atan2_rn table
 
     // cpw channels per warp: the loop is one long FP64 dependency chain per sample, so with few channels they are
     // spread over more warps (8 or 16 working lanes each) and the schedulers get independent chains to interleave
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
     const long long gch = a.ch0 + (active ? chl : 0), CT = a.Ctot, N = a.n;
 
     for (int i = tid; i < 1024; i += BT) s_sin[i] = a.p.sincos[i].x;
-    for (int i = tid; i < 65 * 8; i += BT) s_at[i] = a.p.atantab[i];
+    for (int i = tid; i < 65 * 8; i += BT) s_at[(i >> 3) * kAtanPitch + (i & 7)] = a.p.atantab[i];
     for (int i = tid; i < a.p.rs.npfb * L; i += BT) s_b[i] = a.p.rs.bank[i];
     if (worker) for (int i = 0; i < L; i++) { s_L[i * BT + myrow] = a.p.ringL[i * CT + gch]; s_R[i * BT + myrow] = a.p.ringR[i * CT + gch]; }
     float2 prev = a.p.rprime[gch];
@@ -148,7 +148,7 @@ cudaError_t fmstereo_launch(const FmstArgs &a, cudaStream_t stream)
     const int L = a.p.rs.sublen;
     if (L < 1 || L > kFmstMaxSub || a.p.rs.step < (1u << 24)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)2 * BT * PITCH + (size_t)2 * L * BT * sizeof(float) + (size_t)((a.p.rs.npfb * L + 3) & ~3) * sizeof(float)
-                      + 1024 * sizeof(float) + 65 * 8 * sizeof(double);
+                      + 1024 * sizeof(float) + 65 * kAtanPitch * sizeof(double);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fmstereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     if (a.cpw != 8 && a.cpw != 16 && a.cpw != 32) return cudaErrorInvalidValue;
