@@ -93,7 +93,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ uint32_t nco_constrain_dev(float theta)
 {
     float p = (float)((double)theta * 0.159154943091895);
-    float fpart = __fsub_rn(p, (float)((long long)p));
+    float fpart = __fsub_rn(p, truncf(p));               // == p - (float)(long long)p for |p| < 2^63, one conversion instead of two
     if (fpart < 0.f) fpart = __fadd_rn(fpart, 1.0f);
     float scaled = __fmul_rn(fpart, 4294967296.0f);
     return (uint32_t)(unsigned long long)(long long)scaled;
