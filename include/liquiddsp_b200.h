@@ -255,6 +255,12 @@ int lqb_bytes_to_iq(const int16_t *iq, size_t n, lqb_cf *out);
  * launches the last execute issued */
 int lqb_chain_plan(lqb_chain c, char *buf, size_t buf_len);
 int lqb_chain_last_launches(lqb_chain c, int *n_launches);
+/* names of the kernels the last execute launched, in launch order, separated by ';' (what the planner dispatched:
+ * bench.py reports its roofline kernel from this) */
+int lqb_chain_last_kernels(lqb_chain c, char *buf, size_t buf_len);
+/* A call that fails after its first kernel launch leaves device state ahead of the host-side bookkeeping; the chain then
+ * refuses further calls (LQB_EINVAL) until the stages have been reset and this has been called. */
+int lqb_chain_clear_error(lqb_chain c);
 /* Per-segment device timing of lqb_chain_execute_dev: while enabled, every call records one CUDA-event pair per
  * launch-plan segment on the caller's stream (up to 1024 calls).  get_timing waits for the recorded events and
  * returns, per segment, the elapsed milliseconds summed over the recorded calls. */

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,7 @@
 #include "bam.h"
 #include "fmst.h"
 #include "front.h"
+#include "lanes.h"
 #include "pipe.h"
 #include "par.h"
 #include "scan.h"
@@ -55,25 +57,30 @@ template <class T> struct DevArr {
     DevArr(const DevArr &) = delete; DevArr &operator=(const DevArr &) = delete;
     ~DevArr() { release(); }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-    int alloc(size_t count)
+    // State arrays are zeroed; scratch (reserve) is not.  cudaMemset / cudaMemcpy run on the legacy default stream,
+    // which orders nothing against the non-blocking streams callers execute on (lqb_stream_create, torch side streams),
+    // and both may return before the device has finished: settle() waits, so that whatever stream runs next sees the
+    // initialised state.  State is set up once per object, so the wait is off every hot path.
+    static int settle() { LQB_CUDA(cudaStreamSynchronize(cudaStreamLegacy)); return LQB_OK; }
+    int alloc(size_t count, bool zeroed = true)
     {
         release();
         if (count == 0) return LQB_OK;
         cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
         if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? LQB_ENOMEM : LQB_ECUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
         n = count;
-        return zero();
+        return zeroed ? zero() : LQB_OK;
     }
-    int reserve(size_t count) { return count <= n ? LQB_OK : alloc(count); }
-    int zero() { if (p) LQB_CUDA(cudaMemset(p, 0, n * sizeof(T))); return LQB_OK; }
+    int reserve(size_t count) { return count <= n ? LQB_OK : alloc(count, false); }      // scratch: contents undefined
+    int zero() { if (p) { LQB_CUDA(cudaMemset(p, 0, n * sizeof(T))); return settle(); } return LQB_OK; }
     int fill(const T &v)
     {
         if (!p) return LQB_OK;
         std::vector<T> h(n, v);
         LQB_CUDA(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
-        return LQB_OK;
+        return settle();
     }
-    int upload(const T *h, size_t count) { LQB_CUDA(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice)); return LQB_OK; }
+    int upload(const T *h, size_t count) { LQB_CUDA(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice)); return settle(); }
     int download(T *h, size_t count) const { LQB_CUDA(cudaMemcpy(h, p, count * sizeof(T), cudaMemcpyDeviceToHost)); return LQB_OK; }
 };
 
@@ -165,12 +172,31 @@ enum Kind { K_NCO = 0, K_IIR, K_RESAMP, K_AGC, K_AM, K_FM, K_DEEMPH, K_FIR, K_TF
 }  // namespace lqb
 
 struct lqb_chain_s;
+struct lqb_stage_s;
+
+namespace lqb {
+// Stage handles that exist.  A chain borrows raw stage pointers; an object layer that destroys and recreates a stage
+// (AmpModem's property setters, demod.hpp:250-276) leaves such a pointer dangling, so chains check their stages against
+// this set before touching them instead of dereferencing freed memory.
+static std::mutex g_live_mu;
+static std::set<const lqb_stage_s *> g_live;
+// entry points that may run from a destructor / garbage collector put the caller's current device back
+struct DevGuard {
+    int prev = -1;
+    DevGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace lqb
 
 struct lqb_stage_s {
     lqb::Kind kind; int C = 1; int device = 0;
     lqb_chain_s *self_chain = nullptr;         // one-stage chain used by lqb_stage_execute*
     bool ready = false;                        // device state allocated (first execute / state access)
-    lqb_stage_s(lqb::Kind k, int c) : kind(k), C(c) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    lqb_stage_s(lqb::Kind k, int c) : kind(k), C(c)
+    {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+        std::lock_guard<std::mutex> lk(lqb::g_live_mu); lqb::g_live.insert(this);
+    }
     virtual ~lqb_stage_s();
     virtual int materialize() = 0;             // allocate and initialise the carried state in HBM
     virtual int clear() = 0;                   // liquid *_reset() on materialised state
@@ -319,6 +345,8 @@ struct ResampStage : lqb_stage_s {
     bool out_real() const override { return variant == 2; }
     float rate = 1.f; design::ResampDesign d; uint32_t step = 0, phase = 0, count = 0;
     DevArr<float> bank; DevArr<float2> ring;            // ring [sublen][C]
+    // lane-split front kernels: the call's tap stream (lanes.cu), one scratch buffer per stream that runs the stage
+    std::map<cudaStream_t, DevArr<char>> tapbuf;
     ResampStage(int c) : lqb_stage_s(K_RESAMP, c) {}
     int materialize() override
     {
@@ -539,6 +567,9 @@ struct lqb_chain_s {
     int fuse = 1;                              // 0 one kernel per stage, 1 front/tail split, 2 longest runs
     int last_launches = 0;
     std::string plan;
+    std::string last_kernels;                  // kernels the last execute launched, in order (lqb_chain_last_kernels)
+    // a call that failed after its first launch leaves device state ahead of the host bookkeeping: refuse further calls
+    bool poisoned = false; std::string poison_why;
     // host-execute resources: per-stream input/output staging and ping-pong scratch
     static constexpr int kStreams = 3;
     cudaStream_t streams[kStreams] = { nullptr, nullptr, nullptr };
@@ -571,7 +602,11 @@ struct lqb_chain_s {
     }
 };
 
-lqb_stage_s::~lqb_stage_s() { delete self_chain; }
+lqb_stage_s::~lqb_stage_s()
+{
+    { std::lock_guard<std::mutex> lk(lqb::g_live_mu); lqb::g_live.erase(this); }
+    delete self_chain;
+}
 
 namespace lqb {
 
@@ -733,8 +768,10 @@ static int build_plan(lqb_chain_s *c, std::vector<Segment> &segs)
 static size_t seg_out_len(const Segment &g, size_t n) { for (auto *s : g.st) n = s->out_len(n); return n; }
 
 // run one segment on channels [ch0, ch0 + nch) of the chain; x/y point at the first of those rows
+static void note_kernel(std::string *kn, const std::string &name) { if (kn) { if (!kn->empty()) *kn += ";"; *kn += name; } }
+
 static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_t n_out, int ch0, int nch, cudaStream_t stream,
-                       bool in_tmajor, bool out_tmajor, int *launches, unsigned extra_mask = 0, int front_ring = 3)
+                       bool in_tmajor, bool out_tmajor, int *launches, unsigned extra_mask = 0, int front_ring = 3, std::string *kn = nullptr)
 {
     (*launches)++;
     const lqb_stage_s *first = g.st.front();
@@ -749,6 +786,8 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
             else if (s->kind == K_DEEMPH) { static_cast<DeemphStage *>(s)->fill(a.de); has_de = true; }
         }
         LQB_CUDA(amtail_launch(has_agc, has_de, a, stream));
+        if (amtail_launch_count(has_agc, a) > 1) note_kernel(kn, "agc_tmajor_kernel");
+        note_kernel(kn, "amtail_kernel");
         *launches += amtail_launch_count(has_agc, a) - 1;
         return LQB_OK;
     }
@@ -760,12 +799,14 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         a.cpw = nch >= 32768 ? 32 : (nch >= 4096 ? 16 : 8);        // (measured at 16384 channels: 23.5 / 25.0 / 13.6 GS/s at 32 / 16 / 8 -- idle lanes still cost conversion-unit slots)
         if (const char *e = getenv("LQB_CPW")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) a.cpw = v; }
         LQB_CUDA(fmstereo_launch(a, stream));
+        note_kernel(kn, "fmstereo_kernel");
         return LQB_OK;
     }
     if (g.type == Segment::DELAY) {
         const DelayStage *d = static_cast<const DelayStage *>(first);
         // histories are float2-slotted arrays; a real delay line uses them as float rows of the same length
         LQB_CUDA(delay_launch(d->real_io, x, y, d->hist[d->cur].p, d->hist[d->cur ^ 1].p, nch, ch0, (long long)n, d->D, stream));
+        note_kernel(kn, "delay_kernel");
         return LQB_OK;
     }
     if (g.type == Segment::BAM) {
@@ -779,12 +820,14 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
                 ag.x = a.x; ag.C = nch; ag.ch0 = ch0; ag.Ctot = first->C; ag.in_tmajor = 1; ag.n = a.n; ag.in_pitch = a.in_pitch;
                 LQB_TRY(static_cast<AgcStage *>(s)->fill(ag.agc));
                 LQB_CUDA(agc_tmajor_launch(ag, stream));
+                note_kernel(kn, "agc_tmajor_kernel");
                 (*launches)++;
             }
             else if (s->kind == K_BAM) LQB_TRY(static_cast<BamStage *>(s)->fill(a.p));
             else if (s->kind == K_DEEMPH) { static_cast<DeemphStage *>(s)->fill(a.de); a.has_de = 1; }
         }
         LQB_CUDA(bam_launch(a, stream));
+        note_kernel(kn, "bam_kernel");
         return LQB_OK;
     }
     if (g.type == Segment::FIR) {
@@ -823,6 +866,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         }
         a.n = (long long)n; a.scale = f->scale; a.taps = f->taps.p; a.hist_in = f->hist[f->cur].p; a.hist_out = f->hist[f->cur ^ 1].p;
         LQB_CUDA(fir_launch(a, stream));
+        note_kernel(kn, "fir_kernel");
         return LQB_OK;
     }
     if (g.type == Segment::RESAMP_PAR) {
@@ -832,11 +876,13 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         if (has_nco) LQB_TRY(static_cast<NcoStage *>(g.st.front())->fill(q));
         LQB_CUDA(resamp_par_launch(p, has_nco ? &q : nullptr, x, y, nch, ch0, r->C, (long long)n, (long long)n_out, stream));
         *launches += resamp_par_launch_count(has_nco, (long long)n_out) - 1;
+        note_kernel(kn, has_nco ? "resamp_par_kernel<nco>" : "resamp_par_kernel");
         return LQB_OK;
     }
     if (g.type == Segment::NCO_PAR) {
         NcoP q{}; LQB_TRY(static_cast<NcoStage *>(g.st.front())->fill(q));
         LQB_CUDA(nco_par_launch(q, (const float2 *)x, (float2 *)y, nch, ch0, (long long)n, stream));
+        note_kernel(kn, "nco_par_kernel");
         (*launches)++;
         return LQB_OK;
     }
@@ -858,6 +904,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
             sa.y = (float2 *)y; sa.C = nch; sa.ch0 = ch0; sa.Ctot = q->C; sa.nsos = q->nsos; sa.B = B; sa.n = (long long)n;
             sa.H = q->scanH.p; sa.M = q->scanM.p; sa.vblk = q->vblk.p; sa.v = q->v.p; sa.sin = q->sin.p;
             LQB_CUDA(iir_scan_launch(sa, stream));
+            note_kernel(kn, "seq_kernel[scan blocks];iir_scan_kernels");
             *launches += 2;
             return LQB_OK;
         }
@@ -892,9 +939,26 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         make_input_tmap(&a.tmap, x, n, (size_t)nch)) {
         a.use_tma = 1;
         LQB_CUDA(pipe_launch(g.nsos, a, stream));
+        note_kernel(kn, "pipe_kernel<" + std::to_string(g.nsos) + ">");
         return LQB_OK;
     }
-    // the headline front (cascade + decimating resampler) with many channels: two channels per thread (front.cu)
+    // the front of the receiver (cascade + decimating resampler): one component per lane (lanes.cu)
+    {
+        const int lanes = (extra_mask == 0 && !in_real && !getenv("LQB_NO_LANES")) ? lanes_per_channel(g.mask, g.nsos, nch) : 0;
+        if (lanes && make_input_tmap(&a.tmap, x, n, (size_t)nch, (unsigned)lanes_box_rows(lanes))) {
+            ResampStage *r = nullptr;
+            for (lqb_stage_s *s : g.st) if (s->kind == K_RESAMP) r = static_cast<ResampStage *>(s);
+            DevArr<char> &tb = r->tapbuf[stream];
+            LQB_TRY(tb.reserve(lanes_tapstream_bytes((long long)n)));
+            LQB_CUDA(lanes_tapstream_launch(a.rs, (long long)n, tb.p, stream));
+            a.tapstream = tb.p; a.use_tma = 1;
+            LQB_CUDA(lanes_launch(g.nsos, lanes, a, stream));
+            (*launches)++;
+            note_kernel(kn, std::string("tapstream_kernel;") + lanes_kernel_name(g.nsos, lanes));
+            return LQB_OK;
+        }
+    }
+    // (A/B: LQB_NO_LANES=1) the same front with two channels per thread, packed arithmetic (front.cu)
     {
         bool two = nch >= 32768 && extra_mask == 0 && !in_real && front2_supported(g.mask, g.nsos);
         if (const char *e = getenv("LQB_FRONT2")) two = two && atoi(e) != 0;
@@ -902,6 +966,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
             a.cpw = 32; a.use_tma = 1;
             if (const char *e = getenv("LQB_FRONT_RING")) { const int v = atoi(e); if (v == 2 || v == 3) front_ring = v; }   // tuning override
             LQB_CUDA(front2_launch(g.nsos, a, stream, front_ring));
+            note_kernel(kn, "front2_kernel<" + std::to_string(g.nsos) + ">");
             return LQB_OK;
         }
     }
@@ -912,6 +977,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
     if (a.use_tma && !(g.mask & F_RS) && !out_real && (n_out & 1) == 0 && make_input_tmap(&a.tmap_out, y, n_out, (size_t)nch)) a.tma_out = 1;
     if (a.use_tma && !(g.mask & F_RS) && !out_real && !a.tma_out) a.use_tma = 0;     // the TMA instantiation stores by TMA only
     LQB_CUDA(seq_launch(g.mask | extra_mask, g.nsos, a, stream));
+    note_kernel(kn, "seq_kernel<" + g.name + (a.use_tma ? ",tma>" : (a.cpw == 32 ? ">" : ",cpw" + std::to_string(a.cpw) + ">")));
     return LQB_OK;
 }
 
@@ -920,6 +986,12 @@ static size_t elem_bytes(bool real) { return real ? 4 : 8; }
 static int chain_validate(lqb_chain_s *c)
 {
     if (!c || c->stages.empty()) return fail(LQB_EINVAL, "empty chain");
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        for (size_t i = 0; i < c->stages.size(); i++)
+            if (!g_live.count(c->stages[i])) return fail(LQB_EINVAL, "stage %zu of the chain was destroyed (rebuild the chain after recreating a stage)", i);
+    }
+    if (c->poisoned) return fail(LQB_EINVAL, "an earlier call on this chain failed part-way (%s); reset the stages and rebuild the chain", c->poison_why.c_str());
     for (size_t i = 0; i < c->stages.size(); i++) {
         if (c->stages[i]->C != c->stages[0]->C) return fail(LQB_EINVAL, "stages of one chain must have the same channel count");
         if (c->stages[i]->device != c->stages[0]->device) return fail(LQB_EINVAL, "stages of one chain must live on one device");
@@ -944,6 +1016,7 @@ static int run_all(lqb_chain_s *c, const std::vector<Segment> &segs, const void 
         if (first_takes_i16(segs)) first_extra = F_INI16;          // bytes_to_iq fused into the front kernel
         else {                                                      // otherwise one conversion pass, then the usual plan
             LQB_CUDA(i16_to_c64_launch(x, (float2 *)cvt, (long long)nch * (long long)n, stream));
+            note_kernel(&c->last_kernels, "i16_to_c64_kernel");
             (*launches)++; x = cvt;
         }
     }
@@ -962,7 +1035,7 @@ static int run_all(lqb_chain_s *c, const std::vector<Segment> &segs, const void 
         const bool out_tm = k + 1 < segs.size() && segs[k].type == Segment::SEQ && (segs[k].mask & F_RS) &&
                             (segs[k + 1].type == Segment::AMTAIL || segs[k + 1].type == Segment::BAM);
         if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[k].first, stream));
-        if (on > 0 || cur_n > 0) LQB_TRY(run_segment(segs[k], cur, dst, cur_n, on, ch0, nch, stream, in_tm, out_tm, launches, k == 0 ? first_extra : 0u));
+        if (on > 0 || cur_n > 0) LQB_TRY(run_segment(segs[k], cur, dst, cur_n, on, ch0, nch, stream, in_tm, out_tm, launches, k == 0 ? first_extra : 0u, 3, &c->last_kernels));
         if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[k].second, stream));
         cur = dst; cur_n = on; flip ^= 1; in_tm = out_tm;
     }
@@ -1029,17 +1102,25 @@ static int run_overlapped(lqb_chain_s *c, const std::vector<Segment> &segs, cons
     // the front writes the hand-off buffer the tail of two calls ago read
     if (c->tail_pending[b]) LQB_CUDA(cudaStreamWaitEvent(stream, c->ev_tail[b], 0));
     if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[0].first, stream));
-    LQB_TRY(run_segment(segs[0], x, tmp, n, on0, 0, C, stream, false, true, &c->last_launches, 0u, 2));
+    LQB_TRY(run_segment(segs[0], x, tmp, n, on0, 0, C, stream, false, true, &c->last_launches, 0u, 2, &c->last_kernels));
     if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[0].second, stream));
     LQB_CUDA(cudaEventRecord(c->ev_front[b], stream));
     LQB_CUDA(cudaStreamWaitEvent(c->tail_stream, c->ev_front[b], 0));
     if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[1].first, c->tail_stream));
-    if (on > 0 || on0 > 0) LQB_TRY(run_segment(segs[1], tmp, y, on0, on, 0, C, c->tail_stream, true, false, &c->last_launches));
+    if (on > 0 || on0 > 0) LQB_TRY(run_segment(segs[1], tmp, y, on0, on, 0, C, c->tail_stream, true, false, &c->last_launches, 0u, 3, &c->last_kernels));
     if (!evs.empty()) LQB_CUDA(cudaEventRecord(evs[1].second, c->tail_stream));
     LQB_CUDA(cudaEventRecord(c->ev_tail[b], c->tail_stream));
     c->tail_pending[b] = true;
     if (!evs.empty()) c->timed_calls.push_back(std::move(evs));
     return LQB_OK;
+}
+
+// a failure after the first launch of a call leaves device state (filter memories, rings) ahead of the host-side phase /
+// count bookkeeping; every later call would be silently misaligned, so the chain refuses them until it is reset
+static int chain_poison(lqb_chain_s *c, int rc)
+{
+    if (c->last_launches > 0) { c->poisoned = true; c->poison_why = g_err; }
+    return rc;
 }
 
 static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, size_t cap, size_t *n_out, cudaStream_t stream, bool in_i16 = false)
@@ -1051,19 +1132,21 @@ static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, s
     size_t on; chain_out_len(c, n, &on);
     if (n_out) *n_out = on;
     if (on > cap) return fail(LQB_ESIZE, "output needs %zu samples per channel, capacity is %zu", on, cap);
-    c->last_launches = 0;
+    c->last_launches = 0; c->last_kernels.clear();
     if (n == 0) return LQB_OK;
     const int C = c->stages[0]->C;
     const size_t tmpb = max_intermediate_bytes(segs, n, (size_t)C);
     if (segs.size() > 1) LQB_TRY(c->d_tmp[0].reserve(tmpb));
     if (segs.size() > 2) LQB_TRY(c->d_tmp[1].reserve(tmpb));
     if (in_i16 && !first_takes_i16(segs)) LQB_TRY(c->d_cvt.reserve((size_t)C * n * 8));
+    int rc;
     if (overlappable(c, segs, in_i16)) {
-        LQB_TRY(run_overlapped(c, segs, x, y, n, C, tmpb, stream));
+        rc = run_overlapped(c, segs, x, y, n, C, tmpb, stream);
     } else {
         LQB_TRY(chain_join_tails(c, stream));                    // tails of earlier overlapped calls come first
-        LQB_TRY(run_all(c, segs, x, y, n, 0, C, c->d_tmp[0].p, c->d_tmp[1].p, stream, &c->last_launches, c->timing, in_i16, c->d_cvt.p));
+        rc = run_all(c, segs, x, y, n, 0, C, c->d_tmp[0].p, c->d_tmp[1].p, stream, &c->last_launches, c->timing, in_i16, c->d_cvt.p);
     }
+    if (rc != LQB_OK) return chain_poison(c, rc);
     advance_all(c, n);
     return LQB_OK;
 }
@@ -1126,8 +1209,13 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
     size_t on; chain_out_len(c, n, &on);
     if (n_out) *n_out = on;
     if (on > cap) return fail(LQB_ESIZE, "output needs %zu samples per channel, capacity is %zu", on, cap);
-    c->last_launches = 0;
+    c->last_launches = 0; c->last_kernels.clear();
     if (n == 0) return LQB_OK;
+    // tails of earlier overlapped device calls still update the carried state on the chain's tail stream
+    if (c->tail_stream && (c->tail_pending[0] || c->tail_pending[1])) {
+        LQB_CUDA(cudaStreamSynchronize(c->tail_stream));
+        c->tail_pending[0] = c->tail_pending[1] = false;
+    }
     const int C = c->stages[0]->C;
     const size_t ib = in_i16 ? 4 : elem_bytes(c->stages.front()->in_real()), ob = elem_bytes(c->stages.back()->out_real());
     const bool need_cvt = in_i16 && !first_takes_i16(segs);
@@ -1141,7 +1229,7 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
             if (st->kind == K_FIR && static_cast<FirStage *>(st)->mode == FIR_R2C) sliceable = false;
         }
         if (const char *e = getenv("LQB_HOST_MODE")) sliceable = sliceable && strcmp(e, "chunk") != 0;
-        if (sliceable) return chain_execute_host_sliced(c, segs, x, n, y, on, in_i16, ib, ob, need_cvt);
+        if (sliceable) { const int rc = chain_execute_host_sliced(c, segs, x, n, y, on, in_i16, ib, ob, need_cvt); return rc == LQB_OK ? rc : chain_poison(c, rc); }
     }
     // Channel chunks on three streams: the H2D of chunk i+1 overlaps the kernels of chunk i.  A sequential
     // kernel takes about as long for 64 channels as for 64K (it is bound by the per-channel recurrence), so
@@ -1173,7 +1261,7 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
         const size_t c0 = k * chunk, nc = std::min(chunk, (size_t)C - c0);
         char *dst = deferred ? c->h_out[0].p + c0 * on * ob : c->h_out[s].p;
         LQB_CUDA(cudaMemcpyAsync(c->h_in[s].p, (const char *)x + c0 * n * ib, nc * n * ib, cudaMemcpyHostToDevice, c->streams[s]));
-        LQB_TRY(run_all(c, segs, c->h_in[s].p, dst, n, (int)c0, (int)nc, c->h_tmp[s][0].p, c->h_tmp[s][1].p, c->streams[s], &c->last_launches, false, in_i16, c->h_cvt[s].p));
+        { const int rc = run_all(c, segs, c->h_in[s].p, dst, n, (int)c0, (int)nc, c->h_tmp[s][0].p, c->h_tmp[s][1].p, c->streams[s], &c->last_launches, false, in_i16, c->h_cvt[s].p); if (rc != LQB_OK) return chain_poison(c, rc); }
         if (on && !deferred) LQB_CUDA(cudaMemcpyAsync((char *)y + c0 * on * ob, dst, nc * on * ob, cudaMemcpyDeviceToHost, c->streams[s]));
     }
     for (int s = 0; s < lqb_chain_s::kStreams; s++) LQB_CUDA(cudaStreamSynchronize(c->streams[s]));
@@ -1212,7 +1300,7 @@ int lqb_memcpy_d2h(void *h, const void *d, size_t b, void *st) { LQB_CUDA(cudaMe
 int lqb_stream_synchronize(void *st) { LQB_CUDA(cudaStreamSynchronize((cudaStream_t)st)); return LQB_OK; }
 
 // ---- generic
-int lqb_stage_destroy(lqb_stage s) { if (s) { if (s->ready) s->bind(); delete s; } return LQB_OK; }
+int lqb_stage_destroy(lqb_stage s) { if (s) { DevGuard g; if (s->ready) s->bind(); delete s; } return LQB_OK; }
 int lqb_stage_reset(lqb_stage s) { if (!s) return fail(LQB_EINVAL, "null stage"); return s->reset(); }
 int lqb_stage_channels(lqb_stage s, int *n) { if (!s) return fail(LQB_EINVAL, "null stage"); *n = s->C; return LQB_OK; }
 int lqb_stage_out_len(lqb_stage s, size_t n, size_t *n_out) { if (!s) return fail(LQB_EINVAL, "null stage"); *n_out = s->out_len(n); return LQB_OK; }
@@ -1237,7 +1325,6 @@ int lqb_iirfilt_crcf_create_prototype(int ftype, int btype, int order, float fc,
 {
     std::vector<float> B, A;
     const int rc = design::iirdes_sos(ftype, btype, (unsigned)order, fc, f0, ap, as, B, A);
-    if (rc == -2) return fail(LQB_ENOTIMPL, "iirdes: filter family %d (ellip/bessel) is outside the built scope", ftype);
     if (rc != 0) return fail(LQB_EINVAL, "iirdes: invalid design parameters (order %d, fc %g, f0 %g, ap %g, as %g)", order, fc, f0, ap, as);
     return lqb_iirfilt_crcf_create_sos(B.data(), A.data(), (int)B.size() / 3, C, out);
 }
@@ -1410,7 +1497,7 @@ int lqb_resamp_create(float rate, int m, float fc, float as, int npfb, int C, lq
 {
     LQB_TRY(check_channels(C));
     if (!(rate > 0.f) || m < 1 || npfb < 1 || !out) return fail(LQB_EINVAL, "resamp: rate, m and npfb must be positive");
-    if (rate < 0.004f || rate > 250.f) return fail(LQB_EINVAL, "resamp: rate %g outside [0.004, 250]", rate);
+    if (!(rate >= 0.004f && rate <= 250.f)) return fail(LQB_EINVAL, "resamp: rate %g outside [0.004, 250]", rate);
     ResampStage *q = new ResampStage(C);
     if (!design::resamp_design((unsigned)m, fc, as, (unsigned)npfb, q->d)) { delete q; return fail(LQB_EINVAL, "resamp: invalid prototype (fc %g, As %g)", fc, as); }
     q->rate = rate; q->step = design::resamp_step(rate);
@@ -1444,7 +1531,7 @@ int lqb_wdelay_create(int delay, int real_samples, int C, lqb_stage *out)
 int lqb_resamp_set_rate(lqb_stage s, float rate)
 {
     LQB_GET(ResampStage, q, s, K_RESAMP);
-    if (rate < 0.004f || rate > 250.f) return fail(LQB_EINVAL, "resamp: rate %g outside [0.004, 250]", rate);
+    if (!(rate >= 0.004f && rate <= 250.f)) return fail(LQB_EINVAL, "resamp: rate %g outside [0.004, 250]", rate);
     q->rate = rate; q->step = design::resamp_step(rate); return LQB_OK;
 }
 int lqb_resamp_get_state(lqb_stage s, uint32_t *step, uint32_t *phase) { LQB_GET(ResampStage, q, s, K_RESAMP); if (step) *step = q->step; if (phase) *phase = q->phase; return LQB_OK; }
@@ -1699,7 +1786,7 @@ int lqb_freqdem_create(float kf, int C, lqb_stage *out)
 // ---- chain
 int lqb_chain_create(lqb_chain *out) { if (!out) return fail(LQB_EINVAL, "null out"); *out = new lqb_chain_s(); return LQB_OK; }
 int lqb_chain_append(lqb_chain c, lqb_stage s) { if (!c || !s) return fail(LQB_EINVAL, "null handle"); c->stages.push_back(s); return LQB_OK; }
-int lqb_chain_destroy(lqb_chain c) { delete c; return LQB_OK; }
+int lqb_chain_destroy(lqb_chain c) { if (c) { DevGuard g; if (!c->stages.empty()) { std::lock_guard<std::mutex> lk(g_live_mu); if (g_live.count(c->stages[0])) cudaSetDevice(c->stages[0]->device); } delete c; } return LQB_OK; }
 int lqb_chain_out_len(lqb_chain c, size_t n, size_t *n_out) { if (!c || !n_out) return fail(LQB_EINVAL, "null handle"); return chain_out_len(c, n, n_out); }
 int lqb_chain_execute(lqb_chain c, const void *x, size_t n, void *y, size_t cap, size_t *n_out) { if (!c) return fail(LQB_EINVAL, "null chain"); return chain_execute_host(c, x, n, y, cap, n_out); }
 int lqb_chain_execute_dev(lqb_chain c, const void *x, size_t n, void *y, size_t cap, size_t *n_out, void *stream)
@@ -1727,6 +1814,13 @@ int lqb_chain_plan(lqb_chain c, char *buf, size_t len)
     snprintf(buf, len, "%s", c->plan.c_str());
     return LQB_OK;
 }
+int lqb_chain_last_kernels(lqb_chain c, char *buf, size_t len)
+{
+    if (!c || !buf || !len) return fail(LQB_EINVAL, "null argument");
+    snprintf(buf, len, "%s", c->last_kernels.c_str());
+    return LQB_OK;
+}
+int lqb_chain_clear_error(lqb_chain c) { if (!c) return fail(LQB_EINVAL, "null chain"); c->poisoned = false; c->poison_why.clear(); return LQB_OK; }
 int lqb_chain_last_launches(lqb_chain c, int *n) { if (!c || !n) return fail(LQB_EINVAL, "null argument"); *n = c->last_launches; return LQB_OK; }
 int lqb_chain_set_timing(lqb_chain c, int enabled)
 {

@@ -96,6 +96,7 @@ struct alignas(64) SeqArgs {
     int cpw;                       // channels per warp: 32, or 16 / 8 to spread few channels over more warps
     int use_tma;                   // tmap is valid: stage the input with TMA (full-warp kernels that have the variant)
     int out_tmajor;                // decimated output stored [sample][channel] (hand-off to the AM tail kernel)
+    const void *tapstream;         // lane-split front kernels (lanes.cu): per-tile tap records of this call
     long long n, out_pitch;
     NcoP nco; IirP iir; ResampP rs; AgcP agc; AmP am; FmP fm; DeP de; TfP tf;
 };

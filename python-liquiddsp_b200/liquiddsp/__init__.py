@@ -21,8 +21,14 @@ import weakref
 import os
 import numpy as np
 
-__all__ = ["bytes_to_iq", "ComplexIIRFilter", "DeemphasisFilter", "FIRFilter", "ComplexResampler", "NCO", "AGC",
-           "AmpModem", "FreqDem", "Chain", "PcmFramer", "synth_fill", "lib_path"]
+# every class and function wrapper.cpp binds (`from liquiddsp import *` matches the reference module), then the extensions
+__all__ = ["bytes_to_iq", "CIIRFilter", "CLowpassIIR", "CHighpassIIR", "CBandpassIIR", "CBandstopIIR",
+           "RIIRFilter", "RLowpassIIR", "RHighpassIIR", "RBandpassIIR", "RBandstopIIR", "ComplexIIRFilter", "RealIIRFilter",
+           "HilbertTransform", "DeemphasisFilter", "FreqDem", "AmpModem", "NCO", "Delay", "CResampler", "RResampler",
+           "ComplexResampler", "RealResampler", "AGC", "RealFIRFilter", "RealDCBlocker", "RealKaiserBessel", "BroadcastAM",
+           "FMStereo", "SSBDemod",
+           "FIRFilter", "Chain", "PcmFramer", "DeviceBuffer", "synth_fill", "stream_create", "stream_destroy",
+           "stream_synchronize", "device_count", "set_device", "synchronize", "lib_path"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 lib_path = os.path.join(os.path.dirname(_HERE), "lib", "libliquiddsp_b200.so")
@@ -98,6 +104,7 @@ _SIG = {
     "lqb_chain_execute_i16": [_P, _P, _SZ, _P, _SZ, C.POINTER(_SZ)],
     "lqb_chain_execute_i16_dev": [_P, _P, _SZ, _P, _SZ, C.POINTER(_SZ), _P], "lqb_bytes_to_iq": [_P, _SZ, _P],
     "lqb_chain_set_timing": [_P, _I], "lqb_chain_get_timing": [_P, _P, _I, C.POINTER(_I), C.POINTER(_I)],
+    "lqb_chain_last_kernels": [_P, C.c_char_p, _SZ], "lqb_chain_clear_error": [_P],
     "lqb_chain_plan": [_P, C.c_char_p, _SZ], "lqb_chain_last_launches": [_P, C.POINTER(_I)], "lqb_chain_set_fusion": [_P, _I],
     "lqb_chain_set_overlap": [_P, _I], "lqb_chain_wait": [_P, _P],
     "lqb_stream_create": [C.POINTER(_P), _I], "lqb_stream_destroy": [_P],
@@ -331,6 +338,13 @@ class FIRFilter(_Stage):
         h = np.ascontiguousarray(h, np.float32).ravel()
         _ck(_lib.lqb_firfilt_crcf_create(_ptr(h), h.size, channels, C.byref(self._h)))
 
+    @classmethod
+    def kaiser(cls, n, fc, As=60.0, mu=0.0, channels=1):
+        """firfilt_crcf_create_kaiser: an n-tap Kaiser-windowed lowpass designed by the library (liquid's firdes_kaiser)."""
+        self = cls.__new__(cls); _Stage.__init__(self)
+        _ck(_lib.lqb_firfilt_crcf_create_kaiser(int(n), fc, As, mu, channels, C.byref(self._h)))
+        return self
+
     def taps(self):
         h = np.zeros(1024, np.float32); n = _I(); _ck(_lib.lqb_firfilt_crcf_get_taps(self._h, _ptr(h), C.byref(n))); return h[:n.value].copy()
 
@@ -361,10 +375,12 @@ class RealDCBlocker(RealFIRFilter):
 
 
 class RealKaiserBessel(RealFIRFilter):
-    """wrapper.cpp:254-257 / firfilter.hpp:52-67: Kaiser lowpass scaled to unit gain at DC."""
+    """wrapper.cpp:254-257 / firfilter.hpp:52-67: Kaiser lowpass scaled to unit gain at DC.  `Fc` has no default, as in the reference."""
 
-    def __init__(self, flen=25, Fc=0.25, As=20.0, offset=0.0, channels=1):
+    def __init__(self, flen=25, Fc=None, As=20.0, offset=0.0, channels=1):
         _Stage.__init__(self)
+        if Fc is None:                      # wrapper.cpp:255: py::arg("Fc") carries no default
+            raise TypeError("RealKaiserBessel() missing required argument: 'Fc'")
         _ck(_lib.lqb_firfilt_rrrf_create_kaiser(int(flen), Fc, As, offset, channels, C.byref(self._h)))
         # firfilter.hpp:59-60: set_scale(1.0 / abs(H(0))) -- the division is done in double, then narrowed
         H0 = self.freqresponse(0.0)
@@ -750,8 +766,10 @@ class Chain(_Stage):
         return self.stages[0].channels
 
     def reset(self):
+        self._sync()
         for s in self.stages:
             s.reset()
+        _ck(_lib.lqb_chain_clear_error(self._h))
 
     def plan(self):
         self._sync()
@@ -769,6 +787,7 @@ class Chain(_Stage):
 
     def wait(self, stream=0):
         """Make `stream` wait for the tails of every overlapped execute_dev call issued so far."""
+        self._sync()
         _ck(_lib.lqb_chain_wait(self._h, C.c_void_p(stream)))
 
     def set_timing(self, enabled=True):
@@ -812,12 +831,18 @@ class Chain(_Stage):
         self._after()
         return y.reshape(-1) if flat else y
 
+    def last_kernels(self):
+        """Names of the kernels the last call launched, in launch order (what the C ABI dispatched, not a guess)."""
+        buf = C.create_string_buffer(4096); _ck(_lib.lqb_chain_last_kernels(self._h, buf, 4096)); return buf.value.decode().split(";") if buf.value else []
+
     def execute_i16_dev(self, iq_ptr, n, y_ptr, y_capacity, stream=0):
+        self._sync()
         got = _SZ()
         _ck(_lib.lqb_chain_execute_i16_dev(self._h, C.c_void_p(iq_ptr), n, C.c_void_p(y_ptr), y_capacity, C.byref(got), C.c_void_p(stream)))
         return got.value
 
     def execute_dev(self, x_ptr, n, y_ptr, y_capacity, stream=0):
+        self._sync()                                 # a stage recreated by a property setter: rebuild before the C layer sees it
         got = _SZ()
         _ck(_lib.lqb_chain_execute_dev(self._h, C.c_void_p(x_ptr), n, C.c_void_p(y_ptr), y_capacity, C.byref(got), C.c_void_p(stream)))
         return got.value

@@ -22,7 +22,9 @@ def gather_audio(local, dst=0, group=None):
     import torch
     import torch.distributed as dist
 
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    # `dst` is a GLOBAL rank, as torch.distributed.gather takes it; compare like with like (a sub-group's local ranks
+    # need not be 0..N-1 of the job)
+    world, rank = dist.get_world_size(group), dist.get_rank()
     counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device), group=group)
     counts = [int(c.item()) for c in counts]

@@ -85,7 +85,9 @@ def test_reference_api_surface():
     with pytest.raises(ValueError):
         L.HilbertTransform(m=1)
     assert sig(L.RealDCBlocker) == dict(slen=25, As=20.0)
-    assert sig(L.RealKaiserBessel) == dict(flen=25, Fc=0.25, As=20.0, offset=0.0)
+    assert sig(L.RealKaiserBessel) == dict(flen=25, Fc=None, As=20.0, offset=0.0)      # wrapper.cpp:255: Fc required
+    with pytest.raises(TypeError):
+        L.RealKaiserBessel(31)
     assert L.CBandpassIIR.__name__ == "CBandpassIIR" and L.RLowpassIIR("cheby1", 4, 0.1).band_type == "lowpass"
 
 

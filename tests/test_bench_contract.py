@@ -18,9 +18,9 @@ def _run(args, timeout=600):
 
 def test_reference_arm_line():
     d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-seconds", "1.0"])
-    assert d["impl"] == "reference" and d["unit"] == "Msamples/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["impl"] == "reference" and d["unit"] == "Msamples/s" and d["higher_is_better"] is True and d["scaling"] == "strong"
     assert d["metric"] == "AM-chain aggregate input Msamples/s" and d["value"] > 0 and d["vs_baseline"] is None
-    assert d["config"]["workload"].startswith("config5")
+    assert d["config"]["workload"].startswith("config5") and d["config"]["channels_total"] == 65536 and d["config"]["block"] == 65536
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -28,12 +28,14 @@ def test_reference_arm_line():
 
 @pytest.mark.gpu
 def test_product_arm_line(cuda):
-    d = _run(["--steps", "3", "--warmup", "3", "--no-cpu", "--block", "8192"])
+    d = _run(["--steps", "3", "--warmup", "3", "--no-cpu", "--block", "8192", "--no-side", "--e2e-channels", "4096"])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
-              "data", "config", "gpu_launches", "clocks", "roofline", "e2e"):
+              "data", "config", "gpu", "gpu_launches", "clocks", "roofline", "e2e"):
         assert k in d, k
-    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["dtype"] == "f32" and d["data"] == "synthetic" and d["gpu_launches"] == 9
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["dtype"] == "f32" and d["data"] == "synthetic" and d["scaling"] == "strong"
+    assert d["gpu_launches"] == 3 * len(d["gpu"]["kernels"]) and d["gpu"]["channels_per_gpu"] == 65536
     r = d["roofline"]
+    assert r["kernel"].split(" ")[0] in d["gpu"]["kernels"]            # named by the library, not guessed
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]

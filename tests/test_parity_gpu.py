@@ -705,11 +705,13 @@ def test_fused_chain_matches_stagewise(cuda, fuse):
     x = am_iq(n, seed=5)
     a, b = _Radio(L), _Radio(L)
     chain = L.Chain(*b.stages(), fuse=fuse)
-    expect = {0: 6, 1: 3, 2: 1}[fuse]        # level 1: full-rate kernel, AGC in place on the hand-off, AM tail
+    expect = {0: 6, 1: 4, 2: 1}[fuse]        # level 1: tap stream + full-rate kernel, AGC in place on the hand-off, AM tail
     ys, yc = [], []
     for i in range(0, n, blk):
         ys.append(a(x[i:i + blk])); yc.append(chain(x[i:i + blk]))
         assert chain.last_launches() == expect
+        if fuse == 1:                        # the library names what it dispatched (lqb_chain_last_kernels)
+            assert chain.last_kernels() == ["tapstream_kernel", "lane2_kernel<4>", "agc_tmajor_kernel", "amtail_kernel"]
     ys, yc = np.concatenate(ys), np.concatenate(yc)
     assert np.array_equal(ys.view(np.uint32), yc.view(np.uint32)), rel_l2(yc, ys)
     assert b.resample.state() == a.resample.state()
