@@ -399,9 +399,9 @@ def main():
                     help="BASELINE.json config: 5 (default, the headline AM receiver), 2 FIR, 3 NCO+resampler, 4 IIR+AGC+FM")
     ap.add_argument("--agc-precision", default="auto", choices=["auto", "exact", "fast"],
                     help="--next agc: gain-loop arithmetic of the stage alone (auto = exact for a stage on its own)")
-    ap.add_argument("--overlap", default="auto",
-                    help="config 5: 1 = block k's decimated-rate tail overlaps block k+1's front (lqb_chain_set_overlap), 0 = serial calls, "
-                         "auto = overlapped when a GPU's share leaves the machine partly empty (< 32768 channels)")
+    ap.add_argument("--overlap", default="0",
+                    help="config 5: 1 = block k's decimated-rate tail overlaps block k+1's front (lqb_chain_set_overlap), 0 = serial calls "
+                         "(measured slower both with a full machine and with 8192 channels per GPU: DESIGN 4.9)")
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -490,7 +490,7 @@ def main():
     C = args.channels // world if args.scaling == "strong" else args.channels          # this rank's share
     if C < 1:
         raise SystemExit("bench.py: fewer channels than GPUs")
-    ov = (C < 32768) if args.overlap == "auto" else bool(int(args.overlap))
+    ov = bool(int(args.overlap))
     m = measure_chain(L, torch, dev, rank, C, n, args.steps, args.warmup, args.fuse, ov, barrier, max_over_ranks, sample_clocks=(rank == 0), local=local)
     ms_step = m["ms_step"]
     value = world * C * n / (ms_step * 1e-3) / 1e6

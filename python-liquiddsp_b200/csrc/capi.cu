@@ -950,7 +950,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
             for (lqb_stage_s *s : g.st) if (s->kind == K_RESAMP) r = static_cast<ResampStage *>(s);
             DevArr<char> &tb = r->tapbuf[stream];
             LQB_TRY(tb.reserve(lanes_tapstream_bytes((long long)n)));
-            LQB_CUDA(lanes_tapstream_launch(a.rs, (long long)n, tb.p, stream));
+            LQB_CUDA(lanes_tapstream_launch(a.rs, (long long)n, lanes_lag(g.nsos, lanes), tb.p, stream));
             a.tapstream = tb.p; a.use_tma = 1;
             LQB_CUDA(lanes_launch(g.nsos, lanes, a, stream));
             (*launches)++;

@@ -11,8 +11,10 @@ int lanes_per_channel(unsigned mask, int nsos, long long nch);
 // rows of the TMA box the kernel expects in SeqArgs::tmap for that lane count (= channels per warp)
 inline int lanes_box_rows(int lanes) { return 32 / lanes; }
 // the per-call tap stream (one 144-byte record per 16-sample tile): bytes needed, and the kernel that fills it
+// (records are in step space: the cascade's last section runs lanes_lag() steps behind the input)
+int lanes_lag(int nsos, int lanes);
 size_t lanes_tapstream_bytes(long long n);
-cudaError_t lanes_tapstream_launch(const ResampP &rs, long long n, void *buf, cudaStream_t stream);
+cudaError_t lanes_tapstream_launch(const ResampP &rs, long long n, int lag, void *buf, cudaStream_t stream);
 // a.tmap: [lanes_box_rows x 128 B] boxes, a.tapstream: filled by lanes_tapstream_launch for this call's phase and length
 cudaError_t lanes_launch(int nsos, int lanes, const SeqArgs &a, cudaStream_t stream);
 const char *lanes_kernel_name(int nsos, int lanes);

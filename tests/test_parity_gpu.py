@@ -711,7 +711,7 @@ def test_fused_chain_matches_stagewise(cuda, fuse):
         ys.append(a(x[i:i + blk])); yc.append(chain(x[i:i + blk]))
         assert chain.last_launches() == expect
         if fuse == 1:                        # the library names what it dispatched (lqb_chain_last_kernels)
-            assert chain.last_kernels() == ["tapstream_kernel", "lane2_kernel<4>", "agc_tmajor_kernel", "amtail_kernel"]
+            assert chain.last_kernels() == ["tapstream_kernel", "lanes_kernel<1,4>", "agc_tmajor_kernel", "amtail_kernel"]     # one channel: 4 lane pairs
     ys, yc = np.concatenate(ys), np.concatenate(yc)
     assert np.array_equal(ys.view(np.uint32), yc.view(np.uint32)), rel_l2(yc, ys)
     assert b.resample.state() == a.resample.state()
