@@ -787,7 +787,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         }
         LQB_CUDA(amtail_launch(has_agc, has_de, a, stream));
         if (amtail_launch_count(has_agc, a) > 1) note_kernel(kn, "agc_tmajor_kernel");
-        note_kernel(kn, "amtail_kernel");
+        note_kernel(kn, amtail_few(has_agc, a) ? "amtail8_kernel" : "amtail_kernel");
         *launches += amtail_launch_count(has_agc, a) - 1;
         return LQB_OK;
     }

@@ -87,16 +87,24 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 template <int N> __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// radians -> uint32 phase, the oscillator's own arithmetic (see design.hpp nco_constrain): the
-// 1/(2 pi) product is taken in double and rounded to float, everything after is float; a
-// fractional part that rounds up to 1.0f wraps to phase 0.
+// radians -> uint32 phase, the oscillator's own arithmetic (see design.hpp nco_constrain): liquid takes the 1/(2 pi)
+// product in double and rounds it to float, everything after is float; a fractional part that rounds up to 1.0f wraps
+// to phase 0.  The carrier loops call this twice per sample on their critical path, and the double product costs two
+// format conversions (19 cycles each on sm_100a) around the DMUL, a FRND and a 64-bit F2I: ~110 cycles of the loop's
+// ~170.  Here the same value in single precision: K = 1/(2 pi) as the double literal liquid uses splits exactly into
+// K1 + K2 + K3 (24 + 24 + 3 bits); theta K1 as head + exact tail (FMUL, FFMA), plus theta K2, summed small to large.
+// tools/check_nco_constrain.c compares the result with (float)((double)theta * K) -- and the whole function with the
+// double / int64 formulation -- for EVERY finite float theta: 4,278,190,080 inputs, no mismatch (tests run a sample).
 __device__ __forceinline__ uint32_t nco_constrain_dev(float theta)
 {
-    float p = (float)((double)theta * 0.159154943091895);
-    float fpart = __fsub_rn(p, truncf(p));               // == p - (float)(long long)p for |p| < 2^63, one conversion instead of two
+    const float K1 = 0x1.45f306p-3f, K2 = 0x1.b9390ep-28f;
+    const float h1 = __fmul_rn(theta, K1), l1 = __fmaf_rn(theta, K1, -h1), h2 = __fmul_rn(theta, K2);
+    const float p = __fadd_rn(h1, __fadd_rn(l1, h2));
+    float fpart = p;
+    if (fabsf(p) >= 1.0f) fpart = __fsub_rn(p, truncf(p));          // (loop corrections are far below one turn)
     if (fpart < 0.f) fpart = __fadd_rn(fpart, 1.0f);
-    float scaled = __fmul_rn(fpart, 4294967296.0f);
-    return (uint32_t)(unsigned long long)(long long)scaled;
+    const float scaled = __fmul_rn(fpart, 4294967296.0f);
+    return scaled >= 4294967296.0f ? 0u : __float2uint_rz(scaled);   // (cvt.rzi.u32 saturates; liquid's cast wraps 2^32 to 0)
 }
 
 // y = x * exp(+j theta) or x * exp(-j theta) with (s, c) = (sin, cos):

@@ -300,14 +300,20 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
         const int stage_n = stage + 1 == NST ? 0 : stage + 1;
         const unsigned parity_n = stage + 1 == NST ? parity ^ 1u : parity;
         // (only where a lone warp runs a scheduler: with seven warps per scheduler the wait costs nothing and the probe does)
-        if constexpr (TPS > 1) ready = (sg + 1 < nstg) ? __all_sync(0xffffffffu, mbar_try(&ws.bar[stage_n], parity_n)) != 0 : false;
+        bool probe = false;
+        if constexpr (TPS > 1) probe = (sg + 1 < nstg) ? mbar_try(&ws.bar[stage_n], parity_n) : false;
+        int e_nx = -1, gen_nx = 0; bool flags_nx = false;      // the next tile's flags, read from its record one tile ahead
 #pragma unroll 1
         for (int q = 0; q < TPS; q++) {
         const int t = sg * TPS + q;
         if (t >= ntiles) break;
         const unsigned rowp = rowbase + stage * STB + q * WTA;
         const TileRec &rec = ws.rec[stage][q];
-        const int e = rec.emit;
+        const int e = flags_nx ? e_nx : rec.emit, gen = flags_nx ? gen_nx : rec.gen;
+        if constexpr (TPS > 1) {
+            flags_nx = q + 1 < TPS;
+            if (flags_nx) { const int2 f = *(const int2 *)&ws.rec[stage][q + 1].emit; e_nx = f.x; gen_nx = f.y; }
+        }
         if (t >= tfast0 && t < tfast1) {
             auto body = [&](auto general) {
                 constexpr bool GEN = decltype(general)::value;
@@ -337,7 +343,7 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
                 });
                 if constexpr (GEN) { if (e >= 0) { emit_out(outv); kout++; } }
             };
-            if (rec.gen) body(std::true_type{}); else body(std::false_type{});
+            if (gen) body(std::true_type{}); else body(std::false_type{});
         } else {
             // the call's first and last tiles: the same step with validity predicates, saving the newest L filtered samples
             // to the history ring
@@ -353,6 +359,8 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
             }
         }
         }
+        // (the vote makes the probe's answer warp-uniform; taken here, after the stage's arithmetic, so that nothing waits for it)
+        if constexpr (TPS > 1) ready = __all_sync(0xffffffffu, probe) != 0;
         if (++stage == NST) { stage = 0; parity ^= 1u; }
     }
 

@@ -711,7 +711,7 @@ def test_fused_chain_matches_stagewise(cuda, fuse):
         ys.append(a(x[i:i + blk])); yc.append(chain(x[i:i + blk]))
         assert chain.last_launches() == expect
         if fuse == 1:                        # the library names what it dispatched (lqb_chain_last_kernels)
-            assert chain.last_kernels() == ["tapstream_kernel", "lanes_kernel<1,4>", "agc_tmajor_kernel", "amtail_kernel"]     # one channel: 4 lane pairs
+            assert chain.last_kernels() == ["tapstream_kernel", "lanes_kernel<1,4>", "agc_tmajor_kernel", "amtail8_kernel"]     # one channel: 4 lane pairs
     ys, yc = np.concatenate(ys), np.concatenate(yc)
     assert np.array_equal(ys.view(np.uint32), yc.view(np.uint32)), rel_l2(yc, ys)
     assert b.resample.state() == a.resample.state()
@@ -967,3 +967,25 @@ def test_pipeline_kernel_equals_one_warp_kernel(cuda, C, n, order, monkeypatch):
     for c in sorted({0, C // 2, C - 1}):
         yo = O.FreqDem(0.1)(O.AGC()(O.ComplexIIRFilter(_sos=iir.sos())(x[c])))
         assert np.linalg.norm(yp[c] - yo) / np.sqrt(n) <= 5 * TOL_E2E, c
+
+
+def test_amtail_eight_lane_kernel_equals_thread_per_channel(cuda, monkeypatch):
+    """Few channels run the AM tail with eight lanes per channel (am.cu amtail8_kernel); LQB_NO_AMTAIL8 selects the
+    one-thread-per-channel kernel.  Same arithmetic: bit-identical audio and PLL words, ragged calls, carried state."""
+    C, n = 37, 3 * 4096 + 123
+    rng = np.random.default_rng(88)
+    x = np.stack([am_iq(n, seed=300 + c, f_off=150.0 + 11 * c) for c in range(C)])
+    cuts = split_points(n, 5, rng)
+    outs, words = [], []
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("LQB_NO_AMTAIL8", env)
+        else:
+            monkeypatch.delenv("LQB_NO_AMTAIL8", raising=False)
+        r = _Radio(L, channels=C)
+        ch = L.Chain(*r.stages())
+        ys = [ch(np.ascontiguousarray(x[:, s:e])) for s, e in cuts]
+        assert ("amtail8_kernel" in ch.last_kernels()) == (env is None)
+        outs.append(np.concatenate(ys, axis=1)); words.append(r.am.nco_u32())
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    assert np.array_equal(words[0][0], words[1][0]) and np.array_equal(words[0][1], words[1][1])

@@ -1,0 +1,17 @@
+#!/bin/bash
+cd /root/repo
+python -m pytest tests -q -m gpu -x > gpurun_out/r2c14_pytest.log 2>&1; tail -4 gpurun_out/r2c14_pytest.log
+for c in 1 1024 8192 65536; do
+  python bench.py --channels $c --no-cpu --no-e2e --no-side --steps 10 > gpurun_out/r2c14_c${c}_new.json 2>&1
+  LQB_NO_AMTAIL8=1 python bench.py --channels $c --no-cpu --no-e2e --no-side --steps 10 > gpurun_out/r2c14_c${c}_old.json 2>&1
+done
+python bench.py --next bam --no-cpu --steps 5 2>&1 | tail -1 | cut -c1-200
+python bench.py --next fmstereo --no-cpu --steps 5 2>&1 | tail -1 | cut -c1-200
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r2c14_c*.json')):
+    for l in open(f):
+        if l.startswith('{"metric'):
+            d=json.loads(l); r=d.get('roofline') or {}
+            print(f, round(d['value']), 'MS/s', round(d['ms_per_step'],3), r.get('segments_ms'), d['gpu']['kernels'][1:])
+PY
