@@ -865,6 +865,11 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
             }
         }
         a.n = (long long)n; a.scale = f->scale; a.taps = f->taps.p; a.hist_in = f->hist[f->cur].p; a.hist_out = f->hist[f->cur ^ 1].p;
+        a.utap = 0;
+        if (f->hlane_q.empty() && f->h.size() <= (size_t)kFirUTaps && !getenv("LQB_FIR_NOUTAP")) {
+            a.utap = 1;
+            for (int k = 0; k < kFirUTaps; k++) a.taps_c[k] = k < (int)f->h.size() ? f->h[k] : 0.f;
+        }
         LQB_CUDA(fir_launch(a, stream));
         note_kernel(kn, "fir_kernel");
         return LQB_OK;

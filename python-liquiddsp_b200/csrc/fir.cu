@@ -42,8 +42,8 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 // SKIP: 1 / 2 = the taps at even / odd positions are zero in both lanes except (at most) position a.skip_keep -- the
 // Hilbert-pair filters (firhilbf: quadrature taps on every other position, the in-phase lane a pure delay); those
 // positions' multiply-adds are not issued
-template <bool IN_REAL, bool OUT_REAL, int SKIP>
-__global__ void __launch_bounds__(NT, 4) fir_kernel(const FirArgs a, const int ntiles, const int ntaps_pad, const int tpc, const int groups)
+template <bool IN_REAL, bool OUT_REAL, int SKIP, bool UTAP>
+__global__ void __launch_bounds__(NT, 4) fir_kernel(const __grid_constant__ FirArgs a, const int ntiles, const int ntaps_pad, const int tpc, const int groups)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int halo = ntaps_pad - 1;
@@ -136,8 +136,14 @@ __global__ void __launch_bounds__(NT, 4) fir_kernel(const FirArgs a, const int n
         auto chunk = [&](const u64 (&lo)[R], const u64 (&hi)[R], int kb) {
 #pragma unroll
             for (int kk = 0; kk < R; kk += 2) {
-                const float4 t2 = *(const float4 *)&s_h[kb + kk];       // two taps per load
-                const u64 tap0 = pk(t2.x, t2.y), tap1 = pk(t2.z, t2.w);
+                u64 tap0, tap1;
+                if constexpr (UTAP) {                                   // warp-uniform taps from the constant bank
+                    const float h0 = a.taps_c[kb + kk], h1 = a.taps_c[kb + kk + 1];
+                    tap0 = pk(h0, h0); tap1 = pk(h1, h1);
+                } else {
+                    const float4 t2 = *(const float4 *)&s_h[kb + kk];   // two taps per load
+                    tap0 = pk(t2.x, t2.y); tap1 = pk(t2.z, t2.w);
+                }
                 if (SKIP != 1 || kb + kk == a.skip_keep) {
 #pragma unroll
                     for (int r = 0; r < R; r++) {
@@ -243,9 +249,12 @@ cudaError_t fir_launch(const FirArgs &a, cudaStream_t stream)
     if (a.pair && (!a.real_io || a.mode != FIR_PLAIN || (a.ch0 & 1))) return cudaErrorInvalidValue;
     const bool in_real = a.real_io || a.in_real, out_real = a.real_io || a.out_real;
     const int skip = in_real ? 0 : a.skip;                             // compiled for complex input (the Hilbert-pair users)
-    auto fn = in_real ? (out_real ? fir_kernel<true, true, 0> : fir_kernel<true, false, 0>)
-            : out_real ? (skip == 1 ? fir_kernel<false, true, 1> : skip == 2 ? fir_kernel<false, true, 2> : fir_kernel<false, true, 0>)
-                       : (skip == 1 ? fir_kernel<false, false, 1> : skip == 2 ? fir_kernel<false, false, 2> : fir_kernel<false, false, 0>);
+    const bool ut = a.utap && a.taps_q == nullptr && ntaps_pad <= kFirUTaps;
+    typedef void (*FirFn)(const FirArgs, const int, const int, const int, const int);
+    FirFn fn = in_real ? (out_real ? (ut ? fir_kernel<true, true, 0, true> : fir_kernel<true, true, 0, false>) : fir_kernel<true, false, 0, false>)
+             : out_real ? (skip == 1 ? fir_kernel<false, true, 1, false> : skip == 2 ? fir_kernel<false, true, 2, false> : fir_kernel<false, true, 0, false>)
+                        : (skip == 1 ? fir_kernel<false, false, 1, false> : skip == 2 ? fir_kernel<false, false, 2, false>
+                                     : (ut ? fir_kernel<false, false, 0, true> : fir_kernel<false, false, 0, false>));
     cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     fn<<<(unsigned)(groups * rows), NT, smem, stream>>>(a, (int)ntiles, ntaps_pad, (int)tpc, (int)groups);

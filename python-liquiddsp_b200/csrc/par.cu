@@ -48,16 +48,29 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 template <bool HAS_NCO, int VAR>
 __global__ void __launch_bounds__(NT)
 resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, void *__restrict__ yv, int ch0, int Ctot,
-                  long long n, long long n_out, int KT, int ntiles, int span_max)
+                  long long n, long long n_out, int KT, int ntiles, int span_max, long long nwork)
 {
     constexpr bool REAL = VAR == 2;
     static_assert(!(REAL && HAS_NCO), "the mixer runs on complex samples");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *s_x = (float2 *)smem_raw;                   // span_max samples (float2 slots also when the samples are real)
-    float  *s_xr = (float *)smem_raw;
-    float  *s_b = (float *)(s_x + span_max);            // bank [npfb][sublen]  (span_max leaves room for the alignment shifts below)
-    const int tid = threadIdx.x, L = p.sublen;
-    const long long ch = blockIdx.x / ntiles, tile = blockIdx.x % ntiles;
+    float2 *s_x0 = (float2 *)smem_raw;                  // span_max samples (float2 slots also when the samples are real)
+    // bank [npfb][LP]: rows padded to an odd pitch -- a warp's threads read tap i of up to 16 different sub-filters at once,
+    // and with a pitch of 40 floats those rows start on only four distinct banks
+    float  *s_b = (float *)(s_x0 + span_max);
+    const int tid = threadIdx.x, L = p.sublen, LP = p.sublen | 1;
+    // The oscillator's 1024-entry (sin, cos) table in shared memory; the CTAs are persistent (as many as fit at once, each
+    // walking many (channel, tile) work items), so the table and the filter bank are loaded once per CTA
+    float2 *s_tab = (float2 *)(s_b + ((p.npfb * LP + 3) & ~3));
+    __shared__ unsigned long long s_bar;
+    const bool bulk = !REAL && ((((size_t)xv) & 15) == 0) && ((n & 1) == 0);
+    if (bulk && tid == 0) { mbar_init(&s_bar, 1); mbar_init_fence(); }
+    for (int i = tid; i < p.npfb * L; i += NT) s_b[(i / L) * LP + i % L] = p.bank[i];
+    if (HAS_NCO && q.type == 0) for (int i = tid; i < 1024; i += NT) s_tab[i] = q.sincos[i];
+    __syncthreads();
+    unsigned parity = 0;
+    for (long long work = blockIdx.x; work < nwork; work += gridDim.x) {
+    float2 *s_x = s_x0; float *s_xr = (float *)smem_raw;
+    const long long ch = work / ntiles, tile = work % ntiles;
     const long long k0 = tile * KT;
     const int nk = (int)((n_out - k0) < KT ? (n_out - k0) : KT);
     const unsigned long long P0 = (unsigned long long)p.phase + (unsigned long long)k0 * p.step;
@@ -70,8 +83,6 @@ resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, vo
     // Complex rows that are 16-byte aligned arrive as ONE bulk copy (cp.async.bulk, the TMA engine) issued by one thread:
     // the staged origin moves down to an even sample so source and destination are 16-byte aligned; the few samples from
     // before the call (history ring) and an odd last sample are filled in by the threads.
-    const bool bulk = !REAL && ((((size_t)xv) & 15) == 0) && ((n & 1) == 0);
-    __shared__ unsigned long long s_bar;
     if (bulk) {
         if (i_lo >= 0) i_lo &= ~1LL;
         else if ((-i_lo) & 1) s_x += 1;                 // sample 0 of the call lands on an even slot
@@ -79,10 +90,8 @@ resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, vo
     const int span = (int)(i_hi - i_lo + 1);
     const long long gA = i_lo > 0 ? i_lo : 0;           // first sample of this call in the span (even when bulk)
     const int cnt2 = bulk ? (int)((i_hi + 1 - gA) & ~1LL) : 0;
-    if (bulk && tid == 0) { mbar_init(&s_bar, 1); mbar_init_fence(); }
-    for (int i = tid; i < p.npfb * L; i += NT) s_b[i] = p.bank[i];
-    __syncthreads();
     if (bulk && tid == 0 && cnt2 > 0) {
+        fence_async_smem();                             // (the previous work item's generic-proxy writes to the span come first)
         mbar_arrive_expect_tx(&s_bar, (unsigned)cnt2 * 8u);
         bulk_g2s((unsigned)__cvta_generic_to_shared(&s_x[gA - i_lo]), xrow + gA, (unsigned)cnt2 * 8u, &s_bar);
     }
@@ -99,14 +108,14 @@ resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, vo
         }
     }
     cp_async_commit(); cp_async_wait<0>();
-    if (bulk && cnt2 > 0) mbar_wait(&s_bar, 0);
+    if (bulk && cnt2 > 0) { mbar_wait(&s_bar, parity); parity ^= 1u; }
     __syncthreads();
     if (HAS_NCO) {
         // the mixer runs in front of the filter: rotate the staged samples of this call in place (history samples
         // in the ring were rotated by the call that saw them)
         const uint32_t th0 = q.theta[gch], dth = q.dtheta[gch];
         const bool down = q.dir == 2;
-        // the 8 KB oscillator table is read through L1 (copying it into every CTA's shared memory cost a sixth of the staging)
+
         if (q.type == 0) {
             // table oscillator: four samples per thread and pass, so four table reads and four shared loads are in
             // flight together instead of one dependent pair per loop trip
@@ -117,14 +126,14 @@ resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, vo
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const uint32_t th = th0 + (uint32_t)(i_lo + i + u * NT) * dth;
-                    sc[u] = __ldg(&q.sincos[nco_index(th)]); v[u] = s_x[i + u * NT];
+                    sc[u] = s_tab[nco_index(th)]; v[u] = s_x[i + u * NT];
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) s_x[i + u * NT] = down ? mix_down(v[u], sc[u]) : mix_up(v[u], sc[u]);
             }
             for (; i < span; i += NT) {
                 const uint32_t th = th0 + (uint32_t)(i_lo + i) * dth;
-                const float2 sc = __ldg(&q.sincos[nco_index(th)]);
+                const float2 sc = s_tab[nco_index(th)];
                 s_x[i] = down ? mix_down(s_x[i], sc) : mix_up(s_x[i], sc);
             }
         } else {
@@ -140,7 +149,7 @@ resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, vo
         const unsigned long long P = P0 + (unsigned long long)tid * p.step;
         const int off = (int)((long long)(P >> 24) - (L - 1) - i_lo);
         const unsigned f = (unsigned)((P & 0xffffffull) >> (24 - p.bits));
-        const float *h = s_b + f * L;
+        const float *h = s_b + f * LP;
         // dotprod_cccf order and rounding: product rounded, then added, oldest sample first (scalar intrinsics:
         // ptxas contracts a packed mul.f32x2 + add.f32x2 pair into FFMA2 even with .rn)
         float ar = 0.f, ai = 0.f;
@@ -156,6 +165,8 @@ resamp_par_kernel(const ResampP p, const NcoP q, const void *__restrict__ xv, vo
         }
         if (REAL) ((float *)yv)[ch * n_out + k0 + tid] = ar;
         else ((float2 *)yv)[ch * n_out + k0 + tid] = make_float2(ar, ai);
+    }
+    __syncthreads();                                    // the staged span is overwritten by the next work item
     }
 }
 
@@ -273,14 +284,22 @@ cudaError_t resamp_par_launch(const ResampP &p, const NcoP *nco, const void *x, 
         const int span_max = (int)((((unsigned long long)KT * p.step) >> 24) + p.sublen + 3) + 3;
         const long long ntiles = (n_out + KT - 1) / KT;
         if (ntiles * (long long)nch > 0x7fffffffLL) return cudaErrorInvalidValue;
-        const size_t smem = (size_t)span_max * sizeof(float2) + (size_t)((p.npfb * p.sublen + 3) & ~3) * sizeof(float);
+        const size_t smem = (size_t)span_max * sizeof(float2) + (size_t)((p.npfb * (p.sublen | 1) + 3) & ~3) * sizeof(float) + (nco ? 1024 * sizeof(float2) : 0);
         if (smem > 200 * 1024) return cudaErrorInvalidValue;
         auto fn = p.variant == 2 ? resamp_par_kernel<false, 2>
                 : p.variant == 1 ? (nco ? resamp_par_kernel<true, 1> : resamp_par_kernel<false, 1>)
                                  : (nco ? resamp_par_kernel<true, 0> : resamp_par_kernel<false, 0>);
         cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (rc != cudaSuccess) return rc;
-        fn<<<(unsigned)(ntiles * nch), NT, smem, stream>>>(p, q, x, y, ch0, Ctot, n, n_out, KT, (int)ntiles, span_max);
+        // persistent CTAs: as many as are resident at once (shared memory bounds it), each walking the work items with that stride
+        int per_sm = 1;
+        rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, NT, smem);
+        if (rc != cudaSuccess) return rc;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long nwork = ntiles * (long long)nch;
+        const long long resident = (long long)std::max(1, per_sm) * sms;
+        fn<<<(unsigned)std::min(nwork, resident), NT, smem, stream>>>(p, q, x, y, ch0, Ctot, n, n_out, KT, (int)ntiles, span_max, nwork);
         rc = cudaGetLastError();
         if (rc != cudaSuccess) return rc;
     }

@@ -989,3 +989,33 @@ def test_amtail_eight_lane_kernel_equals_thread_per_channel(cuda, monkeypatch):
         outs.append(np.concatenate(ys, axis=1)); words.append(r.am.nco_u32())
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
     assert np.array_equal(words[0][0], words[1][0]) and np.array_equal(words[0][1], words[1][1])
+
+
+@pytest.mark.parametrize("lanes,C,n", [("2", 37, 4098), ("4", 9, 1234), ("8", 3, 530), ("2", 16, 16), ("8", 1, 7)])
+def test_guard_bands_around_device_buffers(cuda, monkeypatch, lanes, C, n):
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted the old way: input, output and
+    nothing else sit between canary bands in one device allocation; ragged shapes (samples not a multiple of the 16-sample
+    tile, channels not a multiple of a warp's share, a last TMA box hanging over both edges) run through the receiver
+    chain by device pointers; the bands must come back untouched and the audio must equal the host-pointer call's."""
+    monkeypatch.setenv("LQB_LANES", lanes)
+    guard = 4096                                              # bytes of canary on each side (16-byte aligned offsets)
+    r = _Radio(L, channels=C); ch = L.Chain(*r.stages())
+    r2 = _Radio(L, channels=C); ch2 = L.Chain(*r2.stages())
+    x = np.stack([am_iq(n, seed=900 + c) for c in range(C)])
+    n_out = ch.out_len(n)
+    xin, yout = C * n * 8, max(16, C * n_out * 4)
+    pad = lambda b: (b + 15) // 16 * 16
+    total = guard + pad(xin) + guard + pad(yout) + guard
+    buf = L.DeviceBuffer(total)
+    host = np.full(total, 0xA5, np.uint8)
+    host[guard:guard + xin] = x.view(np.uint8).ravel()
+    buf.upload(host)
+    px, py = buf.ptr.value + guard, buf.ptr.value + guard + pad(xin) + guard
+    got = ch.execute_dev(px, n, py, n_out, 0); L.synchronize()
+    back = buf.download((total,), np.uint8)
+    assert got == n_out
+    for lo, hi in ((0, guard), (guard + xin, guard + pad(xin) + guard), (guard + pad(xin) + guard + C * n_out * 4, total)):
+        assert np.all(back[lo:hi] == 0xA5), "canary band [%d, %d) was written" % (lo, hi)
+    assert np.array_equal(back[guard:guard + xin], host[guard:guard + xin])          # the input is read-only
+    y = back[guard + pad(xin) + guard:guard + pad(xin) + guard + C * n_out * 4].view(np.float32).reshape(C, n_out)
+    assert np.array_equal(y.view(np.uint32), ch2(x).view(np.uint32))
