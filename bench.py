@@ -179,6 +179,36 @@ def build_radio(L, channels):
     return iir, rs, agc, am, de
 
 
+def pin_to_gpu_numa(local):
+    """Bind this rank's process (and so its page-locked buffers, first-touched after this) to the CPUs NVML reports as local
+    to its GPU.  N ranks streaming 54 GB/s each from host memory otherwise all sit on whatever NUMA node the launcher
+    left them on (round 1: CPU affinity 0-31 / NUMA 0 for all eight) and the far socket's GPUs pull every byte across
+    the inter-socket link.  Returns a small record for the JSON line; never fails the run."""
+    rec = {"cpus_before": None, "cpus": None, "source": None}
+    try:
+        rec["cpus_before"] = len(os.sched_getaffinity(0))
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[local]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(range(os.cpu_count() or 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            rec.update(cpus=len(cpus), first_cpu=min(cpus), last_cpu=max(cpus), source="nvmlDeviceGetCpuAffinity")
+        try:
+            node_mask = pynvml.nvmlDeviceGetMemoryAffinity(h, 4, pynvml.NVML_AFFINITY_SCOPE_NODE)
+            rec["numa_nodes"] = [64 * w + b for w, m in enumerate(node_mask) for b in range(64) if (m >> b) & 1]
+        except Exception:
+            pass
+    except Exception as e:          # no NVML, no permission: run unpinned and say so
+        rec["error"] = repr(e)[:120]
+    return rec
+
+
 def hbm_peak():
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -346,17 +376,19 @@ def e2e_measure(L, torch, np, x_dev, Ce, n, fuse, reps, barrier, max_over_ranks,
         for _ in range(reps):
             y = call(arg)
         L.synchronize()
-        return max_over_ranks(time.perf_counter() - t0) / reps, y
+        own = (time.perf_counter() - t0) / reps
+        return max_over_ranks(own * reps) / reps, y, own
 
-    dt, yh = timed(ch_e, xn, reps)
+    dt, yh, own_pinned = timed(ch_e, xn, reps)
     out = {"value": world * Ce * n / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(xn.nbytes), "d2h_bytes_per_step": int(yh.nbytes),
            "channels_per_gpu": Ce, "ms_per_step": dt * 1e3, "host_memory": "pinned (cudaHostAlloc)",
-           "h2d_gbs_per_gpu": xn.nbytes / dt / 1e9, "api": "liquiddsp.Chain.__call__ -> lqb_chain_execute (host pointers)"}
+           "h2d_gbs_per_gpu": xn.nbytes / dt / 1e9, "own_h2d_gbs": xn.nbytes / own_pinned / 1e9,
+           "api": "liquiddsp.Chain.__call__ -> lqb_chain_execute (host pointers)"}
     # the same call fed the SDR wire format (interleaved int16 I/Q, bytes_to_iq fused into the first kernel)
     ih = torch.empty((Ce, 2 * n), dtype=torch.int16).pin_memory()
     ih.copy_((torch.view_as_real(xh).reshape(Ce, 2 * n) * 32767.0).clamp(-32767, 32767).to(torch.int16))
     inp = ih.numpy()
-    dti, yi = timed(ch_e, inp, reps)
+    dti, yi, _ = timed(ch_e, inp, reps)
     out["int16_iq"] = {"value": world * Ce * n / dti / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(inp.nbytes),
                        "d2h_bytes_per_step": int(yi.nbytes), "ms_per_step": dti * 1e3,
                        "api": "liquiddsp.Chain.__call__(int16 I/Q) -> lqb_chain_execute_i16"}
@@ -365,10 +397,10 @@ def e2e_measure(L, torch, np, x_dev, Ce, n, fuse, reps, barrier, max_over_ranks,
     Cp = min(Ce, 8192)
     xp = np.empty((Cp, n), np.complex64); xp[...] = xn[:Cp]
     ch_p = L.Chain(*build_radio(L, Cp), fuse=fuse)
-    dtp, yp = timed(ch_p, xp, max(2, reps // 2))
+    dtp, yp, own_page = timed(ch_p, xp, max(2, reps // 2))
     out["pageable"] = {"value": world * Cp * n / dtp / 1e6, "unit": UNIT, "channels_per_gpu": Cp, "h2d_bytes_per_step": int(xp.nbytes),
                        "d2h_bytes_per_step": int(yp.nbytes), "ms_per_step": dtp * 1e3, "host_memory": "pageable numpy array",
-                       "h2d_gbs_per_gpu": xp.nbytes / dtp / 1e9}
+                       "h2d_gbs_per_gpu": xp.nbytes / dtp / 1e9, "own_h2d_gbs": xp.nbytes / own_page / 1e9}
     return out
 
 
@@ -445,6 +477,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    numa = pin_to_gpu_numa(local) if os.environ.get("LQB_BENCH_NO_PIN") is None else {"source": "disabled (LQB_BENCH_NO_PIN)"}
     torch.cuda.set_device(local); L.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -531,6 +564,16 @@ def main():
         e2e = e2e_measure(L, torch, np, m["x"], Ce, n, args.fuse, max(2, min(args.steps, 4)), barrier, max_over_ranks, world)
         if Ce != C:
             e2e["note"] = "host memory bounds the e2e share to %d channels per GPU (headline share %d)" % (Ce, C)
+        # every rank's own host -> device rate (the slowest one sets `value`): what tells a saturated host resource from a
+        # badly placed rank
+        mine = torch.tensor([e2e["own_h2d_gbs"], e2e["pageable"]["own_h2d_gbs"], float(numa.get("first_cpu", -1))], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allr, mine)
+        else:
+            allr = [mine]
+        e2e["per_rank"] = [{"rank": i, "pinned_h2d_gbs": round(float(t[0]), 2), "pageable_h2d_gbs": round(float(t[1]), 2), "first_cpu": int(t[2])} for i, t in enumerate(allr)]
+        e2e["host_binding"] = numa
     x_keep = None
     del m["x"], m["chain"], m["stages"]
     torch.cuda.empty_cache()
