@@ -412,7 +412,23 @@ struct AgcStage : lqb_stage_s {
     // only where the planner sees a feed-forward discriminator (FreqDem) and no PLL demodulator downstream.
     int precision = LQB_AGC_AUTO; bool plan_fast = false;
     DevArr<float> g, y2p; DevArr<int> mode; DevArr<unsigned> timer, rise;
+    // few channels: the gain loop runs on this stream, a few hundred samples ahead of the demodulator (run_segment)
+    cudaStream_t ahead = nullptr; cudaEvent_t ev_begin = nullptr, ev_chunk[8] = {};
     AgcStage(int c) : lqb_stage_s(K_AGC, c) {}
+    ~AgcStage() override
+    {
+        if (ahead) { cudaStreamSynchronize(ahead); cudaStreamDestroy(ahead); }
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        for (auto &e : ev_chunk) if (e) cudaEventDestroy(e);
+    }
+    int pipeline_resources()
+    {
+        if (ahead) return LQB_OK;
+        LQB_CUDA(cudaStreamCreateWithFlags(&ahead, cudaStreamNonBlocking));
+        LQB_CUDA(cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming));
+        for (auto &e : ev_chunk) LQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return LQB_OK;
+    }
     int materialize() override
     {
         LQB_TRY(g.alloc(C)); LQB_TRY(y2p.alloc(C)); LQB_TRY(mode.alloc(C)); LQB_TRY(timer.alloc(C)); LQB_TRY(rise.alloc(1));
@@ -784,6 +800,35 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
             if (s->kind == K_AGC) { LQB_TRY(static_cast<AgcStage *>(s)->fill(a.agc)); has_agc = true; }
             else if (s->kind == K_AM) LQB_TRY(static_cast<AmStage *>(s)->fill(a.am));
             else if (s->kind == K_DEEMPH) { static_cast<DeemphStage *>(s)->fill(a.de); has_de = true; }
+        }
+        // Few channels: gain loop and demodulator are each ONE dependent chain per channel with a lone warp per scheduler --
+        // latency, not throughput, and the machine is mostly idle.  So the block is cut along time: the gain loop runs
+        // chunk j + 1 on its own stream while the demodulator works on chunk j (state carries between chunks exactly as
+        // between calls), and the tail takes about max(gain loop, demodulator) instead of their sum.
+        if (has_agc && in_tmajor && nch <= 16384 && n >= 512 && !a.am.suppressed && !getenv("LQB_NO_TAILPIPE")) {
+            AgcStage *ag = nullptr;
+            for (lqb_stage_s *s : g.st) if (s->kind == K_AGC) ag = static_cast<AgcStage *>(s);
+            LQB_TRY(ag->pipeline_resources());
+            const int K = 8;
+            const long long step = (((long long)n + K - 1) / K + 7) / 8 * 8;      // whole groups of the demodulator's eight samples
+            LQB_CUDA(cudaEventRecord(ag->ev_begin, stream));
+            LQB_CUDA(cudaStreamWaitEvent(ag->ahead, ag->ev_begin, 0));
+            int j = 0;
+            for (long long k0 = 0; k0 < (long long)n; k0 += step, j++) {
+                AmTailArgs c = a;
+                c.n = std::min<long long>(step, (long long)n - k0);
+                c.x = a.x + k0 * a.in_pitch; c.y = a.y + k0;
+                c.am.count = (uint32_t)((a.am.count + (unsigned long long)k0) % kAmRing);
+                LQB_CUDA(agc_tmajor_launch(c, ag->ahead));
+                LQB_CUDA(cudaEventRecord(ag->ev_chunk[j], ag->ahead));
+                LQB_CUDA(cudaStreamWaitEvent(stream, ag->ev_chunk[j], 0));
+                LQB_CUDA(amtail_launch(false, has_de, c, stream));
+                (*launches) += 2;
+            }
+            (*launches)--;
+            note_kernel(kn, "agc_tmajor_kernel(x" + std::to_string(j) + ", ahead)");
+            note_kernel(kn, std::string(amtail_few(false, a) ? "amtail8_kernel" : "amtail_kernel") + "(x" + std::to_string(j) + ")");
+            return LQB_OK;
         }
         LQB_CUDA(amtail_launch(has_agc, has_de, a, stream));
         if (amtail_launch_count(has_agc, a) > 1) note_kernel(kn, "agc_tmajor_kernel");

@@ -400,9 +400,11 @@ Pick pick(int nsos, int lanes, bool full)
     }
     return Pick{ nullptr, 0, 0 };
 }
-// four warps per CTA (one per scheduler) and the shallow ring once the warps cover every scheduler several times;
+// four warps per CTA (one per scheduler) and the shallow ring once the warps cover every scheduler;
 // otherwise single-warp CTAs spread the channels over as many SMs as possible, each with a deep ring
-bool full_machine(long long nch, int lanes) { return lanes == 2 && (nch + 15) / 16 >= 148 * 4 * 5; }
+// (the deep variant holds 32 KB of shared memory per warp: six warps per SM.  From 888 warps on -- 14208 channels -- it would
+// need a second wave, so everything above runs the shallow variant, 6 KB per warp)
+bool full_machine(long long nch, int lanes) { return lanes == 2 && (nch + 15) / 16 > 148 * 6; }
 
 }  // namespace
 

@@ -709,9 +709,12 @@ def test_fused_chain_matches_stagewise(cuda, fuse):
     ys, yc = [], []
     for i in range(0, n, blk):
         ys.append(a(x[i:i + blk])); yc.append(chain(x[i:i + blk]))
-        assert chain.last_launches() == expect
         if fuse == 1:                        # the library names what it dispatched (lqb_chain_last_kernels)
-            assert chain.last_kernels() == ["tapstream_kernel", "lanes_kernel<1,4>", "agc_tmajor_kernel", "amtail8_kernel"]     # one channel: 4 lane pairs
+            k = chain.last_kernels()         # one channel: 4 lane pairs; long blocks run the gain loop ahead of the demodulator in 8 chunks
+            assert k[:2] == ["tapstream_kernel", "lanes_kernel<1,4>"] and k[2].startswith("agc_tmajor_kernel") and k[3].startswith("amtail8_kernel")
+            assert chain.last_launches() == (18 if "x8" in k[2] else expect)
+        else:
+            assert chain.last_launches() == expect
     ys, yc = np.concatenate(ys), np.concatenate(yc)
     assert np.array_equal(ys.view(np.uint32), yc.view(np.uint32)), rel_l2(yc, ys)
     assert b.resample.state() == a.resample.state()
