@@ -1324,11 +1324,16 @@ unsigned orc_wrap_fmstereo_execute(orc_fmstereo q, const orc_cf *x, unsigned n, 
         orc_nco_mix_down(q->mixer, sc, &sc);                                  /* and once more */
         orc_nco_pll_step(q->mixer, q->phase_error);
         orc_nco_step(q->mixer);
-        float left, right; orc_cf ol[4], orr[4]; unsigned nl, nr;
+        float left, right; orc_cf ol[256], orr[256]; unsigned nl, nr;      /* (liquid bounds the rate by 250) */
         orc_iirfilt_rrrf_execute(q->emphL, s + sc.re, &left);
         orc_iirfilt_rrrf_execute(q->emphR, s - sc.re, &right);
-        orc_cf li = { left, 0.0f }, ri = { right, 0.0f };
+        orc_cf li = { left, 0.0f };
         orc_resamp_execute(q->audioL, li, ol, &nl);
+        /* demod_one (:79-83) hands the resamplers left = &y[nw] and right = &y[nw + 1] as both input and output: when the
+         * left resampler yields two or more samples (pcm_rate > iq_rate) its second one lands on *right before the right
+         * resampler reads it.  Such steps are dropped by execute() (nl + nr != 2), but the right resampler's window keeps
+         * the overwritten value. */
+        orc_cf ri = { nl >= 2 ? ol[1].re : right, 0.0f };
         orc_resamp_execute(q->audioR, ri, orr, &nr);
         if (nl + nr == 2) { y[nw] = ol[0].re; y[nw + 1] = orr[0].re; nw += 2; }   /* execute(), :45-48 */
     }

@@ -531,17 +531,29 @@ struct FmstStage : lqb_stage_s {
     // FMStereo::reset (demod.hpp:35-38) resets the two resamplers and nothing else
     void host_reset() override { phase = 0; count = 0; }
     int clear() override { LQB_TRY(ringL.zero()); return ringR.zero(); }
-    size_t pairs(size_t n) const
+    // resampler outputs over n input samples: all of them (rate <= 1: at most one per input, every one a kept pair), and for
+    // pcm_rate > iq_rate the inputs that yield exactly one -- the only pairs FMStereo::execute keeps (demod.hpp:45-48)
+    void walk(size_t n, uint64_t *total, uint64_t *kept) const
     {
         const uint64_t lim = ((uint64_t)n << 24);
-        if (n == 0 || (uint64_t)phase > lim - 1) return 0;
-        return (size_t)((lim - 1 - phase) / step + 1);
+        *total = (n == 0 || (uint64_t)phase > lim - 1) ? 0 : (lim - 1 - phase) / step + 1;
+        *kept = *total;
+        if (step < (1u << 24)) {
+            uint64_t k = 0; uint32_t ph = phase;
+            for (size_t i = 0; i < n; i++) {
+                unsigned nl = 0;
+                while (ph <= 0x00ffffffu) { nl++; ph += step; }
+                ph -= (1u << 24);
+                if (nl == 1) k++;
+            }
+            *kept = k;
+        }
     }
-    size_t out_len(size_t n) const override { return 2 * pairs(n); }
+    size_t out_len(size_t n) const override { uint64_t t, k; walk(n, &t, &k); return (size_t)(2 * k); }
     void advance(size_t n) override
     {
-        const uint64_t k = pairs(n);
-        phase = (uint32_t)((uint64_t)phase + k * step - ((uint64_t)n << 24));
+        uint64_t t, k; walk(n, &t, &k);
+        phase = (uint32_t)((uint64_t)phase + t * step - ((uint64_t)n << 24));
         count = (uint32_t)((count + n) % d.sublen);
     }
     int fill(FmstP &p) const
@@ -1745,8 +1757,7 @@ int lqb_fmstereo_create(float iq_rate, float pcm_rate, int C, lqb_stage *out)
     LQB_TRY(check_channels(C));
     if (!out || !(iq_rate > 0.f) || !(pcm_rate > 0.f)) return fail(LQB_EINVAL, "FMStereo: rates must be positive");
     const float rate = pcm_rate / iq_rate;
-    if (rate > 1.0f) return fail(LQB_ENOTIMPL, "FMStereo: pcm_rate above iq_rate (the reference keeps an output pair only when each resampler yields exactly one sample)");
-    if (rate < 0.004f) return fail(LQB_EINVAL, "FMStereo: pcm_rate / iq_rate %g below 0.004", rate);
+    if (!(rate >= 0.004f && rate <= 250.f)) return fail(LQB_EINVAL, "FMStereo: pcm_rate / iq_rate %g outside [0.004, 250] (resamp_rrrf_create_default)", rate);
     FmstStage *q = new FmstStage(C);
     // demod.hpp:20-32: 75 us de-emphasis at the I/Q rate, freqdem(4.0), resamp_rrrf_create_default(pcm_rate / iq_rate)
     const float a1 = (float)(-std::exp(-1.0 / (75.0E-6 * (double)iq_rate)));

@@ -18,6 +18,7 @@ namespace {
 
 constexpr int BT = 64, TS = 16, PITCH = TS * 8 + 16;     // 144-byte rows: conflict-free per-lane LDS.128
 
+template <bool UP>
 __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ FmstArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -113,20 +114,38 @@ __global__ void __launch_bounds__(BT) fmstereo_kernel(const __grid_constant__ Fm
             // de-emphasis (iirfilt_rrrf, b = [b0], a = [1, a1]) of the sum and the difference
             vL = __fmaf_rn(-a.p.a1, vL, __fadd_rn(s, sc.x)); const float left  = __fmaf_rn(a.p.b0, vL, 0.f);
             vR = __fmaf_rn(-a.p.a1, vR, __fsub_rn(s, sc.x)); const float right = __fmaf_rn(a.p.b0, vR, 0.f);
-            // resamp_rrrf_execute on both: push, then one output while the phase is inside this sample
-            s_L[slot * BT + myrow] = left; s_R[slot * BT + myrow] = right;
+            // resamp_rrrf_execute on both: push, then one output for every phase position inside this sample
+            auto dot = [&](const float *win, uint32_t ph) -> float {
+                const float *h = s_b + (ph >> (24 - a.p.rs.bits)) * L;
+                float acc = 0.f;
+                int q = slot;                                      // oldest sample first (slot already points past the newest)
+                for (int i = 0; i < L; i++) { acc = __fmaf_rn(h[i], win[q * BT + myrow], acc); q = q + 1 == L ? 0 : q + 1; }
+                return acc;
+            };
+            const int here = slot;
             slot = slot + 1 == L ? 0 : slot + 1;
-            if (phase <= 0x00ffffffu) {                            // rate <= 1: at most one output per input
-                const float *h = s_b + (phase >> (24 - a.p.rs.bits)) * L;
-                float aL = 0.f, aR = 0.f;
-                int q = slot;                                      // oldest sample first
-                for (int i = 0; i < L; i++) {
-                    aL = __fmaf_rn(h[i], s_L[q * BT + myrow], aL); aR = __fmaf_rn(h[i], s_R[q * BT + myrow], aR);
-                    q = q + 1 == L ? 0 : q + 1;
+            s_L[here * BT + myrow] = left;
+            if constexpr (!UP) {
+                s_R[here * BT + myrow] = right;
+                if (phase <= 0x00ffffffu) {                        // rate <= 1: at most one output per input
+                    const float aL = dot(s_L, phase), aR = dot(s_R, phase);
+                    if (active) *(float2 *)(yrow + 2 * kout) = make_float2(aL, aR);
+                    kout++;
+                    phase += a.p.rs.step;
                 }
-                if (active) *(float2 *)(yrow + 2 * kout) = make_float2(aL, aR);
-                kout++;
-                phase += a.p.rs.step;
+            } else {
+                // pcm_rate > iq_rate: a sample can yield several outputs.  demod_one (demod.hpp:79-83) passes &y[nw] and
+                // &y[nw + 1] to the resamplers as input AND output, so the left resampler's second output overwrites the right
+                // resampler's input before it is read, and execute() (:45-48) keeps a pair only when each yields exactly one.
+                int nl = 0; uint32_t ph = phase;
+                while (ph <= 0x00ffffffu) { nl++; ph += a.p.rs.step; }             // (the same for every channel)
+                s_R[here * BT + myrow] = nl >= 2 ? dot(s_L, phase + a.p.rs.step) : right;
+                if (nl == 1) {
+                    const float aL = dot(s_L, phase), aR = dot(s_R, phase);
+                    if (active) *(float2 *)(yrow + 2 * kout) = make_float2(aL, aR);
+                    kout++;
+                }
+                phase = ph;
             }
             phase -= (1u << 24);
         }
@@ -146,14 +165,15 @@ cudaError_t fmstereo_launch(const FmstArgs &a, cudaStream_t stream)
 {
     if (a.C <= 0 || a.n <= 0) return cudaSuccess;
     const int L = a.p.rs.sublen;
-    if (L < 1 || L > kFmstMaxSub || a.p.rs.step < (1u << 24)) return cudaErrorInvalidValue;
+    if (L < 1 || L > kFmstMaxSub || a.p.rs.step == 0) return cudaErrorInvalidValue;
     const size_t smem = (size_t)2 * BT * PITCH + (size_t)2 * L * BT * sizeof(float) + (size_t)((a.p.rs.npfb * L + 3) & ~3) * sizeof(float)
                       + 1024 * sizeof(float) + 65 * kAtanPitch * sizeof(double);
-    cudaError_t rc = cudaFuncSetAttribute((const void *)fmstereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void (*fn)(const FmstArgs) = a.p.rs.step < (1u << 24) ? fmstereo_kernel<true> : fmstereo_kernel<false>;
+    cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     if (a.cpw != 8 && a.cpw != 16 && a.cpw != 32) return cudaErrorInvalidValue;
     const int rc_cta = (BT / 32) * a.cpw;
-    fmstereo_kernel<<<(unsigned)((a.C + rc_cta - 1) / rc_cta), BT, smem, stream>>>(a);
+    fn<<<(unsigned)((a.C + rc_cta - 1) / rc_cta), BT, smem, stream>>>(a);
     return cudaGetLastError();
 }
 

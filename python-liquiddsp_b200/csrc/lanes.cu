@@ -28,7 +28,7 @@
 //
 // Staging: one elected lane per warp issues one cp.async.bulk.tensor.2d per tile for the warp's [rows x 128 B] box
 // (128-byte swizzle, per-warp mbarrier ring: 3 deep when the machine is full, 8 deep when few warps must keep the HBM
-// pipe busy) plus one 144-byte record of everything that is the same for all channels (tap stream, below).  Warps never
+// pipe busy) plus one 208-byte record of everything that is the same for all channels (tap stream, below).  Warps never
 // wait for each other: no CTA barrier anywhere.
 #include <cuda_runtime.h>
 #include <cuda.h>
@@ -48,16 +48,17 @@ constexpr int DX = 4;                              // slots of the hand-off ring
 
 // What is the same for every channel -- which polyphase tap multiplies a sample, whether the dot product restarts on it,
 // where in a tile an output falls -- is worked out once per call by tapstream_kernel (closed form of liquid's uint32 phase
-// recurrence) and reaches each warp as one 144-byte record per tile, copied by the same mbarrier transaction as the tile.
+// recurrence) and reaches each warp as one 208-byte record per tile, copied by the same mbarrier transaction as the tile.
 // Records are in STEP space: slot j of record t belongs to step k = 16 t + j, i.e. to sample k - lag of the last section.
 struct TileRec {
     float tap[TS];                                 // tap that multiplies the sample (0 outside every window and outside the call)
     float keep[TS];                                // 0 on the sample after an output (the accumulator restarts), else 1
+    float cap[TS];                                 // 1 on the step an output falls on, else 0 (out = cap * acc + out: one FFMA instead of compare + select)
     int emit;                                      // step of the tile an output falls on, or -1 (step >= TS * 2^24: at most one)
     int gen;                                       // 1 when the tile holds an output or a restart, 0: plain accumulation
     int pad[2];
 };
-static_assert(sizeof(TileRec) == 144, "tile records are copied 16 bytes at a time");
+static_assert(sizeof(TileRec) == 208, "tile records are copied 16 bytes at a time");
 // a stage of the ring = TPS consecutive tiles under ONE mbarrier (TPS tensor boxes + one copy of their TPS records): with
 // few channels the per-stage bookkeeping (barrier wait, TMA issue) is what a lone warp cannot hide, so it is paid once
 // per 64 samples there; the full machine stages single tiles (shared memory limits it to three 2 KB stages per warp)
@@ -102,7 +103,7 @@ __global__ void tapstream_kernel(ResampP rs, long long N, int lag, TileRec *out)
     const bool restart = in_call && !(P < step - (1ull << 24) || n == 0);
     TileRec &r = out[k / TS];
     const int j = (int)(k % TS);
-    r.tap[j] = h; r.keep[j] = restart ? 0.f : 1.f;
+    r.tap[j] = h; r.keep[j] = restart ? 0.f : 1.f; r.cap[j] = emit ? 1.f : 0.f;
     const unsigned half = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;     // (TS == 16: one half-warp per tile)
     const unsigned m = __ballot_sync(0xffffffffu, emit) & half, rr = __ballot_sync(0xffffffffu, restart) & half;
     if (j == 0) { r.emit = m ? (__ffs(m) - 1) & 15 : -1; r.gen = (m | rr) ? 1 : 0; r.pad[0] = r.pad[1] = 0; }
@@ -154,11 +155,11 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
         v2[i] = ((const float *)(a.iir.v + (2 * s + 1) * CT + gch))[comp];
         if constexpr (G > 1) { cna1[i] = -a.iir.a[s][1]; cna2[i] = -a.iir.a[s][2]; cb0[i] = a.iir.b[s][0]; cb1[i] = a.iir.b[s][1]; cb2[i] = a.iir.b[s][2]; }
     }
-    auto NA1 = [&](int i) -> float { if constexpr (G == 1) return -a.iir.a[i][1]; else return cna1[i]; };
-    auto NA2 = [&](int i) -> float { if constexpr (G == 1) return -a.iir.a[i][2]; else return cna2[i]; };
-    auto B0 = [&](int i) -> float { if constexpr (G == 1) return a.iir.b[i][0]; else return cb0[i]; };
-    auto B1 = [&](int i) -> float { if constexpr (G == 1) return a.iir.b[i][1]; else return cb1[i]; };
-    auto B2 = [&](int i) -> float { if constexpr (G == 1) return a.iir.b[i][2]; else return cb2[i]; };
+    auto NA1 = [&](int i) -> float { if constexpr (G == 1) return a.lc[i]; else return cna1[i]; };
+    auto NA2 = [&](int i) -> float { if constexpr (G == 1) return a.lc[4 + i]; else return cna2[i]; };
+    auto B1 = [&](int i) -> float { if constexpr (G == 1) return a.lc[8 + i]; else return cb1[i]; };
+    auto B0 = [&](int i) -> float { if constexpr (G == 1) return a.lc[12 + i]; else return cb0[i]; };
+    auto B2 = [&](int i) -> float { if constexpr (G == 1) return a.lc[16 + i]; else return cb2[i]; };
     const int L = a.rs.sublen;
     if (lane == 0) { for (int i = 0; i < NST; i++) mbar_init(&ws.bar[i], 1); mbar_init_fence(); }     // (each warp owns its barriers)
     __syncwarp();
@@ -184,43 +185,58 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
     const int ntx = (int)((N + TS - 1) / TS);                           // tiles that hold samples (2 N fits an int32 tensor-map coordinate)
     const int ntiles = (int)((N + LAG_RS + TS - 1) / TS);               // tiles of steps: the pipeline drains LAG_RS steps past the call
     const int nstg = (ntiles + TPS - 1) / TPS;                          // stages of the call (the tap stream is padded to whole stages)
-    auto load_stage = [&](int sg, int stage) {
+    auto load_stage = [&](int sg, int stage, unsigned soff) {
         if (elect_one()) {
             const int t0 = sg * TPS;
             const int nb = ntx - t0 < TPS ? (ntx - t0 > 0 ? ntx - t0 : 0) : TPS;       // tiles of the stage that hold samples
             mbar_arrive_expect_tx(&ws.bar[stage], (unsigned)nb * WT + (unsigned)(TPS * sizeof(TileRec)));
 #pragma unroll
             for (int q = 0; q < TPS; q++)
-                if (q < nb) tma_load_2d(tile_sh + stage * STB + q * WTA, &a.tmap, (t0 + q) * (TS * 2), irow0, &ws.bar[stage]);
+                if (q < nb) tma_load_2d(tile_sh + soff + q * WTA, &a.tmap, (t0 + q) * (TS * 2), irow0, &ws.bar[stage]);
             bulk_g2s(rec_sh + stage * (unsigned)(TPS * sizeof(TileRec)), recs + t0, (unsigned)(TPS * sizeof(TileRec)), &ws.bar[stage]);
         }
     };
 
-    int kout = 0;
-    float *yf = (float *)a.y;
+    // where this lane's next output goes: a running pointer (one 64-bit add per output instead of an index product); the
+    // stride and the write flag are pinned in registers (ptxas otherwise rebuilds both from the constant bank at every output)
+    float *yp = (float *)a.y + 2 * (a.out_tmajor ? chl : chl * a.out_pitch) + comp;
+    unsigned ystride = (unsigned)(a.out_tmajor ? 8 * a.out_pitch : 8);          // bytes (a time-major row is C * 8 bytes < 4 GB)
+    unsigned writer = (act && last_grp) ? 1u : 0u;
+    asm volatile("" : "+r"(ystride), "+r"(writer));
     auto emit_out = [&](float v) {
-        if (act && last_grp) {
-            const long long o = a.out_tmajor ? (long long)kout * a.out_pitch + chl : chl * a.out_pitch + kout;
-            yf[2 * o + comp] = v;
-        }
+        if (writer) *yp = v;
+        yp = (float *)((char *)yp + ystride);
     };
     // byte address of this lane's component of sample j within its row: 16-byte chunks are permuted by the row's address
     // bits 7..9 under the 128-byte swizzle (rows are 128-byte aligned, so the permuted chunk is an XOR on address bits 4..6)
     unsigned rowbase = tile_sh + c * ROWB + comp * 4;
     rowbase += ((rowbase >> 7) & 7u) << 4;
-    asm volatile("" : "+r"(rowbase));                                   // (kept in its register: ptxas otherwise rebuilds it from %tid every tile)
-    auto ldx = [&](unsigned rowp, int j) -> float {
+    // the eight chunk addresses of the row, kept in registers for the whole call: a load is then [register + stage offset
+    // (uniform) + immediate] with no per-tile address arithmetic (stage offsets are multiples of 1 KB, so they commute with the XOR)
+    unsigned xr[8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) { xr[m] = rowbase ^ ((unsigned)m << 4); asm volatile("" : "+r"(xr[m])); }
+    auto ldx = [&](unsigned soff, auto jc) -> float {
+        constexpr int j = decltype(jc)::value;
         float v;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((rowp ^ (((unsigned)j >> 1) << 4)) + (unsigned)(j & 1) * 8u) : "memory");
+        if (j & 1) asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(v) : "r"(xr[j >> 1] + soff) : "memory");
+        else       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xr[j >> 1] + soff) : "memory");
+        return v;
+    };
+    auto ldx_dyn = [&](unsigned soff, int j) -> float {                 // (the call's first and last tiles)
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(((rowbase + soff) ^ (((unsigned)j >> 1) << 4)) + (unsigned)(j & 1) * 8u) : "memory");
         return v;
     };
 
     // pipeline registers: sv* = what stage A left for stage B of the same section; h[i] = output of local section i for
     // section i + 1; hx[slot] = ring towards the next lane pair; ylp = last section's output for the resampler
     // upf[slot] = the previous lane pair's output fetched two steps ahead of its use (the shuffle's latency off the step)
-    float sv0[SPL], sv1[SPL], sv2[SPL], h[SPL], hx[DX], upf[2] = { 0.f, 0.f }, ylp = 0.f;
+    // (stage B reads v1 / v2 themselves for the two newer delay elements: after a committed stage A they are exactly what it
+    // left behind -- v0 and the old v1 -- and after an uncommitted one the sample is outside the call and its output unused)
+    float sv2[SPL], h[SPL], hx[DX], upf[2] = { 0.f, 0.f }, ylp = 0.f;
 #pragma unroll
-    for (int i = 0; i < SPL; i++) { sv0[i] = sv1[i] = sv2[i] = h[i] = 0.f; }
+    for (int i = 0; i < SPL; i++) { sv2[i] = h[i] = 0.f; }
 #pragma unroll
     for (int i = 0; i < DX; i++) hx[i] = 0.f;
 
@@ -228,8 +244,8 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
     // tap / keep: the tile record's entries of this step; PRED: stages commit only inside the call (first and last
     // tiles), GEN: the accumulator may restart and an output may fall on this step.
     float outv = 0.f;
-    auto step = [&](auto slotc, auto predc, auto genc, float x, float tap, float keep, int e, long long k) {
-        constexpr int SLOT = decltype(slotc)::value;
+    auto step = [&](auto slotc, auto predc, auto genc, float x, float tap, float keep, float cap, int e, long long k) {
+        [[maybe_unused]] constexpr int SLOT = decltype(slotc)::value;
         constexpr bool PRED = decltype(predc)::value, GEN = decltype(genc)::value;
         float in[SPL], tt[SPL], v0[SPL], y[SPL];
         if constexpr (G > 1) {
@@ -245,13 +261,13 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
 #pragma unroll
         for (int i = SPL - 1; i >= 0; i--) tt[i] = __fmaf_rn(NA1(i), v1[i], in[i]);
 #pragma unroll
-        for (int i = SPL - 1; i >= 0; i--) y[i] = __fmul_rn(B1(i), sv1[i]);
+        for (int i = SPL - 1; i >= 0; i--) y[i] = __fmul_rn(B1(i), v2[i]);
         const float p = __fmul_rn(tap, ylp);
         // level 2
 #pragma unroll
         for (int i = SPL - 1; i >= 0; i--) v0[i] = __fmaf_rn(NA2(i), v2[i], tt[i]);
 #pragma unroll
-        for (int i = SPL - 1; i >= 0; i--) y[i] = __fmaf_rn(B0(i), sv0[i], y[i]);
+        for (int i = SPL - 1; i >= 0; i--) y[i] = __fmaf_rn(B0(i), v1[i], y[i]);
         // acc = acc*keep + round(tap*y): the two roundings of liquid's complex-tap dot product; tiles in which no output
         // falls and no dot product restarts (most of them) accumulate with FMUL + FADD
         bool rs_on = true;
@@ -262,15 +278,16 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
         if constexpr (PRED) {
             const long long nl = k - LAG_RS;
             if (rs_on && nl >= N - L && act && last_grp) ((float *)(a.rs.ring + (int)((a.rs.count + nl) % L) * CT + gch))[comp] = ylp;
-            if (rs_on && (int)(k & (TS - 1)) == e) { emit_out(acc); kout++; }                 // (tiles start on multiples of TS)
+            if (rs_on && (int)(k & (TS - 1)) == e) emit_out(acc);                 // (tiles start on multiples of TS)
         } else if constexpr (GEN) {
-            if (SLOT == e) outv = acc;
+            // the output falls on the step whose cap is 1: 1 * acc + 0 is acc exactly (acc is never -0: sums start from +0)
+            outv = __fmaf_rn(cap, acc, outv);
         }
         // level 3, then the hand-overs
 #pragma unroll
         for (int i = SPL - 1; i >= 0; i--) {
             y[i] = __fmaf_rn(B2(i), sv2[i], y[i]);
-            sv0[i] = v0[i]; sv1[i] = v1[i]; sv2[i] = v2[i];
+            sv2[i] = v2[i];
             bool commit = true;
             if constexpr (PRED) { const long long n = k - (g * LAGG + 2 * i); commit = n >= 0 && n < N; }
             if (commit) { v2[i] = v1[i]; v1[i] = v0[i]; }
@@ -284,17 +301,14 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
     // fast tiles: every stage inside the call for all 16 steps and no history-ring save
     const long long lim = (N - L + LAG_RS) < N ? (N - L + LAG_RS) : N;
     const int tfast0 = (LAG_RS + TS - 1) / TS, tfast1 = lim > 0 ? (int)(lim / TS) : 0;
-    for (int p = 0; p < NST - 1; p++) if (p < nstg) load_stage(p, p);
+    const unsigned tfast_n = tfast1 > tfast0 ? (unsigned)(tfast1 - tfast0) : 0u;       // fast tiles: one unsigned compare per tile
+    for (int p = 0; p < NST; p++) if (p < nstg) load_stage(p, p, (unsigned)(p * STB));
     int stage = 0; unsigned parity = 0;                                 // every barrier of the ring completes once per lap
+    unsigned soff = 0;                                                  // byte offset of the stage within the warp's ring (running: no multiply per tile)
     bool ready = false;
 #pragma unroll 1
     for (int sg = 0; sg < nstg; sg++) {
-        if (!ready) mbar_wait(&ws.bar[stage], parity);
-        __syncwarp();                              // stage sg has landed; every lane is done with stage sg-1
-        {
-            const int sn = stage == 0 ? NST - 1 : stage - 1;
-            if (sg + NST - 1 < nstg) load_stage(sg + NST - 1, sn);
-        }
+        if (!ready) mbar_wait(&ws.bar[stage], parity);                  // stage sg has landed (each lane sees the phase flip itself)
         // probe the next stage's barrier now: the answer is needed only after this stage's arithmetic (one vote makes it
         // warp-uniform, so the loop's bookkeeping stays in uniform registers)
         const int stage_n = stage + 1 == NST ? 0 : stage + 1;
@@ -307,41 +321,43 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
         for (int q = 0; q < TPS; q++) {
         const int t = sg * TPS + q;
         if (t >= ntiles) break;
-        const unsigned rowp = rowbase + stage * STB + q * WTA;
+        const unsigned rowp = soff + (unsigned)(q * WTA);                   // (uniform) offset of the tile within the warp's ring
         const TileRec &rec = ws.rec[stage][q];
         const int e = flags_nx ? e_nx : rec.emit, gen = flags_nx ? gen_nx : rec.gen;
         if constexpr (TPS > 1) {
             flags_nx = q + 1 < TPS;
             if (flags_nx) { const int2 f = *(const int2 *)&ws.rec[stage][q + 1].emit; e_nx = f.x; gen_nx = f.y; }
         }
-        if (t >= tfast0 && t < tfast1) {
+        if ((unsigned)(t - tfast0) < tfast_n) {
             auto body = [&](auto general) {
                 constexpr bool GEN = decltype(general)::value;
                 float xs[TS];
                 if (G == 1 || first_grp) {
-#pragma unroll
-                    for (int j = 0; j < TS; j++) xs[j] = ldx(rowp, j);
+                    static_for<TS>([&](auto jc) { xs[decltype(jc)::value] = ldx(rowp, jc); });
                 } else {
 #pragma unroll
                     for (int j = 0; j < TS; j++) xs[j] = 0.f;
                 }
-                float tp[TS], kp[TS];
+                float tp[TS], kp[TS], cp[TS];
 #pragma unroll
                 for (int j = 0; j < TS; j += 4) {
                     const float4 q4 = *(const float4 *)&rec.tap[j];
                     tp[j] = q4.x; tp[j + 1] = q4.y; tp[j + 2] = q4.z; tp[j + 3] = q4.w;
                     if constexpr (GEN) {
-                        const float4 w = *(const float4 *)&rec.keep[j];
+                        const float4 w = *(const float4 *)&rec.keep[j], u = *(const float4 *)&rec.cap[j];
                         kp[j] = w.x; kp[j + 1] = w.y; kp[j + 2] = w.z; kp[j + 3] = w.w;
+                        cp[j] = u.x; cp[j + 1] = u.y; cp[j + 2] = u.z; cp[j + 3] = u.w;
                     } else {
                         kp[j] = kp[j + 1] = kp[j + 2] = kp[j + 3] = 1.f;
+                        cp[j] = cp[j + 1] = cp[j + 2] = cp[j + 3] = 0.f;
                     }
                 }
+                if constexpr (GEN) outv = 0.f;
                 static_for<TS>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    step(jc, std::false_type{}, general, xs[j], tp[j], kp[j], e, 0);
+                    step(jc, std::false_type{}, general, xs[j], tp[j], kp[j], cp[j], e, 0);
                 });
-                if constexpr (GEN) { if (e >= 0) { emit_out(outv); kout++; } }
+                if constexpr (GEN) { if (e >= 0) emit_out(outv); }
             };
             if (gen) body(std::true_type{}); else body(std::false_type{});
         } else {
@@ -353,15 +369,20 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
                 static_for<DX>([&](auto jc) {
                     const int j = jo + decltype(jc)::value;
                     const long long k = k0 + j;
-                    const float x = (k < N && (G == 1 || first_grp)) ? ldx(rowp, j) : 0.f;
-                    step(jc, std::true_type{}, std::true_type{}, x, rec.tap[j], rec.keep[j], e, k);
+                    const float x = (k < N && (G == 1 || first_grp)) ? ldx_dyn(rowp, j) : 0.f;
+                    step(jc, std::true_type{}, std::true_type{}, x, rec.tap[j], rec.keep[j], 0.f, e, k);
                 });
             }
         }
         }
         // (the vote makes the probe's answer warp-uniform; taken here, after the stage's arithmetic, so that nothing waits for it)
         if constexpr (TPS > 1) ready = __all_sync(0xffffffffu, probe) != 0;
-        if (++stage == NST) { stage = 0; parity ^= 1u; }
+        // every lane is done with this stage: refill it with the stage NST ahead (the stage's own addresses are at hand, so the
+        // refill costs no index arithmetic; NST - 1 stages stay in flight while the next one is worked on)
+        __syncwarp();
+        if (sg + NST < nstg) load_stage(sg + NST, stage, soff);
+        soff += STB;
+        if (++stage == NST) { stage = 0; parity ^= 1u; soff = 0; }
     }
 
     // ---- carried state back to HBM ----
@@ -440,8 +461,14 @@ cudaError_t lanes_tapstream_launch(const ResampP &rs, long long n, int lag, void
     return cudaGetLastError();
 }
 
-cudaError_t lanes_launch(int nsos, int lanes, const SeqArgs &a, cudaStream_t stream)
+cudaError_t lanes_launch(int nsos, int lanes, const SeqArgs &a0, cudaStream_t stream)
 {
+    SeqArgs a = a0;
+    for (int i = 0; i < 4; i++) {
+        const bool on = i < nsos;
+        a.lc[i] = on ? -a.iir.a[i][1] : 0.f; a.lc[4 + i] = on ? -a.iir.a[i][2] : 0.f;
+        a.lc[8 + i] = on ? a.iir.b[i][1] : 0.f; a.lc[12 + i] = on ? a.iir.b[i][0] : 0.f; a.lc[16 + i] = on ? a.iir.b[i][2] : 0.f;
+    }
     if (!a.tapstream) return cudaErrorInvalidValue;
     if (a.C <= 0 || a.n <= 0) return cudaSuccess;
     const bool full = full_machine(a.C, lanes);

@@ -76,8 +76,11 @@ def test_reference_api_surface():
     assert sig(L.FMStereo) == dict(iq_rate=600000.0, pcm_rate=48000.0)
     assert L.FMStereo().deemph() == O.FMStereo().deemph() and L.FMStereo().out_len(600000) == 96000
     assert L.FMStereo(240000.0, 44100.0).deemph() == O.FMStereo(240000.0, 44100.0).deemph()
-    with pytest.raises(NotImplementedError):
-        L.FMStereo(48000.0, 96000.0)
+    # pcm_rate > iq_rate: pairs only where the resamplers yield exactly one sample each (demod.hpp:45-48): a rate in (1, 2)
+    # keeps 2 - rate of the inputs, from 2 on nothing
+    assert L.FMStereo(48000.0, 96000.0).out_len(1000) == 0 and L.FMStereo(48000.0, 60000.0).out_len(4000) == 2 * 3000
+    x = np.exp(2j * np.pi * np.cumsum(0.05 * np.sin(0.01 * np.arange(4000)))).astype(np.complex64)
+    assert O.FMStereo(48000.0, 60000.0)(x).size == 2 * 3000 and O.FMStereo(48000.0, 96000.0)(x).size == 0
     assert sig(L.BroadcastAM) == dict(slen=25) and sig(L.SSBDemod) == dict(band=inspect._empty)
     assert sig(L.HilbertTransform) == dict(m=5, As=60.0)
     assert np.array_equal(L.SSBDemod("usb").hq(), O.SSBDemod("usb").hq()) and L.SSBDemod("anything").usb is False

@@ -279,7 +279,10 @@ def test_delay(cuda, nd):
     assert np.array_equal(yb, ref)
 
 
-@pytest.mark.parametrize("iq_rate,pcm_rate,n", [(600000.0, 48000.0, 60000), (240000.0, 44100.0, 20001), (96000.0, 96000.0, 3000)])
+# pcm_rate > iq_rate (demod.hpp:17-32 takes any ratio): pairs survive only where each resampler yields exactly one sample, and
+# the right resampler reads the left one's second output where it yields two (demod.hpp:79-83, the shared y[] slots)
+@pytest.mark.parametrize("iq_rate,pcm_rate,n", [(600000.0, 48000.0, 60000), (240000.0, 44100.0, 20001), (96000.0, 96000.0, 3000),
+                                                (48000.0, 60000.0, 6001), (44100.0, 48000.0, 5000), (48000.0, 96000.0, 2000), (48000.0, 130000.0, 1500)])
 def test_fmstereo_single_channel(cuda, iq_rate, pcm_rate, n):
     x = fm_stereo_iq(n, fs=iq_rate)
     g, o = L.FMStereo(iq_rate, pcm_rate), O.FMStereo(iq_rate, pcm_rate)
