@@ -30,6 +30,7 @@ constexpr int G  = 8;                // samples per register-blocked group
 constexpr int NG = 2;                // groups between window slides
 constexpr int H  = kAmTaps - 1;      // history samples a window needs: 50
 constexpr int W  = H + NG * G;       // window length: 66
+constexpr int kSlide = 10;           // window entries moved per batch of a slide (loads ahead of the stores; 25 per batch measured no faster)
 
 // OUT_V1 (ampmodem USB / LSB with carrier): the kernel stops after the carrier loop and writes the mixed-down delayed
 // branch v1 as complex samples; the Hilbert pair and the DC blocker are feed-forward and follow as FIR launches
@@ -205,12 +206,12 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
             // (loads in batches ahead of the stores: the source lies above everything a batch writes)
             const float2 *ls = lp + consumed * BT; const float *ds = dc + consumed * BT;
 #pragma unroll
-            for (int i0 = 0; i0 < H; i0 += 10) {
-                float2 tl[10]; float td[10];
+            for (int i0 = 0; i0 < H; i0 += kSlide) {
+                float2 tl[kSlide]; float td[kSlide];
 #pragma unroll
-                for (int i = 0; i < 10; i++) { tl[i] = ls[(i0 + i) * BT]; td[i] = ds[(i0 + i) * BT]; }
+                for (int i = 0; i < kSlide; i++) { tl[i] = ls[(i0 + i) * BT]; td[i] = ds[(i0 + i) * BT]; }
 #pragma unroll
-                for (int i = 0; i < 10; i++) { lp[(i0 + i) * BT] = tl[i]; dc[(i0 + i) * BT] = td[i]; }
+                for (int i = 0; i < kSlide; i++) { lp[(i0 + i) * BT] = tl[i]; dc[(i0 + i) * BT] = td[i]; }
             }
         }
     }
@@ -425,6 +426,11 @@ bool amtail_few(bool has_agc, const AmTailArgs &a)
     // (up to 2048 channels: beyond that the carrier loop run on all eight lanes costs more issue slots than the filters'
     // parallelism saves -- measured 0.74 vs 0.79 ms at 1024 channels, 1.24 vs 0.81 ms at 8192)
     return a.C <= 2048 && !a.am.suppressed && !a.am.out_v1 && (!has_agc || a.in_tmajor);
+}
+
+const char *amtail_kernel_name(bool has_agc, const AmTailArgs &a)
+{
+    return amtail_few(has_agc, a) ? "amtail8_kernel" : "amtail_kernel";
 }
 
 cudaError_t agc_tmajor_launch(const AmTailArgs &a, cudaStream_t stream)

@@ -154,11 +154,13 @@ static EncodeTiledFn encode_tiled()
     return fn;
 }
 // rows of n complex64 samples as a 2-D float tensor [rows][2n]; box = one warp's tile: 32 rows x 16 samples (128 B), 128B swizzle
-static bool make_input_tmap(CUtensorMap *tm, const void *x, size_t n, size_t rows, unsigned box_rows = 32, unsigned box_floats = 32)
+// (pitch: samples between the starts of two rows when the call works on a time slice of longer rows; 0 = n)
+static bool make_input_tmap(CUtensorMap *tm, const void *x, size_t n, size_t rows, unsigned box_rows = 32, unsigned box_floats = 32, size_t pitch = 0)
 {
     EncodeTiledFn enc = encode_tiled();
-    if (!enc || (((size_t)x) & 15) || (n & 1) || n * 2 > 0x7fffffffull || rows > 0x7fffffffull) return false;   // box coordinates are int32
-    const cuuint64_t gdim[2] = { (cuuint64_t)n * 2, (cuuint64_t)rows }, gstride[1] = { (cuuint64_t)n * 8 };
+    if (pitch == 0) pitch = n;
+    if (!enc || (((size_t)x) & 15) || (n & 1) || (pitch & 1) || n * 2 > 0x7fffffffull || rows > 0x7fffffffull) return false;   // box coordinates are int32
+    const cuuint64_t gdim[2] = { (cuuint64_t)n * 2, (cuuint64_t)rows }, gstride[1] = { (cuuint64_t)pitch * 8 };
     const cuuint32_t box[2] = { box_floats, box_rows }, estr[2] = { 1, 1 };
     // the 32-float box is the staged tile (128-byte swizzle); wider boxes are L2-prefetch shapes and carry no swizzle
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -612,6 +614,9 @@ struct lqb_chain_s {
     cudaEvent_t ev_front[2] = { nullptr, nullptr }, ev_tail[2] = { nullptr, nullptr };
     bool tail_pending[2] = { false, false };
     unsigned ov_calls = 0;
+    // few channels (run_timepipe): the decimated-rate tail of time slice j runs on pipe_stream while the front works on slice j + 1
+    cudaStream_t pipe_stream = nullptr, front_stream = nullptr;
+    std::vector<cudaEvent_t> ev_pipe;
     // optional per-segment timing of execute_dev: one event pair per segment per call, on the stream the segment ran on
     bool timing = false;
     std::vector<std::vector<std::pair<cudaEvent_t, cudaEvent_t>>> timed_calls;
@@ -623,6 +628,9 @@ struct lqb_chain_s {
     ~lqb_chain_s()
     {
         if (tail_stream) { cudaStreamSynchronize(tail_stream); cudaStreamDestroy(tail_stream); }
+        if (pipe_stream) { cudaStreamSynchronize(pipe_stream); cudaStreamDestroy(pipe_stream); }
+        if (front_stream) { cudaStreamSynchronize(front_stream); cudaStreamDestroy(front_stream); }
+        for (auto &e : ev_pipe) cudaEventDestroy(e);
         for (int b = 0; b < 2; b++) { if (ev_front[b]) cudaEventDestroy(ev_front[b]); if (ev_tail[b]) cudaEventDestroy(ev_tail[b]); }
         clear_timing();
         for (auto &s : streams) if (s) cudaStreamDestroy(s);
@@ -798,8 +806,12 @@ static size_t seg_out_len(const Segment &g, size_t n) { for (auto *s : g.st) n =
 // run one segment on channels [ch0, ch0 + nch) of the chain; x/y point at the first of those rows
 static void note_kernel(std::string *kn, const std::string &name) { if (kn) { if (!kn->empty()) *kn += ";"; *kn += name; } }
 
+// a time slice of a longer call (run_timepipe): input rows in_pitch samples apart, output rows out_pitch samples apart
+struct SegIO { size_t in_pitch = 0, out_pitch = 0; };
+
 static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_t n_out, int ch0, int nch, cudaStream_t stream,
-                       bool in_tmajor, bool out_tmajor, int *launches, unsigned extra_mask = 0, int front_ring = 3, std::string *kn = nullptr)
+                       bool in_tmajor, bool out_tmajor, int *launches, unsigned extra_mask = 0, int front_ring = 3, std::string *kn = nullptr,
+                       SegIO io = SegIO())
 {
     (*launches)++;
     const lqb_stage_s *first = g.st.front();
@@ -807,7 +819,8 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         AmTailArgs a{};
         bool has_agc = false, has_de = false;
         a.x = (const float2 *)x; a.y = (float *)y; a.C = nch; a.ch0 = ch0; a.Ctot = first->C; a.in_tmajor = in_tmajor ? 1 : 0;
-        a.n = (long long)n; a.in_pitch = in_tmajor ? (long long)nch : (long long)n; a.out_pitch = (long long)n_out;
+        a.n = (long long)n; a.in_pitch = in_tmajor ? (long long)nch : (long long)n; a.out_pitch = (long long)(io.out_pitch ? io.out_pitch : n_out);
+        if (io.in_pitch && !in_tmajor) return fail(LQB_EINVAL, "internal: a time slice reaches the AM tail through the time-major hand-off only");
         for (lqb_stage_s *s : g.st) {
             if (s->kind == K_AGC) { LQB_TRY(static_cast<AgcStage *>(s)->fill(a.agc)); has_agc = true; }
             else if (s->kind == K_AM) LQB_TRY(static_cast<AmStage *>(s)->fill(a.am));
@@ -817,7 +830,9 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         // latency, not throughput, and the machine is mostly idle.  So the block is cut along time: the gain loop runs
         // chunk j + 1 on its own stream while the demodulator works on chunk j (state carries between chunks exactly as
         // between calls), and the tail takes about max(gain loop, demodulator) instead of their sum.
-        if (has_agc && in_tmajor && nch <= 16384 && n >= 512 && !a.am.suppressed && !getenv("LQB_NO_TAILPIPE")) {
+        int pipe_max = 16384;
+        if (const char *e = getenv("LQB_TAILPIPE_MAX")) pipe_max = atoi(e);                // tuning override
+        if (has_agc && in_tmajor && nch <= pipe_max && n >= 512 && !a.am.suppressed && !getenv("LQB_NO_TAILPIPE")) {
             AgcStage *ag = nullptr;
             for (lqb_stage_s *s : g.st) if (s->kind == K_AGC) ag = static_cast<AgcStage *>(s);
             LQB_TRY(ag->pipeline_resources());
@@ -839,12 +854,12 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
             }
             (*launches)--;
             note_kernel(kn, "agc_tmajor_kernel(x" + std::to_string(j) + ", ahead)");
-            note_kernel(kn, std::string(amtail_few(false, a) ? "amtail8_kernel" : "amtail_kernel") + "(x" + std::to_string(j) + ")");
+            note_kernel(kn, std::string(amtail_kernel_name(false, a)) + "(x" + std::to_string(j) + ")");
             return LQB_OK;
         }
         LQB_CUDA(amtail_launch(has_agc, has_de, a, stream));
         if (amtail_launch_count(has_agc, a) > 1) note_kernel(kn, "agc_tmajor_kernel");
-        note_kernel(kn, amtail_few(has_agc, a) ? "amtail8_kernel" : "amtail_kernel");
+        note_kernel(kn, amtail_kernel_name(has_agc, a));
         *launches += amtail_launch_count(has_agc, a) - 1;
         return LQB_OK;
     }
@@ -1007,7 +1022,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
     // the front of the receiver (cascade + decimating resampler): one component per lane (lanes.cu)
     {
         const int lanes = (extra_mask == 0 && !in_real && !getenv("LQB_NO_LANES")) ? lanes_per_channel(g.mask, g.nsos, nch) : 0;
-        if (lanes && make_input_tmap(&a.tmap, x, n, (size_t)nch, (unsigned)lanes_box_rows(lanes))) {
+        if (lanes && make_input_tmap(&a.tmap, x, n, (size_t)nch, (unsigned)lanes_box_rows(lanes), 32, io.in_pitch)) {
             ResampStage *r = nullptr;
             for (lqb_stage_s *s : g.st) if (s->kind == K_RESAMP) r = static_cast<ResampStage *>(s);
             DevArr<char> &tb = r->tapbuf[stream];
@@ -1020,6 +1035,7 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
             return LQB_OK;
         }
     }
+    if (io.in_pitch) return fail(LQB_EINVAL, "internal: a time slice needs the lane-split front kernel");
     // (A/B: LQB_NO_LANES=1) the same front with two channels per thread, packed arithmetic (front.cu)
     {
         bool two = nch >= 32768 && extra_mask == 0 && !in_real && front2_supported(g.mask, g.nsos);
@@ -1177,6 +1193,87 @@ static int run_overlapped(lqb_chain_s *c, const std::vector<Segment> &segs, cons
     return LQB_OK;
 }
 
+// ---- few channels: front and tail as a pipeline along TIME -------------------------------------------------------------
+// With few channels both segments are latency-bound (one warp per scheduler walks a recurrence) and most of the machine is
+// idle, so a call is cut into time slices: the front kernel of slice j + 1 runs on the caller's stream while the tail of
+// slice j (gain loop, carrier loop, filters) runs on the chain's own stream.  Every stage carries its state from slice to
+// slice exactly as it does from call to call (the host bookkeeping advances per slice), so the results are bit-identical
+// to the unsliced call; what stays exposed behind the front is the last slice's tail instead of the whole tail.
+static int timepipe_slices(const lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, size_t n, int C, bool in_i16)
+{
+    if (getenv("LQB_NO_TIMEPIPE") || getenv("LQB_NO_LANES") || c->overlap || in_i16 || segs.size() != 2) return 0;
+    if (segs[0].type != Segment::SEQ || segs[0].mask != (F_IIR | F_RS) || segs[1].type != Segment::AMTAIL) return 0;
+    // (up to 1024 channels: from 2048 on the sliced front loses more -- a launch, a pipeline fill and the generic first and last
+    // tiles per slice, and tail CTAs that take whole SMs away from it -- than the hidden tail gives back: measured 1.83 vs 1.78 ms
+    // at 2048 channels, 2.6 vs 2.2 ms at 8192, 6.8 vs 3.3 ms at 16384; there the gain loop alone runs ahead, run_segment)
+    int cmax = 1024;
+    if (const char *e = getenv("LQB_TIMEPIPE_MAX")) cmax = atoi(e);                    // tuning override
+    if (C > cmax || n < 16384 || (n & 1) || (((size_t)x) & 15) || !lanes_per_channel(segs[0].mask, segs[0].nsos, C)) return 0;
+    int k = 6;
+    if (const char *e = getenv("LQB_TIMEPIPE_SLICES")) { const int v = atoi(e); if (v >= 2 && v <= 64) k = v; }
+    return k;
+}
+
+static int run_timepipe(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, void *y, size_t n, int C, char *tmp,
+                        cudaStream_t stream, int K, bool timed)
+{
+    // The front must keep every one of its CTAs resident (a CTA that finds its SM taken waits for a whole slice), so it runs
+    // on a stream of its own with the HIGHEST priority and the small tail kernels fill what it leaves: with the tail ahead in
+    // the block scheduler's queue, 8192 channels ran 2.5 ms instead of 1.6 (measured).
+    if (!c->pipe_stream) {
+        int lo = 0, hi = 0;
+        LQB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        LQB_CUDA(cudaStreamCreateWithPriority(&c->front_stream, cudaStreamNonBlocking, hi));
+        LQB_CUDA(cudaStreamCreateWithPriority(&c->pipe_stream, cudaStreamNonBlocking, lo));
+    }
+    while (c->ev_pipe.size() < (size_t)K + 3) { cudaEvent_t e; LQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_pipe.push_back(e); }
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+    cudaStream_t fs = c->front_stream, ts = c->pipe_stream;
+    if (getenv("LQB_TIMEPIPE_SERIAL")) ts = fs;                         // A/B: the slices alone, nothing concurrent
+    // both follow everything already queued on the caller's stream
+    LQB_CUDA(cudaEventRecord(c->ev_pipe[K], stream));
+    LQB_CUDA(cudaStreamWaitEvent(fs, c->ev_pipe[K], 0));
+    LQB_CUDA(cudaStreamWaitEvent(ts, c->ev_pipe[K], 0));
+    if (timed && c->timed_calls.size() < 1024) {
+        evs.resize(2);
+        for (auto &p : evs) { LQB_CUDA(cudaEventCreate(&p.first)); LQB_CUDA(cudaEventCreate(&p.second)); }
+        LQB_CUDA(cudaEventRecord(evs[0].first, fs));
+    }
+    size_t on_total; chain_out_len(c, n, &on_total);
+    const size_t slice = (((n + K - 1) / K) + 15) / 16 * 16;                           // whole tiles of the front kernel
+    size_t off = 0; int j = 0;
+    for (size_t t0 = 0; t0 < n; t0 += slice, j++) {
+        const size_t ns = std::min(slice, n - t0);
+        const size_t on0 = seg_out_len(segs[0], ns), on = seg_out_len(segs[1], on0);
+        if (off + on > on_total) return fail(LQB_ESIZE, "internal: time slices produce more than the call");
+        char *hand = tmp + off * (size_t)C * 8;                                        // time-major [sample][channel]: slices are contiguous
+        SegIO fio; fio.in_pitch = n;
+        LQB_TRY(run_segment(segs[0], (const char *)x + t0 * 8, hand, ns, on0, 0, C, fs, false, true, &c->last_launches, 0u, 3, j == 0 ? &c->last_kernels : nullptr, fio));
+        LQB_CUDA(cudaEventRecord(c->ev_pipe[j], fs));
+        LQB_CUDA(cudaStreamWaitEvent(ts, c->ev_pipe[j], 0));
+        SegIO tio; tio.out_pitch = on_total;
+        if (on > 0 || on0 > 0)
+            LQB_TRY(run_segment(segs[1], hand, (char *)y + off * 4, on0, on, 0, C, ts, true, false, &c->last_launches, 0u, 3, j == 0 ? &c->last_kernels : nullptr, tio));
+        advance_all(c, ns);
+        off += on;
+    }
+    if (off != on_total) return fail(LQB_ESIZE, "internal: time slices produced %zu samples, the call %zu", off, on_total);
+    LQB_CUDA(cudaEventRecord(c->ev_pipe[K + 1], fs));
+    LQB_CUDA(cudaEventRecord(c->ev_pipe[K + 2], ts));
+    if (!evs.empty()) {
+        // front: first launch to last front kernel; tail: what stays exposed behind the front
+        LQB_CUDA(cudaEventRecord(evs[0].second, fs));
+        LQB_CUDA(cudaStreamWaitEvent(ts, c->ev_pipe[K + 1], 0));
+        LQB_CUDA(cudaEventRecord(evs[1].first, fs)); LQB_CUDA(cudaEventRecord(evs[1].second, ts));
+        LQB_CUDA(cudaEventRecord(c->ev_pipe[K + 2], ts));
+        c->timed_calls.push_back(std::move(evs));
+    }
+    LQB_CUDA(cudaStreamWaitEvent(stream, c->ev_pipe[K + 1], 0));
+    LQB_CUDA(cudaStreamWaitEvent(stream, c->ev_pipe[K + 2], 0));
+    note_kernel(&c->last_kernels, "(x" + std::to_string(j) + " time slices, tail on its own stream)");
+    return LQB_OK;
+}
+
 // a failure after the first launch of a call leaves device state (filter memories, rings) ahead of the host-side phase /
 // count bookkeeping; every later call would be silently misaligned, so the chain refuses them until it is reset
 static int chain_poison(lqb_chain_s *c, int rc)
@@ -1202,6 +1299,11 @@ static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, s
     if (segs.size() > 2) LQB_TRY(c->d_tmp[1].reserve(tmpb));
     if (in_i16 && !first_takes_i16(segs)) LQB_TRY(c->d_cvt.reserve((size_t)C * n * 8));
     int rc;
+    if (const int K = timepipe_slices(c, segs, x, n, C, in_i16)) {
+        LQB_TRY(chain_join_tails(c, stream));
+        rc = run_timepipe(c, segs, x, y, n, C, c->d_tmp[0].p, stream, K, c->timing);
+        return rc == LQB_OK ? rc : chain_poison(c, rc);           // (the slices advanced the host bookkeeping themselves)
+    }
     if (overlappable(c, segs, in_i16)) {
         rc = run_overlapped(c, segs, x, y, n, C, tmpb, stream);
     } else {
@@ -1317,6 +1419,16 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
         if (!deferred) LQB_TRY(c->h_out[s].reserve(std::max<size_t>(16, chunk * on * ob)));
         if (segs.size() > 1) LQB_TRY(c->h_tmp[s][0].reserve(tmpb));
         if (segs.size() > 2) LQB_TRY(c->h_tmp[s][1].reserve(tmpb));
+    }
+    if (nchunks == 1 && deferred) {
+        if (const int K = timepipe_slices(c, segs, c->h_in[0].p, n, C, in_i16)) {
+            LQB_CUDA(cudaMemcpyAsync(c->h_in[0].p, x, (size_t)C * n * ib, cudaMemcpyHostToDevice, c->streams[0]));
+            const int rc = run_timepipe(c, segs, c->h_in[0].p, c->h_out[0].p, n, C, c->h_tmp[0][0].p, c->streams[0], K, false);
+            if (rc != LQB_OK) return chain_poison(c, rc);
+            LQB_CUDA(cudaStreamSynchronize(c->streams[0]));
+            if (on) LQB_CUDA(cudaMemcpy(y, c->h_out[0].p, out_total, cudaMemcpyDeviceToHost));
+            return LQB_OK;
+        }
     }
     for (size_t k = 0; k < nchunks; k++) {
         const int s = (int)(k % lqb_chain_s::kStreams);

@@ -170,11 +170,23 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
     if (last_grp) {
         const long long nnext = a.rs.phase >> 24;
         const unsigned f = (a.rs.phase & 0xffffffu) >> (24 - a.rs.bits);
-        for (long long j = nnext - (L - 1); j < 0; j++) {
-            const int slot = (int)(((long long)a.rs.count + j + 4LL * L) % L);
-            const float h = __ldg(a.rs.bank + f * L + (int)(j - nnext + L - 1));
-            const float w = ((const float *)(a.rs.ring + slot * CT + gch))[comp];
-            acc = __fadd_rn(acc, __fmul_rn(h, w));
+        // (eight loads in flight at a time, one modulo for the whole walk: as a plain loop this was ~40 dependent global-memory
+        // round trips, 20 us per launch -- as much as 1000 samples of a lone warp's work)
+        const long long j0 = nnext - (L - 1);
+        const int cnt = j0 < 0 ? (int)(-j0) : 0;                        // ring samples in the window (at most L - 1)
+        int slot = (int)(((long long)a.rs.count + j0 + 4LL * L) % L);
+        const float *hb = a.rs.bank + f * L;
+        for (int i0 = 0; i0 < cnt; i0 += 8) {
+            float h[8], w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const bool on = i0 + i < cnt;
+                h[i] = on ? __ldg(hb + i0 + i) : 0.f;
+                w[i] = on ? ((const float *)(a.rs.ring + slot * CT + gch))[comp] : 0.f;
+                slot = slot + 1 == L ? 0 : slot + 1;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (i0 + i < cnt) acc = __fadd_rn(acc, __fmul_rn(h[i], w[i]));
         }
     }
 

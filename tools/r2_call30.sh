@@ -1,0 +1,19 @@
+#!/bin/bash
+cd /root/repo
+T=r2c30
+python -m pytest tests -q -m gpu -x > gpurun_out/${T}_pytest.log 2>&1; tail -3 gpurun_out/${T}_pytest.log
+run() { tag=$1; shift; env "$@" python bench.py --channels $C --no-cpu --no-e2e --no-side --steps 10 > gpurun_out/${T}_c${C}_$tag.json 2>&1; }
+for C in 1 1024 2048; do run def LQB_X=1; done
+C=8192; run l2 LQB_X=1; run l4 LQB_LANES=4
+C=4096; run l2 LQB_X=1; run l4 LQB_LANES=4
+C=65536; run def LQB_X=1
+python tools/config1_bench.py --blocks 32 > gpurun_out/${T}_config1.json 2>&1
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r2c30_c*.json')):
+    for l in open(f):
+        if l.startswith('{"metric'):
+            d=json.loads(l); r=d.get('roofline') or {}
+            print(f, round(d['value']), 'MS/s', round(d['ms_per_step'],3), [round(x,3) for x in r.get('segments_ms')], d['gpu']['kernels'][1:])
+print(open('gpurun_out/r2c30_config1.json').read()[:400])
+PY
