@@ -225,9 +225,20 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
     rowbase += ((rowbase >> 7) & 7u) << 4;
     // the eight chunk addresses of the row, kept in registers for the whole call: a load is then [register + stage offset
     // (uniform) + immediate] with no per-tile address arithmetic (stage offsets are multiples of 1 KB, so they commute with the XOR)
+    // (they come back through a volatile shared-memory load of the warp's own, still empty, ring: an XOR with an immediate
+    // is something ptxas rematerialises at every use to save a register -- six LOP3 per tile again -- a volatile load is not)
     unsigned xr[8];
+    {
+        unsigned *scr = (unsigned *)tiles + lane * 8;
 #pragma unroll
-    for (int m = 0; m < 8; m++) { xr[m] = rowbase ^ ((unsigned)m << 4); asm volatile("" : "+r"(xr[m])); }
+        for (int m = 0; m < 8; m++) scr[m] = rowbase ^ ((unsigned)m << 4);
+        __syncwarp();
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(scr);
+        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(xr[0]), "=r"(xr[1]), "=r"(xr[2]), "=r"(xr[3]) : "r"(sa) : "memory");
+        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(xr[4]), "=r"(xr[5]), "=r"(xr[6]), "=r"(xr[7]) : "r"(sa + 16u) : "memory");
+        __syncwarp();
+        fence_async_smem();                        // the ring is written by the TMA engine next
+    }
     auto ldx = [&](unsigned soff, auto jc) -> float {
         constexpr int j = decltype(jc)::value;
         float v;
@@ -314,6 +325,7 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
     const long long lim = (N - L + LAG_RS) < N ? (N - L + LAG_RS) : N;
     const int tfast0 = (LAG_RS + TS - 1) / TS, tfast1 = lim > 0 ? (int)(lim / TS) : 0;
     const unsigned tfast_n = tfast1 > tfast0 ? (unsigned)(tfast1 - tfast0) : 0u;       // fast tiles: one unsigned compare per tile
+    const bool no_stage_body = a.lanes_flags & 1;                       // (A/B: LQB_NO_STAGEBODY=1)
     for (int p = 0; p < NST; p++) if (p < nstg) load_stage(p, p, (unsigned)(p * STB));
     int stage = 0; unsigned parity = 0;                                 // every barrier of the ring completes once per lap
     unsigned soff = 0;                                                  // byte offset of the stage within the warp's ring (running: no multiply per tile)
@@ -328,6 +340,51 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
         // (only where a lone warp runs a scheduler: with seven warps per scheduler the wait costs nothing and the probe does)
         bool probe = false;
         if constexpr (TPS > 1) probe = (sg + 1 < nstg) ? mbar_try(&ws.bar[stage_n], parity_n) : false;
+        // A lone warp pays for everything around a tile body in full (flags, fast-tile test, branches, the loads' latency at the
+        // head of the body: 60 % of a one-channel call's cycles, ncu), so a stage whose TPS tiles all lie inside the call runs as
+        // ONE unrolled body: the next tile's samples and taps are fetched before the current tile's steps, every tile takes the
+        // general step (capture stream, restart multiplier), outputs are stored after the body in order.
+        bool whole = false;
+        if constexpr (TPS > 1) {
+            const int t0 = sg * TPS;
+            whole = (unsigned)(t0 - tfast0) < tfast_n && (unsigned)(t0 + TPS - 1 - tfast0) < tfast_n && !no_stage_body;
+        }
+        if (whole) {
+            if constexpr (TPS > 1) {
+                float xs[2][TS], tp[2][TS], kp[2][TS], cp[2][TS], outs[TPS]; int es[TPS];
+                auto fetch = [&](auto qc) {
+                    constexpr int q = decltype(qc)::value, b = q & 1;
+                    const unsigned rowq = soff + (unsigned)(q * WTA);
+                    const TileRec &rq = ws.rec[stage][q];
+                    if (G == 1 || first_grp) {
+                        static_for<TS>([&](auto jc) { xs[b][decltype(jc)::value] = ldx(rowq, jc); });
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TS; j++) xs[b][j] = 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < TS; j += 4) {
+                        const float4 q4 = *(const float4 *)&rq.tap[j], w = *(const float4 *)&rq.keep[j], u = *(const float4 *)&rq.cap[j];
+                        tp[b][j] = q4.x; tp[b][j + 1] = q4.y; tp[b][j + 2] = q4.z; tp[b][j + 3] = q4.w;
+                        kp[b][j] = w.x; kp[b][j + 1] = w.y; kp[b][j + 2] = w.z; kp[b][j + 3] = w.w;
+                        cp[b][j] = u.x; cp[b][j + 1] = u.y; cp[b][j + 2] = u.z; cp[b][j + 3] = u.w;
+                    }
+                    es[q] = rq.emit;
+                };
+                fetch(std::integral_constant<int, 0>{});
+                static_for<TPS>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value, b = q & 1;
+                    if constexpr (q + 1 < TPS) fetch(std::integral_constant<int, q + 1>{});
+                    outv = 0.f;
+                    static_for<TS>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        step(jc, std::false_type{}, std::true_type{}, xs[b][j], tp[b][j], kp[b][j], cp[b][j], 0, 0);
+                    });
+                    outs[q] = outv;
+                });
+                static_for<TPS>([&](auto qc) { constexpr int q = decltype(qc)::value; if (es[q] >= 0) emit_out(outs[q]); });
+            }
+        } else {
         int e_nx = -1, gen_nx = 0; bool flags_nx = false;      // the next tile's flags, read from its record one tile ahead
 #pragma unroll 1
         for (int q = 0; q < TPS; q++) {
@@ -385,6 +442,7 @@ __global__ void __launch_bounds__(128, TPS == 1 ? 7 : 1) lanes_kernel(const __gr
                     step(jc, std::true_type{}, std::true_type{}, x, rec.tap[j], rec.keep[j], 0.f, e, k);
                 });
             }
+        }
         }
         }
         // (the vote makes the probe's answer warp-uniform; taken here, after the stage's arithmetic, so that nothing waits for it)
@@ -481,6 +539,7 @@ cudaError_t lanes_launch(int nsos, int lanes, const SeqArgs &a0, cudaStream_t st
         a.lc[i] = on ? -a.iir.a[i][1] : 0.f; a.lc[4 + i] = on ? -a.iir.a[i][2] : 0.f;
         a.lc[8 + i] = on ? a.iir.b[i][1] : 0.f; a.lc[12 + i] = on ? a.iir.b[i][0] : 0.f; a.lc[16 + i] = on ? a.iir.b[i][2] : 0.f;
     }
+    a.lanes_flags = getenv("LQB_NO_STAGEBODY") ? 1 : 0;
     if (!a.tapstream) return cudaErrorInvalidValue;
     if (a.C <= 0 || a.n <= 0) return cudaSuccess;
     const bool full = full_machine(a.C, lanes);

@@ -97,6 +97,7 @@ struct alignas(64) SeqArgs {
     int use_tma;                   // tmap is valid: stage the input with TMA (full-warp kernels that have the variant)
     int out_tmajor;                // decimated output stored [sample][channel] (hand-off to the AM tail kernel)
     const void *tapstream;         // lane-split front kernels (lanes.cu): per-tile tap records of this call
+    int lanes_flags;               // lanes.cu tuning switches (bit 0: no whole-stage bodies)
     alignas(16) float lc[20];      // lanes.cu, one lane pair per channel: -a1[4], -a2[4], b1[4], b0[4], b2[4] of the cascade, in the
                                    // order a step uses them (five 16-byte uniform loads per tile instead of eleven scattered ones)
     long long n, out_pitch;
