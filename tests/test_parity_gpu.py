@@ -999,6 +999,31 @@ def test_amtail_eight_lane_kernel_equals_thread_per_channel(cuda, monkeypatch):
     assert np.array_equal(words[0][0], words[1][0]) and np.array_equal(words[0][1], words[1][1])
 
 
+def test_pageable_input_staged_by_host_threads(cuda, monkeypatch):
+    """A plain numpy array is pageable memory; the time-sliced host path copies it through pinned bounce buffers with a few host
+    threads (capi.cu staged_h2d) instead of leaving it to the driver's single-threaded staging.  Same bytes reach the device:
+    the audio is bit-identical to the driver-staged call (LQB_NO_STAGING=1) for complex64 and for int16 I/Q input, with a row
+    count that does not divide among the threads and rows that do not fill a bounce buffer evenly."""
+    C, n = 141, 3 * 32768
+    x = np.stack([am_iq(n, seed=700 + c, f_off=90.0 + 7 * c) for c in range(C)])
+    xi = np.empty((C, 2 * n), np.int16)
+    xi[:, 0::2] = np.clip(np.round(x.real * 32767), -32767, 32767); xi[:, 1::2] = np.clip(np.round(x.imag * 32767), -32767, 32767)
+    outs = {}
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("LQB_NO_STAGING", env)
+        else:
+            monkeypatch.delenv("LQB_NO_STAGING", raising=False)
+        for name, arr in (("c64", x), ("i16", xi)):
+            r = _Radio(L, channels=C); ch = L.Chain(*r.stages())
+            y = np.concatenate([ch(np.ascontiguousarray(arr[:, :arr.shape[1] // 3 * 2])), ch(np.ascontiguousarray(arr[:, arr.shape[1] // 3 * 2:]))], axis=1)
+            outs[(env, name)] = y
+    for name in ("c64", "i16"):
+        assert np.array_equal(outs[(None, name)].view(np.uint32), outs[("1", name)].view(np.uint32)), name
+    ref = _oracle_radio_with_product_coeffs(_Radio(L))(x[57])
+    assert np.array_equal(outs[(None, "c64")][57].view(np.uint32), ref.view(np.uint32))
+
+
 @pytest.mark.parametrize("lanes,C,n", [("2", 37, 4098), ("4", 9, 1234), ("8", 3, 530), ("2", 16, 16), ("8", 1, 7)])
 def test_guard_bands_around_device_buffers(cuda, monkeypatch, lanes, C, n):
     """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted the old way: input, output and
