@@ -1525,11 +1525,13 @@ static int chain_execute_host(lqb_chain_s *c, const void *x, size_t n, void *y, 
             return LQB_OK;
         }
     }
+    const bool chunk_pinned = host_pinned(x) || getenv("LQB_NO_STAGING");
     for (size_t k = 0; k < nchunks; k++) {
         const int s = (int)(k % lqb_chain_s::kStreams);
         const size_t c0 = k * chunk, nc = std::min(chunk, (size_t)C - c0);
         char *dst = deferred ? c->h_out[0].p + c0 * on * ob : c->h_out[s].p;
-        LQB_CUDA(cudaMemcpyAsync(c->h_in[s].p, (const char *)x + c0 * n * ib, nc * n * ib, cudaMemcpyHostToDevice, c->streams[s]));
+        if (!chunk_pinned && nc * n * ib >= ((size_t)16 << 20)) LQB_TRY(staged_h2d(c, c->h_in[s].p, (const char *)x + c0 * n * ib, n * ib, n * ib, nc, c->streams[s]));
+        else LQB_CUDA(cudaMemcpyAsync(c->h_in[s].p, (const char *)x + c0 * n * ib, nc * n * ib, cudaMemcpyHostToDevice, c->streams[s]));
         { const int rc = run_all(c, segs, c->h_in[s].p, dst, n, (int)c0, (int)nc, c->h_tmp[s][0].p, c->h_tmp[s][1].p, c->streams[s], &c->last_launches, false, in_i16, c->h_cvt[s].p); if (rc != LQB_OK) return chain_poison(c, rc); }
         if (on && !deferred) LQB_CUDA(cudaMemcpyAsync((char *)y + c0 * on * ob, dst, nc * on * ob, cudaMemcpyDeviceToHost, c->streams[s]));
     }

@@ -1022,6 +1022,17 @@ def test_pageable_input_staged_by_host_threads(cuda, monkeypatch):
         assert np.array_equal(outs[(None, name)].view(np.uint32), outs[("1", name)].view(np.uint32)), name
     ref = _oracle_radio_with_product_coeffs(_Radio(L))(x[57])
     assert np.array_equal(outs[(None, "c64")][57].view(np.uint32), ref.view(np.uint32))
+    # the channel-chunk path (full-rate output: a FIR filter) stages its chunks the same way
+    h = O.firdes_kaiser(33, 0.1, 60.0)
+    ys = []
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("LQB_NO_STAGING", env)
+        else:
+            monkeypatch.delenv("LQB_NO_STAGING", raising=False)
+        f = L.FIRFilter(h, channels=C)
+        ys.append(np.concatenate([f(np.ascontiguousarray(x[:, :70000])), f(np.ascontiguousarray(x[:, 70000:]))], axis=1))
+    assert np.array_equal(ys[0].view(np.uint32), ys[1].view(np.uint32))
 
 
 @pytest.mark.parametrize("lanes,C,n", [("2", 37, 4098), ("4", 9, 1234), ("8", 3, 530), ("2", 16, 16), ("8", 1, 7)])
