@@ -1330,7 +1330,7 @@ static int chain_execute_dev(lqb_chain_s *c, const void *x, size_t n, void *y, s
 // bounce buffers while the previous buffer crosses PCIe.
 class StagePool {
     std::vector<std::thread> th;
-    std::mutex m; std::condition_variable cv, done;
+    std::mutex m, callers; std::condition_variable cv, done;      // (callers: one parallel copy at a time -- chains may run on several host threads)
     std::function<void(int, int)> job; int gen = 0, pending = 0;
 public:
     explicit StagePool(int n)
@@ -1350,6 +1350,7 @@ public:
     int size() const { return (int)th.size(); }
     void run(const std::function<void(int, int)> &f)
     {
+        std::lock_guard<std::mutex> one(callers);
         std::unique_lock<std::mutex> lk(m);
         job = f; pending = (int)th.size(); gen++;
         cv.notify_all();
