@@ -30,7 +30,10 @@ constexpr int G  = 8;                // samples per register-blocked group
 constexpr int NG = 2;                // groups between window slides
 constexpr int H  = kAmTaps - 1;      // history samples a window needs: 50
 constexpr int W  = H + NG * G;       // window length: 66
-constexpr int kSlide = 10;           // window entries moved per batch of a slide (loads ahead of the stores; 25 per batch measured no faster)
+constexpr int DOFF = 2;              // amtail_kernel: the DC window starts two slots into its row, so that the slot a group's results go to
+                                     // (H + DOFF = 52) is 16-byte aligned
+constexpr int WDP = W + DOFF;        // DC row length: 68 floats (68 mod 32 = 4: a quarter warp's 16-byte accesses cover all 32 banks, as
+                                     // do the lowpass rows of 66 float2 = 132 words)
 
 // OUT_V1 (ampmodem USB / LSB with carrier): the kernel stops after the carrier loop and writes the mixed-down delayed
 // branch v1 as complex samples; the Hilbert pair and the DC blocker are feed-forward and follow as FIR launches
@@ -38,9 +41,9 @@ template <bool HAS_AGC, bool HAS_DE, bool OUT_V1>
 __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ AmTailArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    float2 *s_lp  = (float2 *)smem;                       // [W][BT]
-    float  *s_dc  = (float *)(s_lp + W * BT);             // [W][BT]
-    float  *s_sin = s_dc + W * BT;                        // [1024]
+    float2 *s_lp  = (float2 *)smem;                       // [BT][W]   one row per thread: 16-byte loads, stores and slides
+    float  *s_dc  = (float *)(s_lp + W * BT);             // [BT][WDP]
+    float  *s_sin = s_dc + WDP * BT;                      // [1024]
     double2 *s_log = (double2 *)(s_sin + 1024);           // [128] (only with the AGC)
 
     const int tid = threadIdx.x;
@@ -57,12 +60,12 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
     uint32_t theta = a.am.theta[gch], dtheta = a.am.dtheta[gch];
     float de_v1 = HAS_DE ? a.de.v1[gch] : 0.f;
     // history: the H samples before this call, oldest first, from the rings
-    float2 *lp = s_lp + tid; float *dc = s_dc + tid;
+    float2 *lp = s_lp + tid * W; float *dc = s_dc + tid * WDP;
     if (!a.am.suppressed) {
         for (int i = 0; i < H; i++) {
             const unsigned slot = (a.am.count + (unsigned)(kAmRing - H) + i) & (kAmRing - 1);
-            lp[i * BT] = a.am.lp_ring[slot * CT + gch];
-            dc[i * BT] = a.am.dc_ring[slot * CT + gch];
+            lp[i] = a.am.lp_ring[slot * CT + gch];
+            dc[DOFF + i] = a.am.dc_ring[slot * CT + gch];
         }
     }
     __syncthreads();                                      // the sine table; the only barrier
@@ -137,26 +140,30 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
                 const int ng = consumed - gi * G < G ? consumed - gi * G : G;
                 if (ng <= 0) break;
                 const long long k0 = kk + gi * G;
-                float2 *lw = lp + gi * G * BT; float *dw = dc + gi * G * BT;     // this group's window base
+                float2 *lw = lp + gi * G; float *dw = dc + gi * G;               // this group's window base (16-byte aligned)
                 float2 z[G];
 #pragma unroll
                 for (int g = 0; g < G; g++) { z[g] = zn[g]; zn[g] = k0 + G + g < N ? load_x(k0 + G + g) : make_float2(0.f, 0.f); }
 #pragma unroll
-                for (int g = 0; g < G; g++) {
-                    if (HAS_AGC && g < ng) z[g] = agc_step(z[g]);
-                    lw[(H + g) * BT] = z[g];
-                }
+                for (int g = 0; g < G; g++) if (HAS_AGC && g < ng) z[g] = agc_step(z[g]);
+#pragma unroll
+                for (int g = 0; g < G; g += 2) *(float4 *)&lw[H + g] = make_float4(z[g].x, z[g].y, z[g + 1].x, z[g + 1].y);
                 // lowpass: x0[g] = sum_i lp[i] * window[g + i], i ascending (oldest sample first)
                 u64 s2[G];                      // (re, im) accumulators: one FFMA2 per tap and output
 #pragma unroll
                 for (int g = 0; g < G; g++) s2[g] = 0ull;
 #pragma unroll
-                for (int i = 0; i < H + G; i++) {
-                    const u64 w = pk(lw[i * BT]);
+                for (int i0 = 0; i0 < H + G; i0 += 2) {
+                    const float4 q = *(const float4 *)&lw[i0];                 // window samples i0 and i0 + 1
 #pragma unroll
-                    for (int g = 0; g < G; g++) {
-                        const int t = i - g;
-                        if (t >= 0 && t < kAmTaps) s2[g] = fma2(pk(a.am.lp[t], a.am.lp[t]), w, s2[g]);
+                    for (int h = 0; h < 2; h++) {
+                        const int i = i0 + h;
+                        const u64 w = h ? pk(q.z, q.w) : pk(q.x, q.y);
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            const int t = i - g;
+                            if (t >= 0 && t < kAmTaps) s2[g] = fma2(pk(a.am.lp[t], a.am.lp[t]), w, s2[g]);
+                        }
                     }
                 }
                 // carrier PLL on the filtered branch, mix the delayed branch with the same phase
@@ -166,26 +173,33 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
                     m[g] = 0.f;
                     if (g < ng) {
                         const float2 sc = nco_sc();
-                        const float2 x1 = lw[(H + g - kAmDelay) * BT];
+                        const float2 x1 = lw[H + g - kAmDelay];
                         const float2 v0 = mix_down(upk(s2[g]), sc), v1 = mix_down(x1, sc);
                         pll(v0.y);
                         if (OUT_V1) { if (active) ((float2 *)a.y)[cl * a.out_pitch + k0 + g] = v1; }
                         else m[g] = __fdiv_rn(v1.x, a.am.mod_index);
                     }
-                    dw[(H + g) * BT] = m[g];
                 }
+                *(float4 *)&dw[H + 2] = make_float4(m[0], m[1], m[2], m[3]);   // (H + 2 = 52: 16-byte aligned; the window starts two slots in)
+                *(float4 *)&dw[H + 6] = make_float4(m[4], m[5], m[6], m[7]);
                 if constexpr (!OUT_V1) {
                 // dc blocker, same blocking
                 float acc[G];
 #pragma unroll
                 for (int g = 0; g < G; g++) acc[g] = 0.f;
 #pragma unroll
-                for (int i = 0; i < H + G; i++) {
-                    const float w = dw[i * BT];
+                for (int i0 = 0; i0 < H + G + 2; i0 += 4) {                       // window slots 2 .. H + G + 1 of the row (DOFF = 2)
+                    const float4 q = *(const float4 *)&dw[i0];
+                    const float wv[4] = { q.x, q.y, q.z, q.w };
 #pragma unroll
-                    for (int g = 0; g < G; g++) {
-                        const int t = i - g;
-                        if (t >= 0 && t < kAmTaps) acc[g] = __fmaf_rn(a.am.dc[t], w, acc[g]);
+                    for (int h = 0; h < 4; h++) {
+                        const int i = i0 + h - DOFF;
+                        if (i < 0 || i >= H + G) continue;
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            const int t = i - g;
+                            if (t >= 0 && t < kAmTaps) acc[g] = __fmaf_rn(a.am.dc[t], wv[h], acc[g]);
+                        }
                     }
                 }
 #pragma unroll
@@ -204,14 +218,23 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
             }
             // slide both windows by the samples consumed
             // (loads in batches ahead of the stores: the source lies above everything a batch writes)
-            const float2 *ls = lp + consumed * BT; const float *ds = dc + consumed * BT;
+            if (consumed == NG * G) {
+                // (rows are 16-byte aligned and a whole frame is a multiple of 16 bytes: the slide moves four floats at a time)
+                const float4 *ls = (const float4 *)(lp + NG * G); float4 *ld = (float4 *)lp;
+                const float4 *ds = (const float4 *)(dc + NG * G); float4 *dd = (float4 *)dc;
+                constexpr int NL = H / 2, ND = (DOFF + H + 3) / 4;                   // 25 and 13 vectors
+                float4 tl[NL], td[ND];
 #pragma unroll
-            for (int i0 = 0; i0 < H; i0 += kSlide) {
-                float2 tl[kSlide]; float td[kSlide];
+                for (int i = 0; i < NL; i++) tl[i] = ls[i];
 #pragma unroll
-                for (int i = 0; i < kSlide; i++) { tl[i] = ls[(i0 + i) * BT]; td[i] = ds[(i0 + i) * BT]; }
+                for (int i = 0; i < ND; i++) td[i] = ds[i];
 #pragma unroll
-                for (int i = 0; i < kSlide; i++) { lp[(i0 + i) * BT] = tl[i]; dc[(i0 + i) * BT] = td[i]; }
+                for (int i = 0; i < NL; i++) ld[i] = tl[i];
+#pragma unroll
+                for (int i = 0; i < ND; i++) dd[i] = td[i];
+            } else {
+                // the call's last, shorter frame: one entry at a time (ascending: the source lies above the destination)
+                for (int i = 0; i < H; i++) { lp[i] = lp[consumed + i]; dc[DOFF + i] = dc[DOFF + consumed + i]; }
             }
         }
     }
@@ -228,8 +251,8 @@ __global__ void __launch_bounds__(BT, 4) amtail_kernel(const __grid_constant__ A
             const unsigned base = a.am.count + (unsigned)(N % kAmRing) + (unsigned)(kAmRing - H);
             for (int i = 0; i < H; i++) {
                 const unsigned slot = (base + i) & (kAmRing - 1);
-                a.am.lp_ring[slot * CT + gch] = lp[i * BT];
-                a.am.dc_ring[slot * CT + gch] = dc[i * BT];
+                a.am.lp_ring[slot * CT + gch] = lp[i];
+                a.am.dc_ring[slot * CT + gch] = dc[DOFF + i];
             }
         }
     }
@@ -462,7 +485,7 @@ cudaError_t amtail_launch(bool has_agc, bool has_de, const AmTailArgs &a, cudaSt
     AmFn fn = a.am.out_v1 ? (has_agc ? amtail_kernel<true, false, true> : amtail_kernel<false, false, true>)
             : has_agc ? (has_de ? amtail_kernel<true, true, false> : amtail_kernel<true, false, false>)
                       : (has_de ? amtail_kernel<false, true, false> : amtail_kernel<false, false, false>);
-    const size_t smem = (size_t)W * BT * (sizeof(float2) + sizeof(float)) + 1024 * sizeof(float) + (has_agc ? 128 * sizeof(double2) : 0);
+    const size_t smem = (size_t)BT * (W * sizeof(float2) + WDP * sizeof(float)) + 1024 * sizeof(float) + (has_agc ? 128 * sizeof(double2) : 0);
     cudaError_t rc = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     fn<<<(unsigned)((a.C + BT - 1) / BT), BT, smem, stream>>>(a);
