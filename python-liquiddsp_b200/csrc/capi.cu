@@ -838,13 +838,16 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         // latency, not throughput, and the machine is mostly idle.  So the block is cut along time: the gain loop runs
         // chunk j + 1 on its own stream while the demodulator works on chunk j (state carries between chunks exactly as
         // between calls), and the tail takes about max(gain loop, demodulator) instead of their sum.
-        int pipe_max = 16384;
+        // (eight chunks up to 16384 channels; two up to 40000, where the second half of the gain loop hides behind the first
+        // half of the demodulator: 32768 channels 1.06 -> 1.01 ms; at 65536 both fill the machine and nothing is gained, measured)
+        int pipe_max = 40000;
         if (const char *e = getenv("LQB_TAILPIPE_MAX")) pipe_max = atoi(e);                // tuning override
         if (has_agc && in_tmajor && nch <= pipe_max && n >= 512 && !a.am.suppressed && !getenv("LQB_NO_TAILPIPE")) {
             AgcStage *ag = nullptr;
             for (lqb_stage_s *s : g.st) if (s->kind == K_AGC) ag = static_cast<AgcStage *>(s);
             LQB_TRY(ag->pipeline_resources());
-            const int K = 8;
+            int K = nch <= 16384 ? 8 : 2;
+            if (const char *e = getenv("LQB_TAILPIPE_CHUNKS")) { const int v = atoi(e); if (v >= 2 && v <= 8) K = v; }     // tuning override
             const long long step = (((long long)n + K - 1) / K + 7) / 8 * 8;      // whole groups of the demodulator's eight samples
             LQB_CUDA(cudaEventRecord(ag->ev_begin, stream));
             LQB_CUDA(cudaStreamWaitEvent(ag->ahead, ag->ev_begin, 0));
