@@ -185,6 +185,11 @@ namespace lqb {
 // this set before touching them instead of dereferencing freed memory.
 static std::mutex g_live_mu;
 static std::set<const lqb_stage_s *> g_live;
+static thread_local bool t_no_tail_ahead = false;      // run_timepipe inside an SM partition: the tail's own side stream would leave it
+// an SM partition of the device (green contexts): a stream for the front's SMs, one for the rest (sm_partition_create)
+struct SmPartition {
+    CUgreenCtx ga = nullptr, gb = nullptr; cudaStream_t front = nullptr, tail = nullptr, tail2 = nullptr; int sm_a = 0, sm_b = 0; bool ok = false;
+};
 // entry points that may run from a destructor / garbage collector put the caller's current device back
 struct DevGuard {
     int prev = -1;
@@ -623,6 +628,7 @@ struct lqb_chain_s {
     unsigned ov_calls = 0;
     // few channels (run_timepipe): the decimated-rate tail of time slice j runs on pipe_stream while the front works on slice j + 1
     cudaStream_t pipe_stream = nullptr, front_stream = nullptr;
+    std::map<int, lqb::SmPartition> sm_parts;       // SM partitions by front size (created once, kept for the chain's life)
     std::vector<cudaEvent_t> ev_pipe;
     // optional per-segment timing of execute_dev: one event pair per segment per call, on the stream the segment ran on
     bool timing = false;
@@ -815,7 +821,7 @@ static size_t seg_out_len(const Segment &g, size_t n) { for (auto *s : g.st) n =
 static void note_kernel(std::string *kn, const std::string &name) { if (kn) { if (!kn->empty()) *kn += ";"; *kn += name; } }
 
 // a time slice of a longer call (run_timepipe): input rows in_pitch samples apart, output rows out_pitch samples apart
-struct SegIO { size_t in_pitch = 0, out_pitch = 0; };
+struct SegIO { size_t in_pitch = 0, out_pitch = 0; int tail_part = 0; };      // tail_part: 0 the whole AM tail, 1 its gain loop only, 2 its demodulator only
 
 static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_t n_out, int ch0, int nch, cudaStream_t stream,
                        bool in_tmajor, bool out_tmajor, int *launches, unsigned extra_mask = 0, int front_ring = 3, std::string *kn = nullptr,
@@ -838,11 +844,17 @@ static int run_segment(const Segment &g, const void *x, void *y, size_t n, size_
         // latency, not throughput, and the machine is mostly idle.  So the block is cut along time: the gain loop runs
         // chunk j + 1 on its own stream while the demodulator works on chunk j (state carries between chunks exactly as
         // between calls), and the tail takes about max(gain loop, demodulator) instead of their sum.
+        if (io.tail_part && has_agc && in_tmajor && !a.am.suppressed) {
+            // run_timepipe inside an SM partition: gain loop and demodulator of a slice on two streams of the tail's SMs
+            if (io.tail_part == 1) { LQB_CUDA(agc_tmajor_launch(a, stream)); note_kernel(kn, "agc_tmajor_kernel"); }
+            else { LQB_CUDA(amtail_launch(false, has_de, a, stream)); note_kernel(kn, amtail_kernel_name(false, a)); }
+            return LQB_OK;
+        }
         // (eight chunks up to 16384 channels; two up to 40000, where the second half of the gain loop hides behind the first
         // half of the demodulator: 32768 channels 1.06 -> 1.01 ms; at 65536 both fill the machine and nothing is gained, measured)
         int pipe_max = 40000;
         if (const char *e = getenv("LQB_TAILPIPE_MAX")) pipe_max = atoi(e);                // tuning override
-        if (has_agc && in_tmajor && nch <= pipe_max && n >= 512 && !a.am.suppressed && !getenv("LQB_NO_TAILPIPE")) {
+        if (has_agc && in_tmajor && nch <= pipe_max && n >= 512 && !a.am.suppressed && !t_no_tail_ahead && !getenv("LQB_NO_TAILPIPE")) {
             AgcStage *ag = nullptr;
             for (lqb_stage_s *s : g.st) if (s->kind == K_AGC) ag = static_cast<AgcStage *>(s);
             LQB_TRY(ag->pipeline_resources());
@@ -1204,22 +1216,85 @@ static int run_overlapped(lqb_chain_s *c, const std::vector<Segment> &segs, cons
     return LQB_OK;
 }
 
+// ---- SM partitions (green contexts) --------------------------------------------------------------------------------------
+// A front of few channels leaves SMs idle but needs every one of its warps alone on a scheduler; tail kernels placed beside
+// them take their issue slots one for one (run_timepipe).  A green context confines a stream's kernels to a set of SMs: the
+// front gets as many SMs as its warps fill four to an SM, the tail the rest.  Driver API, fetched at run time like the
+// tensor-map encoder; every failure falls back to ordinary streams.
+template <class F> static F drv(const char *name)
+{
+    void *p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+    return (F)p;
+}
+static bool sm_partition_create(SmPartition &sp, int want_front_sms)
+{
+    typedef CUresult (*GetDev)(CUdevice *, int);
+    typedef CUresult (*GetRes)(CUdevice, CUdevResource *, CUdevResourceType);
+    typedef CUresult (*Split)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int);
+    typedef CUresult (*GenDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int);
+    typedef CUresult (*GCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+    typedef CUresult (*GStream)(CUstream *, CUgreenCtx, unsigned int, int);
+    static GetDev get_dev = drv<GetDev>("cuDeviceGet");
+    static GetRes get_res = drv<GetRes>("cuDeviceGetDevResource");
+    static Split split = drv<Split>("cuDevSmResourceSplitByCount");
+    static GenDesc gen = drv<GenDesc>("cuDevResourceGenerateDesc");
+    static GCreate gcreate = drv<GCreate>("cuGreenCtxCreate");
+    static GStream gstream = drv<GStream>("cuGreenCtxStreamCreate");
+    if (!get_dev || !get_res || !split || !gen || !gcreate || !gstream) return false;
+    int ord = 0; if (cudaGetDevice(&ord) != cudaSuccess) return false;
+    CUdevice dev; if (get_dev(&dev, ord) != CUDA_SUCCESS) return false;
+    CUdevResource all{}, grp{}, rest{};
+    if (get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    unsigned int nb = 1;
+    if (split(&grp, &nb, &all, &rest, 0, (unsigned)want_front_sms) != CUDA_SUCCESS || nb != 1) return false;
+    if (grp.sm.smCount < (unsigned)want_front_sms || rest.sm.smCount < 8) return false;
+    CUdevResourceDesc da = nullptr, db = nullptr;
+    if (gen(&da, &grp, 1) != CUDA_SUCCESS || gen(&db, &rest, 1) != CUDA_SUCCESS) return false;
+    if (gcreate(&sp.ga, da, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    if (gcreate(&sp.gb, db, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    CUstream fa = nullptr, fb = nullptr, fc = nullptr;
+    if (gstream(&fa, sp.ga, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS || gstream(&fb, sp.gb, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+        gstream(&fc, sp.gb, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+    sp.front = (cudaStream_t)fa; sp.tail = (cudaStream_t)fb; sp.tail2 = (cudaStream_t)fc; sp.sm_a = (int)grp.sm.smCount; sp.sm_b = (int)rest.sm.smCount; sp.ok = true;
+    return true;
+}
 // ---- few channels: front and tail as a pipeline along TIME -------------------------------------------------------------
 // With few channels both segments are latency-bound (one warp per scheduler walks a recurrence) and most of the machine is
 // idle, so a call is cut into time slices: the front kernel of slice j + 1 runs on the caller's stream while the tail of
 // slice j (gain loop, carrier loop, filters) runs on the chain's own stream.  Every stage carries its state from slice to
 // slice exactly as it does from call to call (the host bookkeeping advances per slice), so the results are bit-identical
 // to the unsliced call; what stays exposed behind the front is the last slice's tail instead of the whole tail.
-static int timepipe_slices(const lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, size_t n, int C, bool in_i16)
+// SMs the front of C channels fills with four lone warps each (rounded up to a multiple of eight), or 0 when too few are left over
+static int partition_front_sms(const std::vector<Segment> &segs, int C)
+{
+    const int lanes = lanes_per_channel(segs[0].mask, segs[0].nsos, C);
+    if (!lanes) return 0;
+    const long long warps = ((long long)C * lanes + 31) / 32;
+    const long long want = ((warps + 3) / 4 + 7) / 8 * 8;
+    return (want >= 8 && want <= 100) ? (int)want : 0;                                 // (at least 48 SMs stay for the tail)
+}
+static SmPartition *timepipe_partition(lqb_chain_s *c, const std::vector<Segment> &segs, int C)
+{
+    if (getenv("LQB_NO_PARTITION")) return nullptr;
+    const int want = partition_front_sms(segs, C);
+    if (!want) return nullptr;
+    SmPartition &sp = c->sm_parts[want];
+    if (!sp.ok && !sp.ga) sm_partition_create(sp, want);           // (tried once per chain and size)
+    return sp.ok ? &sp : nullptr;
+}
+static int timepipe_slices(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, size_t n, int C, bool in_i16)
 {
     if (getenv("LQB_NO_TIMEPIPE") || getenv("LQB_NO_LANES") || c->overlap || in_i16 || segs.size() != 2) return 0;
     if (segs[0].type != Segment::SEQ || segs[0].mask != (F_IIR | F_RS) || segs[1].type != Segment::AMTAIL) return 0;
-    // (up to 1024 channels: from 2048 on the sliced front loses more -- a launch, a pipeline fill and the generic first and last
-    // tiles per slice, and tail CTAs that take whole SMs away from it -- than the hidden tail gives back: measured 1.83 vs 1.78 ms
-    // at 2048 channels, 2.6 vs 2.2 ms at 8192, 6.8 vs 3.3 ms at 16384; there the gain loop alone runs ahead, run_segment)
+    if (n < 16384 || (n & 1) || (((size_t)x) & 15) || !lanes_per_channel(segs[0].mask, segs[0].nsos, C)) return 0;
+    // Up to 1024 channels the slices pay on ordinary streams.  Beyond that the concurrent tail takes the front's issue slots one
+    // for one (8192 channels: 2.01 ms unsliced, 2.20 sliced) -- unless the two run on DISJOINT SMs: with an SM partition
+    // (green contexts: the front on the SMs its lone warps fill, the tail on the rest) 4096 channels go from 1.95 to 1.58 ms.
+    // At 8192 channels the front needs 128 SMs and 20 are too few for the tail to keep up (1.99 ms): no slices there.
     int cmax = 1024;
     if (const char *e = getenv("LQB_TIMEPIPE_MAX")) cmax = atoi(e);                    // tuning override
-    if (C > cmax || n < 16384 || (n & 1) || (((size_t)x) & 15) || !lanes_per_channel(segs[0].mask, segs[0].nsos, C)) return 0;
+    if (C > cmax && !timepipe_partition(c, segs, C)) return 0;
     int k = 6;
     if (const char *e = getenv("LQB_TIMEPIPE_SLICES")) { const int v = atoi(e); if (v >= 2 && v <= 64) k = v; }
     return k;
@@ -1237,14 +1312,19 @@ static int run_timepipe(lqb_chain_s *c, const std::vector<Segment> &segs, const 
         LQB_CUDA(cudaStreamCreateWithPriority(&c->front_stream, cudaStreamNonBlocking, hi));
         LQB_CUDA(cudaStreamCreateWithPriority(&c->pipe_stream, cudaStreamNonBlocking, lo));
     }
-    while (c->ev_pipe.size() < (size_t)K + 3) { cudaEvent_t e; LQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_pipe.push_back(e); }
+    while (c->ev_pipe.size() < (size_t)2 * K + 3) { cudaEvent_t e; LQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_pipe.push_back(e); }
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
-    cudaStream_t fs = c->front_stream, ts = c->pipe_stream;
+    cudaStream_t fs = c->front_stream, ts = c->pipe_stream, ta = nullptr;      // (ta: the gain loop's stream inside an SM partition)
     if (getenv("LQB_TIMEPIPE_SERIAL")) ts = fs;                         // A/B: the slices alone, nothing concurrent
+    // SM partition: the front on the SMs its warps fill (four lone warps per SM), the tail on the others
+    bool parted = false;
+    if (SmPartition *sp = timepipe_partition(c, segs, C)) { fs = sp->front; ts = sp->tail; ta = sp->tail2; parted = true; }
+    struct Flag { bool on; Flag(bool v) : on(v) { if (on) t_no_tail_ahead = true; } ~Flag() { if (on) t_no_tail_ahead = false; } } flag(parted);
     // both follow everything already queued on the caller's stream
     LQB_CUDA(cudaEventRecord(c->ev_pipe[K], stream));
     LQB_CUDA(cudaStreamWaitEvent(fs, c->ev_pipe[K], 0));
     LQB_CUDA(cudaStreamWaitEvent(ts, c->ev_pipe[K], 0));
+    if (ta) LQB_CUDA(cudaStreamWaitEvent(ta, c->ev_pipe[K], 0));
     if (timed && c->timed_calls.size() < 1024) {
         evs.resize(2);
         for (auto &p : evs) { LQB_CUDA(cudaEventCreate(&p.first)); LQB_CUDA(cudaEventCreate(&p.second)); }
@@ -1278,8 +1358,18 @@ static int run_timepipe(lqb_chain_s *c, const std::vector<Segment> &segs, const 
         LQB_CUDA(cudaEventRecord(c->ev_pipe[j], fs));
         LQB_CUDA(cudaStreamWaitEvent(ts, c->ev_pipe[j], 0));
         SegIO tio; tio.out_pitch = on_total;
-        if (on > 0 || on0 > 0)
+        if (on > 0 || on0 > 0) {
+            if (parted && ta) {
+                // three stages: front | gain loop | demodulator, the last two on two streams of the tail's SMs
+                LQB_CUDA(cudaStreamWaitEvent(ta, c->ev_pipe[j], 0));
+                tio.tail_part = 1;
+                LQB_TRY(run_segment(segs[1], hand, (char *)y + off * 4, on0, on, 0, C, ta, true, false, &c->last_launches, 0u, 3, j == 0 ? &c->last_kernels : nullptr, tio));
+                LQB_CUDA(cudaEventRecord(c->ev_pipe[K + 3 + j], ta));
+                LQB_CUDA(cudaStreamWaitEvent(ts, c->ev_pipe[K + 3 + j], 0));
+                tio.tail_part = 2;
+            }
             LQB_TRY(run_segment(segs[1], hand, (char *)y + off * 4, on0, on, 0, C, ts, true, false, &c->last_launches, 0u, 3, j == 0 ? &c->last_kernels : nullptr, tio));
+        }
         advance_all(c, ns);
         off += on;
     }
@@ -1296,7 +1386,7 @@ static int run_timepipe(lqb_chain_s *c, const std::vector<Segment> &segs, const 
     }
     LQB_CUDA(cudaStreamWaitEvent(stream, c->ev_pipe[K + 1], 0));
     LQB_CUDA(cudaStreamWaitEvent(stream, c->ev_pipe[K + 2], 0));
-    note_kernel(&c->last_kernels, "(x" + std::to_string(j) + " time slices, tail on its own stream)");
+    note_kernel(&c->last_kernels, "(x" + std::to_string(j) + " time slices, tail on its own stream" + (parted ? std::string(", front and tail on disjoint SMs") : std::string()) + ")");
     return LQB_OK;
 }
 
