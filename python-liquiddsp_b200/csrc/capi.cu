@@ -628,7 +628,6 @@ struct lqb_chain_s {
     unsigned ov_calls = 0;
     // few channels (run_timepipe): the decimated-rate tail of time slice j runs on pipe_stream while the front works on slice j + 1
     cudaStream_t pipe_stream = nullptr, front_stream = nullptr;
-    std::map<int, lqb::SmPartition> sm_parts;       // SM partitions by front size (created once, kept for the chain's life)
     std::vector<cudaEvent_t> ev_pipe;
     // optional per-segment timing of execute_dev: one event pair per segment per call, on the stream the segment ran on
     bool timing = false;
@@ -1274,13 +1273,18 @@ static int partition_front_sms(const std::vector<Segment> &segs, int C)
     const long long want = ((warps + 3) / 4 + 7) / 8 * 8;
     return (want >= 8 && want <= 100) ? (int)want : 0;                                 // (at least 48 SMs stay for the tail)
 }
-static SmPartition *timepipe_partition(lqb_chain_s *c, const std::vector<Segment> &segs, int C)
+static SmPartition *timepipe_partition(lqb_chain_s *, const std::vector<Segment> &segs, int C)
 {
     if (getenv("LQB_NO_PARTITION")) return nullptr;
     const int want = partition_front_sms(segs, C);
     if (!want) return nullptr;
-    SmPartition &sp = c->sm_parts[want];
-    if (!sp.ok && !sp.ga) sm_partition_create(sp, want);           // (tried once per chain and size)
+    // one partition per device and front size for the whole process (green contexts are not free, and chains come and go):
+    // chains that share one only share its streams' order
+    static std::mutex mu; static std::map<std::pair<int, int>, SmPartition> parts;
+    int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    SmPartition &sp = parts[std::make_pair(dev, want)];
+    if (!sp.ok && !sp.ga) sm_partition_create(sp, want);           // (tried once per device and size)
     return sp.ok ? &sp : nullptr;
 }
 static int timepipe_slices(lqb_chain_s *c, const std::vector<Segment> &segs, const void *x, size_t n, int C, bool in_i16)
