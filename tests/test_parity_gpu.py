@@ -999,6 +999,43 @@ def test_amtail_eight_lane_kernel_equals_thread_per_channel(cuda, monkeypatch):
     assert np.array_equal(words[0][0], words[1][0]) and np.array_equal(words[0][1], words[1][1])
 
 
+@pytest.mark.parametrize("C", [5, 300, 2500])
+def test_time_slices_on_disjoint_sms_equal_plain_call(cuda, monkeypatch, C):
+    """Up to 6400 channels a long call is cut into six time slices: the front of slice j + 1 runs on the SMs its lone warps fill,
+    gain loop and demodulator of slice j on the others (capi.cu run_timepipe, green-context SM partition; ordinary streams for
+    <= 1024 channels when the driver lacks the API).  State carries between slices as between calls: bit-identical to the
+    unsliced call (LQB_NO_TIMEPIPE=1) and, with LQB_NO_PARTITION=1, to the slices on shared SMs; carried over a second call.
+    Device-pointer calls (large host-pointer calls take the host path's own time slices instead)."""
+    n1, n2 = 32768, 4098
+    base = np.stack([am_iq(n1 + n2, seed=40 + c, f_off=100.0 + 3 * c) for c in range(min(C, 125))])
+    x = np.tile(base, ((C + base.shape[0] - 1) // base.shape[0], 1))[:C]          # (2500 channels: 125 signals, twenty times)
+    parts = [np.ascontiguousarray(x[:, :n1]), np.ascontiguousarray(x[:, n1:])]
+    xb = [L.DeviceBuffer(p.nbytes) for p in parts]
+    for b, p in zip(xb, parts):
+        b.upload(p.view(np.uint8).ravel())
+    outs, notes = [], []
+    for env in ({"LQB_NO_TIMEPIPE": "1"}, {}, {"LQB_NO_PARTITION": "1", "LQB_TIMEPIPE_MAX": "100000"}):
+        for k in ("LQB_NO_TIMEPIPE", "LQB_NO_PARTITION", "LQB_TIMEPIPE_MAX"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = _Radio(L, channels=C); ch = L.Chain(*r.stages())
+        ys = []
+        for b, nn in zip(xb, (n1, n2)):
+            cap = ch.out_len(nn)
+            yb = L.DeviceBuffer(max(16, C * cap * 4))
+            got = ch.execute_dev(b.ptr.value, nn, yb.ptr.value, cap, 0); L.synchronize()
+            assert got == cap
+            if nn == n1:
+                notes.append(ch.last_kernels()[-1])
+            ys.append(yb.download((C, cap), np.float32))
+        outs.append(np.concatenate(ys, axis=1))
+    assert "time slices" not in notes[0] and "time slices" in notes[2] and "disjoint" not in notes[2], notes
+    assert "time slices" in notes[1] or C > 1024, notes      # (above 1024 channels the default slices only with an SM partition)
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    assert np.array_equal(outs[0].view(np.uint32), outs[2].view(np.uint32))
+
+
 def test_pageable_input_staged_by_host_threads(cuda, monkeypatch):
     """A plain numpy array is pageable memory; the time-sliced host path copies it through pinned bounce buffers with a few host
     threads (capi.cu staged_h2d) instead of leaving it to the driver's single-threaded staging.  Same bytes reach the device:
